@@ -1,0 +1,1255 @@
+// dslam_api.cu — sessions, frame pyramids and the tracker object behind the C ABI of include/dslam_b200.h.
+//
+// Host side of the photometric Gauss-Newton path.  What stays on the host is exactly what the north star
+// leaves there: the Levenberg-Marquardt control flow of TrackerAndScaler::trackNewestCoarse
+// (src/scale_optimization/TrackerAndScaler.cpp:451-638) and ::optimizeScale (:854-964), the damped 8x8 solve
+// and the SE3 update.  Everything per-point runs in the fused kernels of kernels_residual.cu; a Levenberg-
+// Marquardt round is ONE kernel launch whose result lands in mapped pinned memory (no memcpy, no stream
+// synchronise), and several independent starts (pose hypotheses, scale seeds) advance in lock step inside the
+// same launch.
+//
+// There is no CPU fallback in this file: without a CUDA device every entry point fails with DSLAM_ENODEVICE.
+
+#include <cmath>
+#include <new>
+
+#include "dslam_internal.h"
+
+namespace dslam {
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError) return DSLAM_ENODEVICE;
+  if (e == cudaErrorMemoryAllocation) return DSLAM_ENOMEM;
+  return DSLAM_ECUDA;
+}
+
+namespace {
+
+constexpr float kCoarseCutoffTH = 20.0f;  // setting_coarseCutoffTH  deps:dso/src/util/settings.cpp:138
+constexpr float kHuberTH = 9.0f;          // setting_huberTH         deps:dso/src/util/settings.cpp:127
+constexpr double kScaleXiRot = 1.0, kScaleXiTrans = 0.5, kScaleA = 10.0, kScaleB = 1000.0;  // HessianBlocks.h:59-65
+const int kMaxIterations[dslam::kMaxLevels] = {10, 20, 50, 50, 50, 50};  // :463 (+50 for an optional 6th level)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// driver entry point for tensor maps (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// evaluation plumbing
+// ---------------------------------------------------------------------------------------------------
+struct EvalOut {           // one calcRes* + calcGSSSE* evaluation, host view
+  double acc[kPoseVals];   // raw sums
+  int nE, nSat, nInl;
+  int n_padded;            // pose_buf_warped_n_ / scale_buf_warped_n_
+  double res6[6];          // the Vec6 of calcResPose / calcResScale
+};
+
+int choose_blocks(int n, int nitems, int num_sms) {
+  int per = (n + kEvalThreads - 1) / kEvalThreads;  // one template point per thread: shortest critical path
+  if (per < 1) per = 1;
+  const long budget = (long)num_sms * 6;            // resident CTAs worth ~2 waves when many items share a launch
+  if ((long)per * nitems > budget) {
+    per = (int)(budget / nitems);
+    if (per < 1) per = 1;
+  }
+  if (per > kMaxBlocksPerItem) per = kMaxBlocksPerItem;
+  return per;
+}
+
+// Launch `n` prepared items (any count up to kResultSlots) and wait for their result records.
+int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vector<EvalOut> &outs, long long *launch_counter) {
+  const int n = (int)items.size();
+  if (n < 1) return DSLAM_OK;
+  if (n > kResultSlots) return fail(DSLAM_EINVAL, "too many evaluation items in one round (%d > %d)", n, kResultSlots);
+  const unsigned seq = ++s->seq;
+  EvalBatch batch;
+  for (int base = 0; base < n; base += kMaxItemsPerLaunch) {
+    const int cnt = n - base < kMaxItemsPerLaunch ? n - base : kMaxItemsPerLaunch;
+    int gx = 1;
+    for (int i = 0; i < cnt; i++) {
+      EvalItem &it = items[base + i];
+      it.nblocks = choose_blocks(it.n, n, s->num_sms);
+      it.ppt_stride = it.nblocks * kEvalThreads;
+      if (it.nblocks > gx) gx = it.nblocks;
+      batch.item[i] = it;
+    }
+    long long pts = 0;
+    for (int i = 0; i < cnt; i++) pts += batch.item[i].n;
+    const bool prof = s->prof_on;
+    size_t slot = 0;
+    if (prof) {
+      slot = s->prof_used++;
+      while (s->prof_ev.size() < 2 * (slot + 1)) {
+        cudaEvent_t e;
+        DSLAM_CUDA(cudaEventCreate(&e));
+        s->prof_ev.push_back(e);
+      }
+      if (s->prof_mode.size() <= slot) { s->prof_mode.resize(slot + 1); s->prof_points.resize(slot + 1); }
+      s->prof_mode[slot] = mode;
+      s->prof_points[slot] = pts;
+      DSLAM_CUDA(cudaEventRecord(s->prof_ev[2 * slot], s->stream));
+    }
+    DSLAM_CUDA(launch_eval(mode, batch, cnt, gx, s->scratch, s->results_dev + base, seq, s->stream));
+    if (prof) DSLAM_CUDA(cudaEventRecord(s->prof_ev[2 * slot + 1], s->stream));
+    s->launches++;
+    if (launch_counter) (*launch_counter)++;
+  }
+  // The last CTA of every item writes its record into mapped pinned memory and then the sequence number.
+  outs.resize(n);
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  for (int i = 0; i < n; i++) {
+    volatile dslam::EvalResult *r = s->results_host + i;
+    while (r->seq != seq) {
+      if ((++spins & 0x3fff) == 0) {
+        const cudaError_t q = cudaStreamQuery(s->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "evaluation kernel");
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > s->timeout_s) return fail(DSLAM_ETIMEOUT, "evaluation kernel did not publish its result within %.1f s", s->timeout_s);
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    EvalOut &o = outs[i];
+    const int nv = mode == 0 ? kPoseVals : kScaleVals;
+    for (int k = 0; k < nv; k++) o.acc[k] = r->acc[k];
+    o.nE = r->counts[0];
+    o.nSat = r->counts[1];
+    o.nInl = r->counts[2];
+    o.n_padded = (o.nInl + 3) & ~3;  // zero padding to a multiple of 4  (:824-835, :1147-1158)
+    const EvalItem &it = items[i];
+    const int iE = mode == 0 ? 45 : 3, iT = mode == 0 ? 46 : 4, iRT = mode == 0 ? 47 : 5;
+    const float shiftNum = (it.flags & 1) ? 2.0f * (float)((it.n + 31) / 32) : 0.0f;  // sumSquaredShiftNum
+    o.res6[0] = o.acc[iE];
+    o.res6[1] = o.nE;
+    o.res6[2] = o.acc[iT] / (shiftNum + 0.1);
+    o.res6[3] = 0;
+    o.res6[4] = o.acc[iRT] / (shiftNum + 0.1);
+    o.res6[5] = o.nSat / (float)o.nE;  // :851 float division
+  }
+  return DSLAM_OK;
+}
+
+void fill_common(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, int lvl, float cutoff) {
+  it.tex = f->L.tex[lvl];
+  it.pts = c->pts[lvl];
+  it.n = c->pc_n[lvl];
+  it.w = c->w[lvl];
+  it.h = c->h[lvl];
+  it.flags = lvl == 0 ? 1 : 0;
+  for (int k = 0; k < 9; k++) it.Ki[k] = c->Ki[lvl][k];
+  it.cutoff = cutoff;
+  it.maxEnergy = 2 * kHuberTH * cutoff - kHuberTH * kHuberTH;  // :726-728
+  it.nblocks = 1;
+  it.ppt_stride = kEvalThreads;
+  it.pad_ = 0;
+}
+
+// calcResPose prologue :711-720
+void fill_pose_item(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, float new_exposure, int lvl, const hm::Se3 &refToNew,
+                    const double aff[2], float cutoff) {
+  fill_common(it, c, f, lvl, cutoff);
+  it.fx = c->cam0.fx[lvl]; it.fy = c->cam0.fy[lvl]; it.cx = c->cam0.cx[lvl]; it.cy = c->cam0.cy[lvl];
+  double Rd[9];
+  hm::qmatrix(refToNew.q, Rd);
+  float Rf[9];
+  for (int k = 0; k < 9; k++) Rf[k] = (float)Rd[k];
+  hm::mat33f_mul(Rf, c->Ki[lvl], it.M);
+  for (int k = 0; k < 3; k++) it.t[k] = (float)refToNew.t[k];
+  double affd[2];
+  hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], affd);
+  it.p0 = (float)affd[0];
+  it.p1 = (float)affd[1];
+  it.p2 = (float)c->ref_b;  // b0 of calcGSSSEPose :649
+}
+
+// calcResScale prologue :1019-1027
+void fill_scale_item(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, int lvl, float scale, float cutoff) {
+  fill_common(it, c, f, lvl, cutoff);
+  it.fx = c->cam1.fx[lvl]; it.fy = c->cam1.fy[lvl]; it.cx = c->cam1.cx[lvl]; it.cy = c->cam1.cy[lvl];
+  for (int k = 0; k < 9; k++) it.M[k] = c->M_stereo[lvl][k];
+  for (int k = 0; k < 3; k++) it.t[k] = (float)c->T_f1_f0.t[k];
+  it.p0 = scale;
+  it.p1 = it.p2 = 0.f;
+}
+
+// calcGSSSEPose epilogue :682-696 from the raw sums
+void pose_normal_equations(const EvalOut &o, double H[64], double b[8]) {
+  const float invn = 1.0f / o.n_padded;
+  double Hf[81];
+  int e = 0;
+  for (int r = 0; r < 9; r++)
+    for (int cc = r; cc < 9; cc++, e++) Hf[r * 9 + cc] = Hf[cc * 9 + r] = o.acc[e];
+  for (int r = 0; r < 8; r++) {
+    for (int cc = 0; cc < 8; cc++) H[r * 8 + cc] = Hf[r * 9 + cc] * invn;
+    b[r] = Hf[r * 9 + 8] * invn;
+  }
+  const double sc[8] = {kScaleXiRot, kScaleXiRot, kScaleXiRot, kScaleXiTrans, kScaleXiTrans, kScaleXiTrans, kScaleA, kScaleB};
+  for (int r = 0; r < 8; r++)
+    for (int cc = 0; cc < 8; cc++) H[r * 8 + cc] *= sc[cc];
+  for (int r = 0; r < 8; r++)
+    for (int cc = 0; cc < 8; cc++) H[r * 8 + cc] *= sc[r];
+  for (int r = 0; r < 8; r++) b[r] *= sc[r];
+}
+
+// calcGSSSEScale epilogue :1003-1004 (hessian_ is a float matrix)
+void scale_normal_equations(const EvalOut &o, float *H, float *b) {
+  const float invn = 1.0f / o.n_padded;
+  *H = (float)o.acc[0] * invn;
+  *b = (float)o.acc[1] * invn;
+}
+
+void trace_row(std::vector<double> *tr, int lvl, int it, int accept, int n, double lambda, double e_old, double e_new, const double *inc,
+               int ninc) {
+  if (!tr) return;
+  const size_t o = tr->size();
+  tr->resize(o + 15, 0.0);
+  double *r = tr->data() + o;
+  r[0] = lvl; r[1] = it; r[2] = accept; r[3] = n; r[4] = lambda; r[5] = e_old; r[6] = e_new;
+  for (int k = 0; k < ninc && k < 8; k++) r[7 + k] = inc[k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trackNewestCoarse as a resumable state machine: request() says which evaluation it needs next, consume()
+// advances with the result.  Several machines run in lock step (one launch per round for all of them).
+// ---------------------------------------------------------------------------------------------------
+struct PoseLM {
+  // configuration
+  const dslam_ctx *c = nullptr;
+  const dslam_frame *f = nullptr;
+  float new_exposure = 1.f;
+  double minResForAbort[5]{};
+  std::vector<double> *trace = nullptr;
+  // state
+  enum Phase { START, ITER, DONE } phase = START;
+  hm::Se3 cur, cand;
+  double aff_cur[2]{}, aff_cand[2]{};
+  int lvl = 0, iteration = 0;
+  bool haveRepeated = false;
+  float levelCutoffRepeat = 1, lambda = 0.01f;
+  double H[64]{}, b[8]{}, inc[8]{};
+  EvalOut resOld{};
+  // outputs
+  bool ok = false;
+  double lastResiduals[5]{};
+  double flow[3]{};
+  long long iters = 0;
+
+  void begin(const dslam_ctx *c_, const dslam_frame *f_, float exposure, const double pose7[7], const double aff[2], int coarsestLvl,
+             const double minRes[5], std::vector<double> *tr) {
+    c = c_; f = f_; new_exposure = exposure; trace = tr;
+    cur = hm::Se3::from7(pose7);
+    aff_cur[0] = aff[0]; aff_cur[1] = aff[1];
+    for (int i = 0; i < 5; i++) { lastResiduals[i] = NAN; minResForAbort[i] = minRes[i]; }
+    flow[0] = flow[1] = flow[2] = 1000;  // lastFlowIndicators.setConstant(1000)  :460
+    lvl = coarsestLvl;
+    haveRepeated = false;
+    start_level();
+  }
+  void start_level() {
+    levelCutoffRepeat = 1;
+    phase = START;
+  }
+  void request(EvalItem &it) const {
+    const float cutoff = kCoarseCutoffTH * levelCutoffRepeat;
+    if (phase == START) fill_pose_item(it, c, f, new_exposure, lvl, cur, aff_cur, cutoff);
+    else fill_pose_item(it, c, f, new_exposure, lvl, cand, aff_cand, cutoff);
+  }
+  void consume(const EvalOut &o) {
+    if (phase == START) {
+      resOld = o;
+      if (resOld.res6[5] > 0.6 && levelCutoffRepeat < 50) {  // :475-485
+        levelCutoffRepeat *= 2;
+        return;
+      }
+      pose_normal_equations(o, H, b);  // :487
+      lambda = 0.01f;
+      iteration = 0;
+      trace_row(trace, lvl, -1, 1, o.n_padded, lambda, 0.0, resOld.res6[0] / resOld.res6[1], nullptr, 0);
+      prepare_iteration();
+      return;
+    }
+    // ITER: resNew = o
+    iters++;
+    const bool accept = (o.res6[0] / o.res6[1]) < (resOld.res6[0] / resOld.res6[1]);  // :559
+    trace_row(trace, lvl, iteration, accept, o.n_padded, lambda, resOld.res6[0] / resOld.res6[1], o.res6[0] / o.res6[1], inc, 8);
+    if (accept) {  // :576-582
+      pose_normal_equations(o, H, b);
+      resOld = o;
+      aff_cur[0] = aff_cand[0]; aff_cur[1] = aff_cand[1];
+      cur = cand;
+      lambda *= 0.5;
+    } else {
+      lambda *= 4;
+      if (lambda < 0.001f) lambda = 0.001f;
+    }
+    double nrm = 0;
+    for (int i = 0; i < 8; i++) nrm += inc[i] * inc[i];
+    nrm = std::sqrt(nrm);
+    if (!(nrm > 1e-3)) {  // :588
+      finish_level();
+      return;
+    }
+    iteration++;
+    prepare_iteration();
+  }
+  void prepare_iteration() {
+    if (iteration >= kMaxIterations[lvl]) {
+      finish_level();
+      return;
+    }
+    const float lambdaExtrapolationLimit = 0.001f;
+    double Hl[64];
+    std::memcpy(Hl, H, sizeof(Hl));
+    for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + lambda);
+    double nb[8];
+    for (int i = 0; i < 8; i++) nb[i] = -b[i];
+    hm::ldlt_solve(8, Hl, 8, nb, inc);  // :509
+    const int mA = c->affModeA, mB = c->affModeB;
+    if (mA < 0 && mB < 0) {  // fix a, b  :511-515
+      hm::ldlt_solve(6, Hl, 8, nb, inc);
+      inc[6] = inc[7] = 0;
+    }
+    if (!(mA < 0) && mB < 0) {  // fix b  :516-520
+      hm::ldlt_solve(7, Hl, 8, nb, inc);
+      inc[7] = 0;
+    }
+    if (mA < 0 && !(mB < 0)) {  // fix a  :521-534
+      double Hs[64], bs[8], is[8];
+      std::memcpy(Hs, Hl, sizeof(Hs));
+      std::memcpy(bs, nb, sizeof(bs));
+      for (int i = 0; i < 8; i++) Hs[i * 8 + 6] = Hs[i * 8 + 7];
+      for (int j = 0; j < 8; j++) Hs[6 * 8 + j] = Hs[7 * 8 + j];
+      bs[6] = bs[7];
+      hm::ldlt_solve(7, Hs, 8, bs, is);
+      for (int i = 0; i < 6; i++) inc[i] = is[i];
+      inc[6] = 0;
+      inc[7] = is[6];
+    }
+    float extrapFac = 1;
+    if (lambda < lambdaExtrapolationLimit) extrapFac = std::sqrt(std::sqrt(lambdaExtrapolationLimit / lambda));  // :536-539
+    for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+    double incScaled[8];
+    for (int i = 0; i < 3; i++) incScaled[i] = inc[i] * kScaleXiRot;
+    for (int i = 3; i < 6; i++) incScaled[i] = inc[i] * kScaleXiTrans;
+    incScaled[6] = inc[6] * kScaleA;
+    incScaled[7] = inc[7] * kScaleB;
+    double sum = 0;
+    for (int i = 0; i < 8; i++) sum += incScaled[i];
+    if (!std::isfinite(sum))
+      for (int i = 0; i < 8; i++) incScaled[i] = 0;  // :547-548
+    cand = hm::se3_exp(incScaled) * cur;             // :550-551
+    aff_cand[0] = aff_cur[0] + incScaled[6];
+    aff_cand[1] = aff_cur[1] + incScaled[7];
+    phase = ITER;
+  }
+  void finish_level() {
+    lastResiduals[lvl] = sqrtf((float)(resOld.res6[0] / resOld.res6[1]));  // :595
+    flow[0] = resOld.res6[2]; flow[1] = resOld.res6[3]; flow[2] = resOld.res6[4];
+    if (lastResiduals[lvl] > 1.5 * minResForAbort[lvl]) {  // :597-598
+      ok = false;
+      phase = DONE;
+      return;
+    }
+    if (levelCutoffRepeat > 1 && !haveRepeated) {  // :601-604
+      lvl++;
+      haveRepeated = true;
+    }
+    lvl--;
+    if (lvl >= 0) {
+      start_level();
+      return;
+    }
+    phase = DONE;
+    ok = true;
+  }
+};
+
+struct ScaleLM {
+  const dslam_ctx *c = nullptr;
+  const dslam_frame *f = nullptr;
+  std::vector<double> *trace = nullptr;
+  enum Phase { START, ITER, DONE } phase = START;
+  float scale_current = 1.f, scale_new = 1.f, inc = 0.f;
+  int lvl = 0, iteration = 0;
+  bool haveRepeated = false;
+  float levelCutoffRepeat = 1, lambda = 0.01f, H = 0.f, b = 0.f;
+  EvalOut resOld{};
+  float last_residuals[5]{};
+  long long iters = 0;
+
+  void begin(const dslam_ctx *c_, const dslam_frame *f_, float scale, int coarsestLvl, std::vector<double> *tr) {
+    c = c_; f = f_; trace = tr;
+    scale_current = scale;
+    for (int i = 0; i < 5; i++) last_residuals[i] = NAN;
+    lvl = coarsestLvl;
+    haveRepeated = false;
+    levelCutoffRepeat = 1;
+    phase = START;
+  }
+  void request(EvalItem &it) const {
+    fill_scale_item(it, c, f, lvl, phase == START ? scale_current : scale_new, kCoarseCutoffTH * levelCutoffRepeat);
+  }
+  void consume(const EvalOut &o) {
+    if (phase == START) {
+      resOld = o;
+      if (resOld.res6[5] > 0.6 && levelCutoffRepeat < 50) {  // :873-881
+        levelCutoffRepeat *= 2;
+        return;
+      }
+      scale_normal_equations(o, &H, &b);  // :883
+      lambda = 0.01f;
+      iteration = 0;
+      const double t[2] = {0.0, scale_current};
+      trace_row(trace, lvl, -1, 1, o.n_padded, lambda, 0.0, resOld.res6[0] / resOld.res6[1], t, 2);
+      prepare_iteration();
+      return;
+    }
+    iters++;
+    const bool accept = (o.res6[0] / o.res6[1]) < (resOld.res6[0] / resOld.res6[1]);  // :915
+    const double t[2] = {inc, scale_new};
+    trace_row(trace, lvl, iteration, accept, o.n_padded, lambda, resOld.res6[0] / resOld.res6[1], o.res6[0] / o.res6[1], t, 2);
+    if (accept) {  // :926-936
+      scale_normal_equations(o, &H, &b);
+      resOld = o;
+      scale_current = scale_new;
+      lambda *= 0.5;
+    } else {
+      lambda *= 4;
+      if (lambda < 0.001f) lambda = 0.001f;
+    }
+    if (!(inc > 1e-3)) {  // :937 (signed: any non-positive step ends the level)
+      finish_level();
+      return;
+    }
+    iteration++;
+    prepare_iteration();
+  }
+  void prepare_iteration() {
+    if (iteration >= kMaxIterations[lvl]) {
+      finish_level();
+      return;
+    }
+    const float lambdaExtrapolationLimit = 0.001f;
+    float Hl = H;
+    Hl *= (1 + lambda);
+    inc = -b / Hl;  // :898-900
+    float extrapFac = 1;
+    if (lambda < lambdaExtrapolationLimit) extrapFac = std::sqrt(std::sqrt(lambdaExtrapolationLimit / lambda));
+    inc *= extrapFac;
+    if (!std::isfinite(inc) || std::fabs(inc) > scale_current) inc = 0.0;  // :907
+    scale_new = scale_current + inc;
+    phase = ITER;
+  }
+  void finish_level() {
+    last_residuals[lvl] = sqrtf((float)(resOld.res6[0] / resOld.res6[1]));  // :946
+    if (levelCutoffRepeat > 1 && !haveRepeated) {
+      lvl++;
+      haveRepeated = true;
+    }
+    lvl--;
+    if (lvl >= 0) {
+      levelCutoffRepeat = 1;
+      phase = START;
+      return;
+    }
+    phase = DONE;
+  }
+};
+
+template <class LM>
+int run_lock_step(dslam_session *s, int mode, std::vector<LM> &lms, dslam_ctx *counters) {
+  std::vector<EvalItem> items;
+  std::vector<EvalOut> outs;
+  std::vector<int> who;
+  for (;;) {
+    items.clear();
+    who.clear();
+    for (size_t i = 0; i < lms.size(); i++)
+      if (lms[i].phase != LM::DONE) {
+        items.emplace_back();
+        lms[i].request(items.back());
+        who.push_back((int)i);
+      }
+    if (items.empty()) break;
+    const int rc = run_items(s, mode, items, outs, counters ? &counters->n_launches : nullptr);
+    if (rc != DSLAM_OK) return rc;
+    if (counters) counters->n_evals += (long long)items.size();
+    for (size_t k = 0; k < who.size(); k++) lms[who[k]].consume(outs[k]);
+  }
+  return DSLAM_OK;
+}
+
+int check_ctx_frame(const dslam_ctx *c, const dslam_frame *f, int coarsestLvl) {
+  if (!c || !f) return fail(DSLAM_EINVAL, "null context or frame");
+  if (c->s != f->s) return fail(DSLAM_EINVAL, "context and frame belong to different sessions");
+  if (!c->have_ref) return fail(DSLAM_ESTATE, "no tracking reference uploaded (dslam_ref_upload / dslam_ref_build)");
+  if (!f->built) return fail(DSLAM_ESTATE, "frame pyramid has not been built");
+  if (f->w != c->w[0] || f->h != c->h[0] || f->levels < c->levels) return fail(DSLAM_EINVAL, "frame geometry does not match the context");
+  if (coarsestLvl < 0 || coarsestLvl >= c->levels || coarsestLvl >= 5) return fail(DSLAM_EINVAL, "coarsestLvl %d out of range", coarsestLvl);
+  return DSLAM_OK;
+}
+
+}  // namespace
+}  // namespace dslam
+
+using namespace dslam;
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+int dslam_version(void) { return 100; }
+const char *dslam_last_error(void) { return dslam::g_err; }
+
+int dslam_device_count(int *count) {
+  if (!count) return fail(DSLAM_EINVAL, "null argument");
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cuda_fail(e, "cudaGetDeviceCount");
+  }
+  *count = n;
+  return DSLAM_OK;
+}
+
+// ---- sessions ------------------------------------------------------------------------------------
+int dslam_session_create(int device, dslam_session **out) {
+  if (!out) return fail(DSLAM_EINVAL, "null argument");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (n < 1) return fail(DSLAM_ENODEVICE, "no CUDA device");
+  if (device < 0 || device >= n) return fail(DSLAM_EINVAL, "device %d out of range (%d devices)", device, n);
+  DSLAM_CUDA(cudaSetDevice(device));
+  dslam_session *s = new (std::nothrow) dslam_session();
+  if (!s) return fail(DSLAM_ENOMEM, "out of host memory");
+  s->device = device;
+  cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (s->num_sms <= 0) s->num_sms = 148;
+  DSLAM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  DSLAM_CUDA(cudaHostAlloc((void **)&s->results_host, sizeof(EvalResult) * kResultSlots, cudaHostAllocMapped));
+  std::memset(s->results_host, 0, sizeof(EvalResult) * kResultSlots);
+  DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->results_dev, s->results_host, 0));
+  DSLAM_CUDA(cudaMalloc((void **)&s->scratch.partials, sizeof(double) * kMaxItemsPerLaunch * kMaxBlocksPerItem * kPoseVals));
+  DSLAM_CUDA(cudaMalloc((void **)&s->scratch.counters, sizeof(int) * kMaxItemsPerLaunch * 4));
+  DSLAM_CUDA(cudaMemsetAsync(s->scratch.counters, 0, sizeof(int) * kMaxItemsPerLaunch * 4, s->stream));
+  DSLAM_CUDA(cudaEventCreate(&s->mark[0]));
+  DSLAM_CUDA(cudaEventCreate(&s->mark[1]));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return DSLAM_OK;
+}
+
+int dslam_session_destroy(dslam_session *s) {
+  if (!s) return DSLAM_OK;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  cudaFree(s->scratch.partials);
+  cudaFree(s->scratch.counters);
+  cudaFreeHost(s->results_host);
+  cudaEventDestroy(s->mark[0]);
+  cudaEventDestroy(s->mark[1]);
+  for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(s->stream);
+  delete s;
+  return DSLAM_OK;
+}
+
+int dslam_session_sync(dslam_session *s) {
+  if (!s) return fail(DSLAM_EINVAL, "null session");
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  return DSLAM_OK;
+}
+
+int dslam_session_stream(dslam_session *s, void **cuda_stream_out) {
+  if (!s || !cuda_stream_out) return fail(DSLAM_EINVAL, "null argument");
+  *cuda_stream_out = (void *)s->stream;
+  return DSLAM_OK;
+}
+
+int dslam_session_launch_count(dslam_session *s, long long *count) {
+  if (!s || !count) return fail(DSLAM_EINVAL, "null argument");
+  *count = s->launches;
+  return DSLAM_OK;
+}
+
+int dslam_session_mark(dslam_session *s, int which) {
+  if (!s || which < 0 || which > 1) return fail(DSLAM_EINVAL, "bad argument");
+  DSLAM_CUDA(cudaEventRecord(s->mark[which], s->stream));
+  return DSLAM_OK;
+}
+
+int dslam_session_elapsed_ms(dslam_session *s, float *ms) {
+  if (!s || !ms) return fail(DSLAM_EINVAL, "null argument");
+  DSLAM_CUDA(cudaEventSynchronize(s->mark[1]));
+  DSLAM_CUDA(cudaEventElapsedTime(ms, s->mark[0], s->mark[1]));
+  return DSLAM_OK;
+}
+
+int dslam_session_profile(dslam_session *s, int enable) {
+  if (!s) return fail(DSLAM_EINVAL, "null session");
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  s->prof_on = enable != 0;
+  s->prof_used = 0;
+  return DSLAM_OK;
+}
+
+int dslam_session_profile_read(dslam_session *s, double out[8]) {
+  if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  for (size_t k = 0; k < s->prof_used; k++) {
+    float ms = 0;
+    DSLAM_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * k], s->prof_ev[2 * k + 1]));
+    const int m = s->prof_mode[k] ? 4 : 0;
+    out[m + 0] += 1;
+    out[m + 1] += ms;
+    out[m + 2] += (double)s->prof_points[k];
+    if (ms > out[m + 3]) out[m + 3] = ms;
+  }
+  s->prof_used = 0;
+  return DSLAM_OK;
+}
+
+int dslam_host_alloc(unsigned long long bytes, void **out) {
+  if (!out) return fail(DSLAM_EINVAL, "null argument");
+  DSLAM_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return DSLAM_OK;
+}
+int dslam_host_free(void *p) {
+  if (p) DSLAM_CUDA(cudaFreeHost(p));
+  return DSLAM_OK;
+}
+
+// ---- frames --------------------------------------------------------------------------------------
+int dslam_frame_create(dslam_session *s, int w, int h, int levels, dslam_frame **out) {
+  if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
+  *out = nullptr;
+  if (w < 8 || h < 8 || levels < 1 || levels > DSLAM_MAX_LEVELS || (w >> (levels - 1)) < 1 || (h >> (levels - 1)) < 1)
+    return fail(DSLAM_EINVAL, "bad pyramid geometry %dx%d, %d levels", w, h, levels);
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(DSLAM_ENODEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  dslam_frame *f = new (std::nothrow) dslam_frame();
+  if (!f) return fail(DSLAM_ENOMEM, "out of host memory");
+  f->s = s; f->w = w; f->h = h; f->levels = levels;
+  PyramidLevels &L = f->L;
+  L.levels = levels;
+  size_t bytes = 0, plane_off[kMaxLevels], tex_off[kMaxLevels];
+  f->px_off[0] = 0;
+  int tiles = 0;
+  for (int l = 0; l < levels; l++) {
+    L.w[l] = w >> l;
+    L.h[l] = h >> l;
+    L.pitch[l] = (int)align_up((size_t)L.w[l], 4);
+    plane_off[l] = bytes;
+    bytes = align_up(bytes + (size_t)L.pitch[l] * L.h[l] * sizeof(float), 256);
+    tex_off[l] = bytes;
+    bytes = align_up(bytes + (size_t)L.w[l] * L.h[l] * sizeof(float4), 256);
+    f->px_off[l + 1] = f->px_off[l] + (size_t)L.w[l] * L.h[l];
+    L.tiles_x[l] = (L.w[l] + kGradTileW - 1) / kGradTileW;
+    L.tile_begin[l] = tiles;
+    tiles += L.tiles_x[l] * ((L.h[l] + kGradTileH - 1) / kGradTileH);
+    L.host_dIp[l] = nullptr;
+    L.host_abs[l] = nullptr;
+  }
+  for (int l = levels; l <= kMaxLevels; l++) L.tile_begin[l] = tiles;
+  cudaError_t e = cudaMalloc(&f->block, bytes);
+  if (e != cudaSuccess) {
+    delete f;
+    return cuda_fail(e, "cudaMalloc(frame)");
+  }
+  for (int l = 0; l < levels; l++) {
+    L.plane[l] = (float *)((char *)f->block + plane_off[l]);
+    L.tex[l] = (float4 *)((char *)f->block + tex_off[l]);
+    const cuuint64_t gdim[2] = {(cuuint64_t)L.w[l], (cuuint64_t)L.h[l]};
+    const cuuint64_t gstride[1] = {(cuuint64_t)L.pitch[l] * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kGradBoxW, (cuuint32_t)kGradBoxH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&f->maps.map[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.plane[l], gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      cudaFree(f->block);
+      delete f;
+      return fail(DSLAM_ECUDA, "cuTensorMapEncodeTiled failed (%d) for level %d", (int)r, l);
+    }
+  }
+  for (int l = levels; l < kMaxLevels; l++) f->maps.map[l] = f->maps.map[0];
+  e = cudaEventCreateWithFlags(&f->host_ready, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    cudaFree(f->block);
+    delete f;
+    return cuda_fail(e, "cudaEventCreate");
+  }
+  *out = f;
+  return DSLAM_OK;
+}
+
+int dslam_frame_destroy(dslam_frame *f) {
+  if (!f) return DSLAM_OK;
+  cudaSetDevice(f->s->device);
+  cudaStreamSynchronize(f->s->stream);
+  cudaFree(f->block);
+  cudaFree(f->stage_dIp);
+  cudaFree(f->stage_abs);
+  cudaFree(f->B_dev);
+  cudaEventDestroy(f->host_ready);
+  delete f;
+  return DSLAM_OK;
+}
+
+int dslam_frame_upload(dslam_frame *f, const float *color) {
+  if (!f || !color) return fail(DSLAM_EINVAL, "null argument");
+  const PyramidLevels &L = f->L;
+  DSLAM_CUDA(cudaMemcpy2DAsync(L.plane[0], (size_t)L.pitch[0] * sizeof(float), color, (size_t)f->w * sizeof(float), (size_t)f->w * sizeof(float),
+                               f->h, cudaMemcpyHostToDevice, f->s->stream));
+  f->uploaded = true;
+  f->built = false;
+  return DSLAM_OK;
+}
+
+static int frame_ensure_staging(dslam_frame *f, bool want_dIp, bool want_abs) {
+  const size_t tot = f->px_off[f->levels];
+  if (want_dIp && !f->stage_dIp) DSLAM_CUDA(cudaMalloc((void **)&f->stage_dIp, tot * 3 * sizeof(float)));
+  if (want_abs && !f->stage_abs) DSLAM_CUDA(cudaMalloc((void **)&f->stage_abs, tot * sizeof(float)));
+  return DSLAM_OK;
+}
+
+static int frame_build_impl(dslam_frame *f, const float *B256, bool stage_dIp, bool stage_abs) {
+  if (!f->uploaded) return fail(DSLAM_ESTATE, "dslam_frame_build before dslam_frame_upload");
+  dslam_session *s = f->s;
+  const float *Bd = nullptr;
+  if (B256) {
+    if (!f->B_dev) DSLAM_CUDA(cudaMalloc((void **)&f->B_dev, 256 * sizeof(float)));
+    DSLAM_CUDA(cudaMemcpyAsync(f->B_dev, B256, 256 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    Bd = f->B_dev;
+  }
+  const int rc = frame_ensure_staging(f, stage_dIp, stage_abs);
+  if (rc != DSLAM_OK) return rc;
+  PyramidLevels L = f->L;
+  for (int l = 0; l < f->levels; l++) {
+    L.host_dIp[l] = stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
+    L.host_abs[l] = stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
+  }
+  if (f->levels > 1) {
+    DSLAM_CUDA(launch_downsample(L, s->stream));
+    s->launches++;
+  }
+  DSLAM_CUDA(launch_gradients(L, f->maps, Bd, s->stream));
+  s->launches++;
+  f->built = true;
+  f->staged = stage_dIp || stage_abs;
+  return DSLAM_OK;
+}
+
+int dslam_frame_build(dslam_frame *f, const float *B256) {
+  if (!f) return fail(DSLAM_EINVAL, "null frame");
+  return frame_build_impl(f, B256, false, false);
+}
+
+static int frame_copy_out(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad) {
+  dslam_session *s = f->s;
+  // contiguous destination (one block for all levels) -> one DMA per array instead of one per level
+  for (int pass = 0; pass < 2; pass++) {
+    float *const *dst = pass == 0 ? host_dIp : host_absgrad;
+    if (!dst) continue;
+    const size_t mul = pass == 0 ? 3 : 1;
+    const float *src = pass == 0 ? f->stage_dIp : f->stage_abs;
+    bool contiguous = true;
+    for (int l = 0; l < f->levels; l++)
+      if (!dst[l] || dst[l] != dst[0] + mul * f->px_off[l]) contiguous = false;
+    if (contiguous) {
+      DSLAM_CUDA(cudaMemcpyAsync(dst[0], src, mul * f->px_off[f->levels] * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    } else {
+      for (int l = 0; l < f->levels; l++)
+        if (dst[l])
+          DSLAM_CUDA(cudaMemcpyAsync(dst[l], src + mul * f->px_off[l], mul * (f->px_off[l + 1] - f->px_off[l]) * sizeof(float),
+                                     cudaMemcpyDeviceToHost, s->stream));
+    }
+  }
+  DSLAM_CUDA(cudaEventRecord(f->host_ready, s->stream));
+  return DSLAM_OK;
+}
+
+int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad) {
+  if (!f) return fail(DSLAM_EINVAL, "null frame");
+  if (!f->built) return fail(DSLAM_ESTATE, "frame pyramid has not been built");
+  if (!host_dIp && !host_absgrad) return DSLAM_OK;
+  const bool need_d = host_dIp != nullptr, need_a = host_absgrad != nullptr;
+  const bool have = f->staged && (!need_d || f->stage_dIp) && (!need_a || f->stage_abs);
+  if (!have) {
+    const int rc = frame_ensure_staging(f, need_d, need_a);
+    if (rc != DSLAM_OK) return rc;
+    PyramidLevels L = f->L;
+    for (int l = 0; l < f->levels; l++) {
+      L.host_dIp[l] = f->stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
+      L.host_abs[l] = f->stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
+    }
+    DSLAM_CUDA(launch_unpack(L, f->s->stream));
+    f->s->launches++;
+    f->staged = true;
+  }
+  return frame_copy_out(f, host_dIp, host_absgrad);
+}
+
+int dslam_frame_wait_host(dslam_frame *f) {
+  if (!f) return fail(DSLAM_EINVAL, "null frame");
+  DSLAM_CUDA(cudaEventSynchronize(f->host_ready));
+  return DSLAM_OK;
+}
+
+int dslam_frame_make_images(dslam_frame *f, const float *color, const float *B256, float *const *host_dIp, float *const *host_absgrad) {
+  int rc = dslam_frame_upload(f, color);
+  if (rc != DSLAM_OK) return rc;
+  rc = frame_build_impl(f, B256, host_dIp != nullptr, host_absgrad != nullptr);
+  if (rc != DSLAM_OK) return rc;
+  if (host_dIp || host_absgrad) return frame_copy_out(f, host_dIp, host_absgrad);
+  DSLAM_CUDA(cudaEventRecord(f->host_ready, f->s->stream));
+  return DSLAM_OK;
+}
+
+// ---- tracker object ----------------------------------------------------------------------------------
+static void ctx_make_K(dslam_ctx *c, const float K0[4]) {
+  c->cam0.set(c->levels, K0[0], K0[1], K0[2], K0[3]);  // makeK :117-141
+  double Rd[9];
+  hm::qmatrix(c->T_f1_f0.q, Rd);
+  float Rf[9];
+  for (int k = 0; k < 9; k++) Rf[k] = (float)Rd[k];
+  for (int l = 0; l < c->levels; l++) {
+    const float K[9] = {c->cam0.fx[l], 0.0f, c->cam0.cx[l], 0.0f, c->cam0.fy[l], c->cam0.cy[l], 0.0f, 0.0f, 1.0f};
+    hm::mat33f_inverse(K, c->Ki[l]);
+    hm::mat33f_mul(Rf, c->Ki[l], c->M_stereo[l]);  // rot_f1_f0_K0_i :1022-1024
+  }
+}
+
+int dslam_ctx_create(dslam_session *s, int w, int h, int levels, const float K0[4], const float K1[4], const double T_f1_f0[16],
+                     dslam_ctx **out) {
+  if (!s || !out || !K0 || !K1 || !T_f1_f0) return fail(DSLAM_EINVAL, "null argument");
+  *out = nullptr;
+  if (w < 8 || h < 8 || levels < 1 || levels > DSLAM_MAX_LEVELS) return fail(DSLAM_EINVAL, "bad geometry");
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  dslam_ctx *c = new (std::nothrow) dslam_ctx();
+  if (!c) return fail(DSLAM_ENOMEM, "out of host memory");
+  c->s = s;
+  c->levels = levels;
+  c->px_off[0] = 0;
+  for (int l = 0; l < levels; l++) {
+    c->w[l] = w >> l;
+    c->h[l] = h >> l;
+    c->px_off[l + 1] = c->px_off[l] + (size_t)c->w[l] * c->h[l];
+  }
+  // SE3(Matrix4d): quaternion from the rotation block, translation from the last column (:82-86)
+  c->T_f1_f0.q = hm::qfrom_matrix(T_f1_f0, 4);
+  c->T_f1_f0.t[0] = T_f1_f0[3]; c->T_f1_f0.t[1] = T_f1_f0[7]; c->T_f1_f0.t[2] = T_f1_f0[11];
+  c->cam1.set(levels, K1[0], K1[1], K1[2], K1[3]);  // :88-98
+  ctx_make_K(c, K0);
+  float4 *block = nullptr;
+  cudaError_t e = cudaMalloc((void **)&block, c->px_off[levels] * sizeof(float4));
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_fail(e, "cudaMalloc(template)");
+  }
+  for (int l = 0; l < levels; l++) c->pts[l] = block + c->px_off[l];
+  e = cudaHostAlloc((void **)&c->pts_stage, c->px_off[levels] * sizeof(float4), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaFree(block);
+    delete c;
+    return cuda_fail(e, "cudaHostAlloc(template staging)");
+  }
+  *out = c;
+  return DSLAM_OK;
+}
+
+int dslam_ctx_destroy(dslam_ctx *c) {
+  if (!c) return DSLAM_OK;
+  cudaSetDevice(c->s->device);
+  cudaStreamSynchronize(c->s->stream);
+  cudaFree(c->pts[0]);
+  cudaFreeHost(c->pts_stage);
+  cudaFree(c->grid_block);
+  cudaFree(c->scan_block);
+  cudaFree(c->pt_stage_dev);
+  delete c;
+  return DSLAM_OK;
+}
+
+int dslam_ctx_make_K(dslam_ctx *c, const float K0[4]) {
+  if (!c || !K0) return fail(DSLAM_EINVAL, "null argument");
+  ctx_make_K(c, K0);
+  return DSLAM_OK;
+}
+
+int dslam_ctx_set_affine_mode(dslam_ctx *c, int modeA, int modeB) {
+  if (!c) return fail(DSLAM_EINVAL, "null context");
+  c->affModeA = modeA;
+  c->affModeB = modeB;
+  return DSLAM_OK;
+}
+
+int dslam_ref_upload(dslam_ctx *c, int lvl, int n, const float *u, const float *v, const float *idepth, const float *color) {
+  if (!c) return fail(DSLAM_EINVAL, "null context");
+  if (lvl < 0 || lvl >= c->levels) return fail(DSLAM_EINVAL, "level %d out of range", lvl);
+  if (n < 0 || (size_t)n > c->px_off[lvl + 1] - c->px_off[lvl]) return fail(DSLAM_EINVAL, "pc_n %d exceeds w*h of level %d", n, lvl);
+  if (n > 0 && (!u || !v || !idepth || !color)) return fail(DSLAM_EINVAL, "null template array");
+  // the staging slice of this level may still be in flight from the previous upload
+  DSLAM_CUDA(cudaStreamSynchronize(c->s->stream));
+  float4 *st = c->pts_stage + c->px_off[lvl];
+  for (int i = 0; i < n; i++) st[i] = make_float4(u[i], v[i], idepth[i], color[i]);
+  if (n > 0) DSLAM_CUDA(cudaMemcpyAsync(c->pts[lvl], st, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->s->stream));
+  c->pc_n[lvl] = n;
+  c->have_ref = true;
+  return DSLAM_OK;
+}
+
+int dslam_ref_set_affine(dslam_ctx *c, float ref_exposure, double ref_a, double ref_b) {
+  if (!c) return fail(DSLAM_EINVAL, "null context");
+  c->ref_exposure = ref_exposure;
+  c->ref_a = ref_a;
+  c->ref_b = ref_b;
+  return DSLAM_OK;
+}
+
+int dslam_ref_scale_idepth(dslam_ctx *c, float scale) {
+  if (!c) return fail(DSLAM_EINVAL, "null context");
+  if (!c->have_ref) return fail(DSLAM_ESTATE, "no tracking reference uploaded");
+  for (int l = 0; l < c->levels; l++)
+    if (c->pc_n[l] > 0) {
+      DSLAM_CUDA(launch_scale_idepth(c->pts[l], c->pc_n[l], scale, c->s->stream));
+      c->s->launches++;
+    }
+  return DSLAM_OK;
+}
+
+int dslam_ref_build(dslam_ctx *c, dslam_frame *ref_frame, int npts, const int *pu, const int *pv, const float *pidepth, const float *pweight,
+                    int *pc_n_out) {
+  if (!c || !ref_frame) return fail(DSLAM_EINVAL, "null argument");
+  if (npts < 0 || (npts > 0 && (!pu || !pv || !pidepth || !pweight))) return fail(DSLAM_EINVAL, "bad point export");
+  if (c->s != ref_frame->s) return fail(DSLAM_EINVAL, "context and frame belong to different sessions");
+  if (!ref_frame->built) return fail(DSLAM_ESTATE, "reference frame pyramid has not been built");
+  if (ref_frame->w != c->w[0] || ref_frame->h != c->h[0] || ref_frame->levels < c->levels) return fail(DSLAM_EINVAL, "frame geometry mismatch");
+  dslam_session *s = c->s;
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  const size_t tot = c->px_off[c->levels];
+  TemplateGrids G{};
+  G.levels = c->levels;
+  int nblocks = 0;
+  for (int l = 0; l < c->levels; l++) {
+    G.w[l] = c->w[l];
+    G.h[l] = c->h[l];
+    G.cblock_begin[l] = nblocks;
+    nblocks += template_compact_blocks(c->w[l], c->h[l]);
+  }
+  for (int l = c->levels; l <= kMaxLevels; l++) G.cblock_begin[l] = nblocks;
+  if (!c->grid_block) DSLAM_CUDA(cudaMalloc((void **)&c->grid_block, 3 * tot * sizeof(float)));
+  if (!c->scan_block) DSLAM_CUDA(cudaMalloc((void **)&c->scan_block, (size_t)(2 * nblocks + kMaxLevels + 8) * sizeof(int)));
+  for (int l = 0; l < c->levels; l++) {
+    G.idepth[l] = c->grid_block + c->px_off[l];
+    G.wsum[l] = c->grid_block + tot + c->px_off[l];
+    G.wsum2[l] = c->grid_block + 2 * tot + c->px_off[l];
+    G.tex[l] = ref_frame->L.tex[l];
+    G.out[l] = c->pts[l];
+  }
+  if (npts > c->pt_stage_cap) {
+    cudaFree(c->pt_stage_dev);
+    c->pt_stage_dev = nullptr;
+    const int cap = npts + npts / 2 + 1024;
+    DSLAM_CUDA(cudaMalloc(&c->pt_stage_dev, (size_t)cap * 16));
+    c->pt_stage_cap = cap;
+  }
+  int *d_pu = (int *)c->pt_stage_dev, *d_pv = d_pu + c->pt_stage_cap;
+  float *d_id = (float *)(d_pv + c->pt_stage_cap), *d_w = d_id + c->pt_stage_cap;
+  if (npts > 0) {
+    DSLAM_CUDA(cudaMemcpyAsync(d_pu, pu, (size_t)npts * 4, cudaMemcpyHostToDevice, s->stream));
+    DSLAM_CUDA(cudaMemcpyAsync(d_pv, pv, (size_t)npts * 4, cudaMemcpyHostToDevice, s->stream));
+    DSLAM_CUDA(cudaMemcpyAsync(d_id, pidepth, (size_t)npts * 4, cudaMemcpyHostToDevice, s->stream));
+    DSLAM_CUDA(cudaMemcpyAsync(d_w, pweight, (size_t)npts * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  int *block_counts = c->scan_block, *block_offsets = c->scan_block + nblocks, *pc_n_dev = c->scan_block + 2 * nblocks;
+  int nl = 0;
+  DSLAM_CUDA(launch_template_build(G, d_pu, d_pv, d_id, d_w, npts, block_counts, block_offsets, pc_n_dev, &nl, s->stream));
+  s->launches += nl;
+  int pcn[kMaxLevels] = {0};
+  DSLAM_CUDA(cudaMemcpyAsync(pcn, pc_n_dev, sizeof(int) * c->levels, cudaMemcpyDeviceToHost, s->stream));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  for (int l = 0; l < c->levels; l++) {
+    c->pc_n[l] = pcn[l];
+    if (pc_n_out) pc_n_out[l] = pcn[l];
+  }
+  c->have_ref = true;
+  return DSLAM_OK;
+}
+
+int dslam_ref_download(dslam_ctx *c, int lvl, int *n_out, float *u, float *v, float *idepth, float *color) {
+  if (!c || !n_out) return fail(DSLAM_EINVAL, "null argument");
+  if (lvl < 0 || lvl >= c->levels) return fail(DSLAM_EINVAL, "level %d out of range", lvl);
+  const int n = c->pc_n[lvl];
+  *n_out = n;
+  if (!u && !v && !idepth && !color) return DSLAM_OK;
+  std::vector<float4> tmp((size_t)n);
+  if (n > 0) {
+    DSLAM_CUDA(cudaMemcpyAsync(tmp.data(), c->pts[lvl], (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->s->stream));
+    DSLAM_CUDA(cudaStreamSynchronize(c->s->stream));
+  }
+  for (int i = 0; i < n; i++) {
+    if (u) u[i] = tmp[i].x;
+    if (v) v[i] = tmp[i].y;
+    if (idepth) idepth[i] = tmp[i].z;
+    if (color) color[i] = tmp[i].w;
+  }
+  return DSLAM_OK;
+}
+
+// ---- batched evaluation ----------------------------------------------------------------------------
+int dslam_pose_eval(dslam_ctx *c, dslam_frame *f, float new_exposure, int lvl, int nb, const double *pose7, const double *aff_ab,
+                    float cutoffTH, double *H64, double *b8, double *res6, int *n_padded, double *acc48) {
+  int rc = check_ctx_frame(c, f, 0);
+  if (rc != DSLAM_OK) return rc;
+  if (lvl < 0 || lvl >= c->levels) return fail(DSLAM_EINVAL, "level %d out of range", lvl);
+  if (nb < 1 || !pose7 || !aff_ab) return fail(DSLAM_EINVAL, "bad batch");
+  std::vector<EvalItem> items;
+  std::vector<EvalOut> outs;
+  for (int base = 0; base < nb; base += kResultSlots) {
+    const int cnt = nb - base < kResultSlots ? nb - base : kResultSlots;
+    items.assign((size_t)cnt, EvalItem());
+    for (int i = 0; i < cnt; i++)
+      fill_pose_item(items[i], c, f, new_exposure, lvl, hm::Se3::from7(pose7 + 7 * (size_t)(base + i)), aff_ab + 2 * (size_t)(base + i), cutoffTH);
+    rc = run_items(c->s, 0, items, outs, &c->n_launches);
+    if (rc != DSLAM_OK) return rc;
+    c->n_evals += cnt;
+    for (int i = 0; i < cnt; i++) {
+      const size_t g = (size_t)base + i;
+      double H[64], b[8];
+      pose_normal_equations(outs[i], H, b);
+      if (H64) std::memcpy(H64 + 64 * g, H, sizeof(H));
+      if (b8) std::memcpy(b8 + 8 * g, b, sizeof(b));
+      if (res6) std::memcpy(res6 + 6 * g, outs[i].res6, sizeof(double) * 6);
+      if (n_padded) n_padded[g] = outs[i].n_padded;
+      if (acc48) std::memcpy(acc48 + 48 * g, outs[i].acc, sizeof(double) * 48);
+    }
+  }
+  return DSLAM_OK;
+}
+
+int dslam_scale_eval(dslam_ctx *c, dslam_frame *f_right, int lvl, int nb, const float *scales, float cutoffTH, float *Hb2, double *res6,
+                     int *n_padded, double *acc8) {
+  int rc = check_ctx_frame(c, f_right, 0);
+  if (rc != DSLAM_OK) return rc;
+  if (lvl < 0 || lvl >= c->levels) return fail(DSLAM_EINVAL, "level %d out of range", lvl);
+  if (nb < 1 || !scales) return fail(DSLAM_EINVAL, "bad batch");
+  std::vector<EvalItem> items;
+  std::vector<EvalOut> outs;
+  for (int base = 0; base < nb; base += kResultSlots) {
+    const int cnt = nb - base < kResultSlots ? nb - base : kResultSlots;
+    items.assign((size_t)cnt, EvalItem());
+    for (int i = 0; i < cnt; i++) fill_scale_item(items[i], c, f_right, lvl, scales[base + i], cutoffTH);
+    rc = run_items(c->s, 1, items, outs, &c->n_launches);
+    if (rc != DSLAM_OK) return rc;
+    c->n_evals += cnt;
+    for (int i = 0; i < cnt; i++) {
+      const size_t g = (size_t)base + i;
+      if (Hb2) scale_normal_equations(outs[i], Hb2 + 2 * g, Hb2 + 2 * g + 1);
+      if (res6) std::memcpy(res6 + 6 * g, outs[i].res6, sizeof(double) * 6);
+      if (n_padded) n_padded[g] = outs[i].n_padded;
+      if (acc8) std::memcpy(acc8 + 8 * g, outs[i].acc, sizeof(double) * 8);
+    }
+  }
+  return DSLAM_OK;
+}
+
+// ---- Levenberg-Marquardt drivers ---------------------------------------------------------------------
+int dslam_track_newest_coarse_multi(dslam_ctx *c, dslam_frame *f, float new_exposure, int nhyp, double *pose7_io, double *aff_io,
+                                    int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3, int *ok) {
+  int rc = check_ctx_frame(c, f, coarsestLvl);
+  if (rc != DSLAM_OK) return rc;
+  if (nhyp < 1 || nhyp > kResultSlots || !pose7_io || !aff_io || !minResForAbort) return fail(DSLAM_EINVAL, "bad argument");
+  c->trace.clear();
+  std::vector<PoseLM> lms((size_t)nhyp);
+  for (int i = 0; i < nhyp; i++) lms[i].begin(c, f, new_exposure, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort, i == 0 ? &c->trace : nullptr);
+  rc = run_lock_step(c->s, 0, lms, c);
+  if (rc != DSLAM_OK) return rc;
+  for (int i = 0; i < nhyp; i++) {
+    PoseLM &m = lms[i];
+    c->n_iters += m.iters;
+    bool good = m.ok;
+    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, m.lastResiduals, sizeof(double) * 5);
+    if (flow3) std::memcpy(flow3 + 3 * i, m.flow, sizeof(double) * 3);
+    if (good) {
+      // :612-637  outputs are only written when the level loop ran to completion
+      m.cur.to7(pose7_io + 7 * i);
+      double *aff = aff_io + 2 * i;
+      aff[0] = m.aff_cur[0];
+      aff[1] = m.aff_cur[1];
+      if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) good = false;
+      if (good) {
+        double rel[2];
+        hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], rel);
+        const float relA = (float)rel[0], relB = (float)rel[1];
+        if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) good = false;
+      }
+      if (good) {
+        if (c->affModeA < 0) aff[0] = 0;
+        if (c->affModeB < 0) aff[1] = 0;
+      }
+    }
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  return DSLAM_OK;
+}
+
+int dslam_track_newest_coarse(dslam_ctx *c, dslam_frame *f, float new_exposure, double pose7_io[7], double aff_io[2], int coarsestLvl,
+                              const double minResForAbort[5], double lastResiduals[5], double flow3[3], int *ok) {
+  return dslam_track_newest_coarse_multi(c, f, new_exposure, 1, pose7_io, aff_io, coarsestLvl, minResForAbort, lastResiduals, flow3, ok);
+}
+
+int dslam_optimize_scale_multi(dslam_ctx *c, dslam_frame *f_right, int nseeds, float *scales_io, int coarsestLvl, float *rmse_out) {
+  int rc = check_ctx_frame(c, f_right, coarsestLvl);
+  if (rc != DSLAM_OK) return rc;
+  if (nseeds < 1 || nseeds > kResultSlots || !scales_io) return fail(DSLAM_EINVAL, "bad argument");
+  c->trace.clear();
+  std::vector<ScaleLM> lms((size_t)nseeds);
+  for (int i = 0; i < nseeds; i++) lms[i].begin(c, f_right, scales_io[i], coarsestLvl, i == 0 ? &c->trace : nullptr);
+  rc = run_lock_step(c->s, 1, lms, c);
+  if (rc != DSLAM_OK) return rc;
+  for (int i = 0; i < nseeds; i++) {
+    c->n_iters += lms[i].iters;
+    scales_io[i] = lms[i].scale_current;               // :954
+    if (rmse_out) rmse_out[i] = lms[i].last_residuals[0];  // :963
+  }
+  return DSLAM_OK;
+}
+
+// Independent stereo streams (one tracker object + one frame each) advanced in lock step: every LM round of all of
+// them is one kernel launch.  Same results as n sequential calls.
+int dslam_track_newest_coarse_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames, const float *new_exposure, double *pose7_io,
+                                    double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3,
+                                    int *ok) {
+  if (n < 1 || n > kResultSlots || !ctxs || !frames || !pose7_io || !aff_io || !minResForAbort) return fail(DSLAM_EINVAL, "bad argument");
+  for (int i = 0; i < n; i++) {
+    const int rc = check_ctx_frame(ctxs[i], frames[i], coarsestLvl);
+    if (rc != DSLAM_OK) return rc;
+    if (ctxs[i]->s != ctxs[0]->s) return fail(DSLAM_EINVAL, "all streams of a batch must live in one session");
+  }
+  std::vector<PoseLM> lms((size_t)n);
+  for (int i = 0; i < n; i++) {
+    ctxs[i]->trace.clear();
+    lms[i].begin(ctxs[i], frames[i], new_exposure ? new_exposure[i] : 1.0f, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort,
+                 &ctxs[i]->trace);
+  }
+  const int rc = run_lock_step(ctxs[0]->s, 0, lms, ctxs[0]);
+  if (rc != DSLAM_OK) return rc;
+  for (int i = 0; i < n; i++) {
+    PoseLM &m = lms[i];
+    dslam_ctx *c = ctxs[i];
+    c->n_iters += m.iters;
+    bool good = m.ok;
+    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, m.lastResiduals, sizeof(double) * 5);
+    if (flow3) std::memcpy(flow3 + 3 * i, m.flow, sizeof(double) * 3);
+    if (good) {
+      m.cur.to7(pose7_io + 7 * i);
+      double *aff = aff_io + 2 * i;
+      aff[0] = m.aff_cur[0];
+      aff[1] = m.aff_cur[1];
+      const float ne = new_exposure ? new_exposure[i] : 1.0f;
+      if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) good = false;
+      if (good) {
+        double rel[2];
+        hm::aff_from_to(c->ref_exposure, ne, c->ref_a, c->ref_b, aff[0], aff[1], rel);
+        const float relA = (float)rel[0], relB = (float)rel[1];
+        if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) good = false;
+      }
+      if (good) {
+        if (c->affModeA < 0) aff[0] = 0;
+        if (c->affModeB < 0) aff[1] = 0;
+      }
+    }
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  return DSLAM_OK;
+}
+
+int dslam_optimize_scale_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames_right, float *scales_io, int coarsestLvl,
+                               float *rmse_out) {
+  if (n < 1 || n > kResultSlots || !ctxs || !frames_right || !scales_io) return fail(DSLAM_EINVAL, "bad argument");
+  for (int i = 0; i < n; i++) {
+    const int rc = check_ctx_frame(ctxs[i], frames_right[i], coarsestLvl);
+    if (rc != DSLAM_OK) return rc;
+    if (ctxs[i]->s != ctxs[0]->s) return fail(DSLAM_EINVAL, "all streams of a batch must live in one session");
+  }
+  std::vector<ScaleLM> lms((size_t)n);
+  for (int i = 0; i < n; i++) {
+    ctxs[i]->trace.clear();
+    lms[i].begin(ctxs[i], frames_right[i], scales_io[i], coarsestLvl, &ctxs[i]->trace);
+  }
+  const int rc = run_lock_step(ctxs[0]->s, 1, lms, ctxs[0]);
+  if (rc != DSLAM_OK) return rc;
+  for (int i = 0; i < n; i++) {
+    ctxs[i]->n_iters += lms[i].iters;
+    scales_io[i] = lms[i].scale_current;
+    if (rmse_out) rmse_out[i] = lms[i].last_residuals[0];
+  }
+  return DSLAM_OK;
+}
+
+int dslam_optimize_scale(dslam_ctx *c, dslam_frame *f_right, float *scale_io, int coarsestLvl, float *rmse_out) {
+  return dslam_optimize_scale_multi(c, f_right, 1, scale_io, coarsestLvl, rmse_out);
+}
+
+int dslam_get_trace(dslam_ctx *c, double *rows, int max_rows, int *rows_out) {
+  if (!c || !rows_out) return fail(DSLAM_EINVAL, "null argument");
+  const int n = (int)(c->trace.size() / 15);
+  *rows_out = n;
+  if (rows)
+    for (int i = 0; i < n && i < max_rows; i++) std::memcpy(rows + 15 * i, c->trace.data() + 15 * (size_t)i, sizeof(double) * 15);
+  return DSLAM_OK;
+}
+
+int dslam_ctx_counters(dslam_ctx *c, long long out[3]) {
+  if (!c || !out) return fail(DSLAM_EINVAL, "null argument");
+  out[0] = c->n_evals;
+  out[1] = c->n_launches;
+  out[2] = c->n_iters;
+  return DSLAM_OK;
+}
+
+}  // extern "C"

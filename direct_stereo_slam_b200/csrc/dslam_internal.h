@@ -1,0 +1,91 @@
+// dslam_internal.h — host-side object layouts shared by the translation units of libdslam_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dslam_b200.h"
+#include "dslam_kernels.h"
+#include "host_math.h"
+
+namespace dslam {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define DSLAM_CUDA(call)                                        \
+  do {                                                          \
+    cudaError_t e__ = (call);                                   \
+    if (e__ != cudaSuccess) return ::dslam::cuda_fail(e__, #call); \
+  } while (0)
+
+constexpr int kResultSlots = 1024;  // pinned, mapped EvalResult ring of a session (8 launches of 128 items)
+
+}  // namespace dslam
+
+// One CUDA stream plus the pinned result ring the evaluation kernels publish into.
+struct dslam_session {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dslam::EvalResult *results_host = nullptr;  // cudaHostAllocMapped
+  dslam::EvalResult *results_dev = nullptr;   // device alias of results_host
+  dslam::EvalScratch scratch{nullptr, nullptr};
+  unsigned seq = 0;        // sequence number of the last evaluation launch group
+  long long launches = 0;  // kernels of this library launched on the stream
+  cudaEvent_t mark[2] = {nullptr, nullptr};
+  int num_sms = 148;
+  double timeout_s = 20.0;
+  // optional per-launch profiling of the evaluation kernels (CUDA events on this stream around every launch)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;     // pairs
+  std::vector<int> prof_mode;           // per pair: 0 pose, 1 scale
+  std::vector<long long> prof_points;   // per pair: template points evaluated by the launch (sum over items)
+  size_t prof_used = 0;                 // pairs recorded since the last read
+};
+
+struct dslam_frame {
+  dslam_session *s = nullptr;
+  int w = 0, h = 0, levels = 0;
+  dslam::PyramidLevels L{};
+  dslam::PyramidMaps maps{};
+  void *block = nullptr;       // one allocation: intensity planes + texels
+  float *stage_dIp = nullptr;  // device staging in the reference host layout, all levels contiguous (lazy)
+  float *stage_abs = nullptr;
+  float *B_dev = nullptr;      // 256-float gamma table (lazy)
+  size_t px_off[dslam::kMaxLevels + 1]{};
+  bool uploaded = false, built = false, staged = false;
+  cudaEvent_t host_ready = nullptr;
+};
+
+struct dslam_ctx {
+  dslam_session *s = nullptr;
+  int w[dslam::kMaxLevels]{}, h[dslam::kMaxLevels]{}, levels = 0;
+  dslam::hm::CamPyramid cam0{}, cam1{};
+  float Ki[dslam::kMaxLevels][9]{};
+  dslam::hm::Se3 T_f1_f0{};
+  float M_stereo[dslam::kMaxLevels][9]{};  // R_f1_f0 * Ki[lvl]
+  // template (pc_u, pc_v, pc_idepth, pc_color packed as float4), one device array per level
+  float4 *pts[dslam::kMaxLevels]{};
+  int pc_n[dslam::kMaxLevels]{};
+  float4 *pts_stage = nullptr;  // pinned host staging for uploads, level l at px_off[l]
+  size_t px_off[dslam::kMaxLevels + 1]{};
+  bool have_ref = false;
+  float ref_exposure = 1.f;
+  double ref_a = 0, ref_b = 0;
+  int affModeA = 0, affModeB = 0;
+  // device scratch of dslam_ref_build
+  float *grid_block = nullptr;  // idepth / weight sums / backup grids, all levels
+  int *scan_block = nullptr;
+  void *pt_stage_dev = nullptr;
+  int pt_stage_cap = 0;
+  std::vector<double> trace;  // rows of 15 doubles
+  long long n_evals = 0, n_launches = 0, n_iters = 0;
+};

@@ -1,0 +1,128 @@
+// dslam_kernels.h — internal launch interface between the host runtime (dslam_api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace dslam {
+
+constexpr int kMaxLevels = 6;
+
+// ---------------------------------------------------------------------------------------------------
+// residual / Jacobian / normal-equation kernels (kernels_residual.cu)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kEvalThreads = 128;        // threads per CTA of the evaluation kernels
+constexpr int kMaxBlocksPerItem = 128;   // partial-sum slots per work item
+constexpr int kMaxItemsPerLaunch = 128;  // work items carried in kernel-parameter space per launch
+constexpr int kPoseVals = 48;            // 45 upper-triangle sums + E + shiftT + shiftRT
+constexpr int kScaleVals = 8;            // JwJ, Jwr, rwr, E, shiftT, shiftRT, 0, 0
+
+// One evaluation of calcRes*+calcGSSSE* = one work item. Lives in kernel-parameter (constant) space.
+struct alignas(16) EvalItem {
+  const float4 *tex;  // level texels (I, dx, dy, absgrad) of the frame sampled
+  const float4 *pts;  // template records (u, v, idepth, color)
+  int n;              // pc_n[lvl]
+  int w, h;           // level size
+  int flags;          // bit0: accumulate flow indicators (lvl == 0)
+  float fx, fy, cx, cy;  // intrinsics of the camera sampled (cam0 for pose, cam1 for scale)
+  float M[9];         // pose: R*Ki ; scale: R_f1_f0*Ki
+  float t[3];         // pose: translation ; scale: t_f1_f0
+  float Ki[9];        // K^-1 of the level (flow indicators)
+  float p0, p1, p2;   // pose: affLL a, affLL b, b0 ; scale: scale, unused, unused
+  float cutoff, maxEnergy;
+  int nblocks;        // CTAs working on this item (<= gridDim.x)
+  int ppt_stride;     // = nblocks * kEvalThreads (grid stride)
+  int pad_;
+};
+
+struct EvalBatch {
+  EvalItem item[kMaxItemsPerLaunch];
+};
+
+// Result record written by the last CTA of an item straight into mapped pinned host memory.
+struct alignas(128) EvalResult {
+  double acc[kPoseVals];
+  int counts[4];  // numTermsInE, numSaturated, numTermsInWarped (unpadded), reserved
+  volatile unsigned seq;  // written last; host spins on it
+  unsigned pad_[27];
+};
+static_assert(sizeof(EvalResult) == 512, "EvalResult layout");
+
+// device scratch of a session: per item-slot partial sums, counters and tickets
+struct EvalScratch {
+  double *partials;   // [kMaxItemsPerLaunch][kMaxBlocksPerItem][kPoseVals]
+  int *counters;      // [kMaxItemsPerLaunch][4]: nE, nSat, nInl, ticket
+};
+
+// mode 0 = pose (8-DoF), 1 = scale (1-DoF). results_dev = device alias of the mapped EvalResult array.
+cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
+                        unsigned seq, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------
+// pyramid kernels (kernels_pyramid.cu)
+// ---------------------------------------------------------------------------------------------------
+struct PyramidLevels {
+  int levels;
+  int w[kMaxLevels], h[kMaxLevels];
+  int pitch[kMaxLevels];        // floats per row of the intensity planes (multiple of 4)
+  float *plane[kMaxLevels];     // intensity planes; plane[0] = uploaded image
+  float4 *tex[kMaxLevels];      // texels (I, dx, dy, absgrad), dense pitch = w
+  float *host_dIp[kMaxLevels];  // optional staging in the reference host layout (3 floats AoS); may be null
+  float *host_abs[kMaxLevels];  // optional staging float plane; may be null
+  int tile_begin[kMaxLevels + 1];  // prefix of gradient tiles per level (kernel B)
+  int tiles_x[kMaxLevels];
+};
+struct PyramidMaps {
+  CUtensorMap map[kMaxLevels];  // 2-D fp32 tensor maps over plane[l], box = (kGradBoxW x kGradBoxH)
+};
+constexpr int kGradTileW = 64, kGradTileH = 16;
+constexpr int kGradBoxW = kGradTileW + 8;  // 72 floats = 288 B; the box starts at x0-4 because TMA needs a 16-B aligned source address
+constexpr int kGradBoxH = kGradTileH + 2;
+constexpr int kDownTileW = 64, kDownTileH = 32;  // level-0 tile of the box-mean chain
+
+cudaError_t launch_downsample(const PyramidLevels &L, cudaStream_t stream);
+cudaError_t launch_gradients(const PyramidLevels &L, const PyramidMaps &maps, const float *B256_dev, cudaStream_t stream);
+// texels -> the reference's host layouts (Vector3f AoS + float plane) for a frame built without staging
+cudaError_t launch_unpack(const PyramidLevels &L, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------
+// template kernels (kernels_template.cu): makeCoarseDepthL0 / scaleCoarseDepthL0 on the device
+// ---------------------------------------------------------------------------------------------------
+struct TemplateGrids {
+  int levels;
+  int w[kMaxLevels], h[kMaxLevels];
+  float *idepth[kMaxLevels];      // idepth_[lvl]
+  float *wsum[kMaxLevels];        // weight_sums_[lvl] before dilation (plays weight_sums_bak_)
+  float *wsum2[kMaxLevels];       // weight_sums_[lvl] after dilation
+  const float4 *tex[kMaxLevels];  // texels of the reference keyframe (colour = .x)
+  float4 *out[kMaxLevels];        // compacted template records (u, v, idepth, color)
+  int cblock_begin[kMaxLevels + 1];  // prefix of 1024-pixel compaction blocks per level
+};
+int template_compact_blocks(int w, int h);
+// makeCoarseDepthL0 from a flat device export of the active points; pc_n_dev[levels] receives the counts
+cudaError_t launch_template_build(const TemplateGrids &G, const int *pu, const int *pv, const float *pid, const float *pw, int npts,
+                                  int *block_counts, int *block_offsets, int *pc_n_dev, int *launches, cudaStream_t stream);
+cudaError_t launch_scale_idepth(float4 *pts, int n, float scale, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------
+// Scan-Context kernels (kernels_sc.cu)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kScTopK = 8;
+// ring-key scan: per query the k (<=8) nearest rows by squared L2 in flann::L2 arithmetic, as packed
+// (float_bits(dist) << 32 | global_id) keys sorted ascending; out[nq][kScTopK], unused = ~0ull
+cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
+                              unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
+// sector-cosine scan: per query top-kScTopK packed (approximate dist, LOCAL ROW) keys over rows with id < max_id and
+// (thres < 0 or ring dist < thres); ids must ascend with the row so that ties still resolve to the lowest id
+cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim,
+                           const float *q_sigs, const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width,
+                           unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
+size_t sc_scratch_bytes(int nq);
+// exact re-score of the scan's survivors in search_sc's arithmetic -> per-query best packed (dist, GLOBAL id) key
+cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const float *sigs, const int *ids, const float *q_sigs, int nq, int n_cells,
+                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, cudaStream_t stream);
+// exact distances of explicit (query, local row) pairs; row < 0 = skip (+inf)
+cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const float *sigs, const float *q_sigs, int n_cells,
+                                    int sc_width, float *diff_out, cudaStream_t stream);
+
+}  // namespace dslam

@@ -1,0 +1,263 @@
+// kernels_pyramid.cu — image pyramid of one frame on the device.  sm_100a.
+//
+// Replaces FrameHessian::makeImages  deps:dso/src/FullSystem/HessianBlocks.cpp:128-191:
+//   level 0 channel 0 = input; level k channel 0 = 0.25f * (((a + b) + c) + d) of the 2x2 block of level k-1
+//   (:162-165, same operand order); for linear idx in [w, w*(h-1)): dx = 0.5f*(I[idx+1]-I[idx-1]),
+//   dy = 0.5f*(I[idx+w]-I[idx-w]), non-finite -> 0 (:169-179) — note the LINEAR index: at x = 0 / x = w-1 the
+//   horizontal neighbour wraps to the previous / next row, and that is reproduced here;
+//   absSquaredGrad = dx*dx + dy*dy, times gw*gw with gw = B[c+1]-B[c], c = clamp((int)(I+0.5f), 5, 250)
+//   (:182-188, getBGradOnly deps:dso/src/FullSystem/HessianBlocks.h:384-390) when a B table is given.
+//   Rows 0 and h-1 (uninitialised in the reference) are written as dx = dy = absSquaredGrad = 0.
+//
+// Two launches per frame, both bit-exact (compiled -fmad=false; only adds, multiplies by 0.25f/0.5f and the
+// squared-gradient sum are involved):
+//   A  downsample_chain_kernel : one CTA per 64x32 level-0 tile builds the intensity of levels 1..L-1 through
+//      shared memory (float2 coalesced loads, every level written once);
+//   B  gradient_kernel         : one CTA per 64x16 tile of ANY level (all levels in one grid); the (64+8)x(16+2)
+//      halo box of the intensity plane is staged into shared memory by TMA (cp.async.bulk.tensor.2d, zero
+//      fill outside the image, completion on an mbarrier); each thread emits one float4 texel
+//      (I, dx, dy, absSquaredGrad) per pixel — 16-B coalesced stores — plus, when the host wants the
+//      reference's layouts, the Vector3f AoS / float plane staging copies that are then DMA'd to the host.
+// Algorithmic traffic: read 4*P0, write 16*sum(P_l) (+16*sum(P_l) staging when host copies are requested).
+
+#include "dslam_kernels.h"
+
+namespace dslam {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// A: box-mean chain
+// ---------------------------------------------------------------------------------------------------
+struct DownParams {
+  int levels;
+  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  float *plane[kMaxLevels];
+};
+
+template <int TW, int TH>  // tile of the level being produced; source in shared memory has size 2TW x 2TH
+__device__ __forceinline__ void down_from_smem(const float *src, float *dst_s, float *dst_g, int pitch, int x0, int y0, int w, int h,
+                                               int tid) {
+  for (int p = tid; p < TW * TH; p += 256) {
+    const int lx = p % TW, ly = p / TW;
+    const float a = src[(2 * ly) * (2 * TW) + 2 * lx], b = src[(2 * ly) * (2 * TW) + 2 * lx + 1];
+    const float c = src[(2 * ly + 1) * (2 * TW) + 2 * lx], d = src[(2 * ly + 1) * (2 * TW) + 2 * lx + 1];
+    const float v = 0.25f * (a + b + c + d);
+    dst_s[ly * TW + lx] = v;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x < w && y < h) dst_g[(size_t)y * pitch + x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) downsample_chain_kernel(const __grid_constant__ DownParams P) {
+  __shared__ float s1[32 * 16], s2[16 * 8], s3[8 * 4], s4[4 * 2], s5[2];
+  const int tid = threadIdx.x;
+  const int X0 = blockIdx.x * kDownTileW, Y0 = blockIdx.y * kDownTileH;  // level-0 origin of the tile
+  // level 1 from global level 0 (float2 loads; pitch is a multiple of 4 floats, x even -> 8-B aligned)
+  {
+    const float *src = P.plane[0];
+    const int pitch0 = P.pitch[0], w0 = P.w[0], h0 = P.h[0];
+    const int w1 = P.w[1], h1 = P.h[1], x10 = X0 >> 1, y10 = Y0 >> 1;
+    for (int p = tid; p < 32 * 16; p += 256) {
+      const int lx = p % 32, ly = p / 32;
+      const int x = x10 + lx, y = y10 + ly;
+      float v = 0.f;
+      if (2 * x + 1 < w0 && 2 * y + 1 < h0) {
+        const float2 r0 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(2 * y) * pitch0 + 2 * x));
+        const float2 r1 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(2 * y + 1) * pitch0 + 2 * x));
+        v = 0.25f * (r0.x + r0.y + r1.x + r1.y);
+        if (x < w1 && y < h1) P.plane[1][(size_t)y * P.pitch[1] + x] = v;
+      }
+      s1[p] = v;
+    }
+  }
+  if (P.levels <= 2) return;
+  __syncthreads();
+  down_from_smem<16, 8>(s1, s2, P.plane[2], P.pitch[2], X0 >> 2, Y0 >> 2, P.w[2], P.h[2], tid);
+  if (P.levels <= 3) return;
+  __syncthreads();
+  down_from_smem<8, 4>(s2, s3, P.plane[3], P.pitch[3], X0 >> 3, Y0 >> 3, P.w[3], P.h[3], tid);
+  if (P.levels <= 4) return;
+  __syncthreads();
+  down_from_smem<4, 2>(s3, s4, P.plane[4], P.pitch[4], X0 >> 4, Y0 >> 4, P.w[4], P.h[4], tid);
+  if (P.levels <= 5) return;
+  __syncthreads();
+  down_from_smem<2, 1>(s4, s5, P.plane[5], P.pitch[5], X0 >> 5, Y0 >> 5, P.w[5], P.h[5], tid);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// B: gradients + texel packing, TMA-staged halo tiles
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct GradParams {
+  PyramidLevels L;
+  const float *B256;  // device gamma table or null
+};
+
+__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ GradParams P, const __grid_constant__ PyramidMaps maps) {
+  __shared__ __align__(128) float box[kGradBoxH * kGradBoxW];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  // which level / tile
+  int lvl = 0;
+#pragma unroll
+  for (int l = 1; l < kMaxLevels; l++)
+    if (l < P.L.levels && (int)blockIdx.x >= P.L.tile_begin[l]) lvl = l;
+  const int t = blockIdx.x - P.L.tile_begin[lvl];
+  const int tx = t % P.L.tiles_x[lvl], ty = t / P.L.tiles_x[lvl];
+  const int x0 = tx * kGradTileW, y0 = ty * kGradTileH;
+  const int w = P.L.w[lvl], h = P.L.h[lvl], pitch = P.L.pitch[lvl];
+  const float *__restrict__ plane = P.L.plane[lvl];
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, kGradBoxH * kGradBoxW * sizeof(float));
+    tma_load_2d(box, &maps.map[lvl], x0 - 4, y0 - 1, &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  float4 *__restrict__ tex = P.L.tex[lvl];
+  float *__restrict__ hd = P.L.host_dIp[lvl];
+  float *__restrict__ ha = P.L.host_abs[lvl];
+  const float *__restrict__ B = P.B256;
+#pragma unroll
+  for (int k = 0; k < kGradTileH / 4; k++) {
+    const int lx = tid % kGradTileW, ly = tid / kGradTileW + 4 * k;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= w || y >= h) continue;
+    const float *s = box + (ly + 1) * kGradBoxW + (lx + 4);
+    const float c = s[0];
+    float dx = 0.f, dy = 0.f, ag = 0.f;
+    if (y >= 1 && y <= h - 2) {
+      // linear-index neighbours: wrap at the row ends exactly like dI_l[idx-1] / dI_l[idx+1]
+      const float left = (x == 0) ? __ldg(plane + (size_t)(y - 1) * pitch + (w - 1)) : s[-1];
+      const float right = (x == w - 1) ? __ldg(plane + (size_t)(y + 1) * pitch) : s[1];
+      dx = 0.5f * (right - left);
+      dy = 0.5f * (s[kGradBoxW] - s[-kGradBoxW]);
+      if (!isfinite(dx)) dx = 0.f;
+      if (!isfinite(dy)) dy = 0.f;
+      ag = dx * dx + dy * dy;
+      if (B != nullptr) {
+        int ci = (int)(c + 0.5f);
+        if (ci < 5) ci = 5;
+        if (ci > 250) ci = 250;
+        const float gw = __ldg(B + ci + 1) - __ldg(B + ci);
+        ag *= gw * gw;
+      }
+    }
+    const size_t idx = (size_t)y * w + x;
+    tex[idx] = make_float4(c, dx, dy, ag);
+    if (hd != nullptr) {
+      hd[3 * idx + 0] = c;
+      hd[3 * idx + 1] = dx;
+      hd[3 * idx + 2] = dy;
+    }
+    if (ha != nullptr) ha[idx] = ag;
+  }
+}
+
+// texels -> staging copies in the reference's host layouts, all levels in one grid (for frames that were
+// built before the host asked for its copies)
+__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ GradParams P, int total) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    int lvl = 0, base = 0, acc = 0;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; l++) {
+      if (l < P.L.levels) {
+        if (i >= acc) { lvl = l; base = acc; }
+        acc += P.L.w[l] * P.L.h[l];
+      }
+    }
+    const int idx = i - base;
+    const float4 t = P.L.tex[lvl][idx];
+    float *hd = P.L.host_dIp[lvl], *ha = P.L.host_abs[lvl];
+    if (hd != nullptr) {
+      hd[3 * (size_t)idx + 0] = t.x;
+      hd[3 * (size_t)idx + 1] = t.y;
+      hd[3 * (size_t)idx + 2] = t.z;
+    }
+    if (ha != nullptr) ha[idx] = t.w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// template helpers
+// ---------------------------------------------------------------------------------------------------
+// scaleCoarseDepthL0  src/scale_optimization/TrackerAndScaler.cpp:329-336  (IEEE division, like the host loop)
+__global__ void scale_idepth_kernel(float4 *__restrict__ pts, int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pts[i].z = pts[i].z / scale;
+}
+
+}  // namespace
+
+cudaError_t launch_downsample(const PyramidLevels &L, cudaStream_t stream) {
+  if (L.levels < 2) return cudaSuccess;
+  DownParams P;
+  P.levels = L.levels;
+  for (int l = 0; l < kMaxLevels; l++) {
+    P.w[l] = L.w[l]; P.h[l] = L.h[l]; P.pitch[l] = L.pitch[l]; P.plane[l] = L.plane[l];
+  }
+  dim3 grid((L.w[0] + kDownTileW - 1) / kDownTileW, (L.h[0] + kDownTileH - 1) / kDownTileH);
+  downsample_chain_kernel<<<grid, 256, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gradients(const PyramidLevels &L, const PyramidMaps &maps, const float *B256_dev, cudaStream_t stream) {
+  GradParams P;
+  P.L = L;
+  P.B256 = B256_dev;
+  gradient_kernel<<<L.tile_begin[L.levels], 256, 0, stream>>>(P, maps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const PyramidLevels &L, cudaStream_t stream) {
+  GradParams P;
+  P.L = L;
+  P.B256 = nullptr;
+  int total = 0;
+  for (int l = 0; l < L.levels; l++) total += L.w[l] * L.h[l];
+  int grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  unpack_kernel<<<grid, 256, 0, stream>>>(P, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_idepth(float4 *pts, int n, float scale, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  scale_idepth_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, scale);
+  return cudaGetLastError();
+}
+
+}  // namespace dslam

@@ -1,0 +1,350 @@
+// kernels_residual.cu — fused warp + bilinear sample + Huber residual + Jacobian + normal-equation
+// accumulation for the 8-DoF pose tracker and the 1-DoF stereo scale optimiser.  sm_100a.
+//
+// Replaces, per launch and for every work item (hypothesis) at once:
+//   pose : TrackerAndScaler::calcResPose   src/scale_optimization/TrackerAndScaler.cpp:699-852
+//          TrackerAndScaler::calcGSSSEPose                                          :640-697
+//          Accumulator9::updateSSE_eighted deps:dso/src/OptimizationBackend/MatrixAccumulators.h:1091-1166
+//   scale: TrackerAndScaler::calcResScale                                           :1007-1172
+//          TrackerAndScaler::calcGSSSEScale                                         :966-1005
+//          ScaleAccumulator::updateSSE_oneed src/scale_optimization/ScaleAccumulator.h:60-77
+//          getInterpolatedElement33        deps:dso/src/util/globalFuncs.h:75-89
+//
+// Numerics contract (checked by tests/test_parity_gpu.py against oracle/dslam_oracle.cpp):
+//   * this translation unit is compiled with -fmad=false and every per-point expression is written in the
+//     reference's operation order, so warp, bilinear weights, residual, Huber weight, energy term and the
+//     Jacobian row are bit-identical to the fp32 CPU arithmetic;
+//   * the weighted outer product is accumulated as acc += (double)(J_r*w) * (double)J_c with an explicit
+//     DFMA — the product of two fp32 values is exact in fp64, so the only rounding is the fp64 add.  The
+//     reference's 4-lane / 3-tier fp32 SSE accumulation is strictly noisier; the oracle's "fp64" mode is this
+//     arithmetic, its "sse" mode is the reference's, and their distance is reported as the noise floor.
+//   * reduction order is fixed (thread-sequential, warp reduce-scatter tree, warps in order, CTAs in order),
+//     so results are bit-reproducible run to run for a given launch geometry.
+//
+// Data movement: one 16-B template record + four 16-B texel taps per point (gather through L1/L2; the
+// whole pyramid of a frame is L2-resident after the pyramid kernels wrote it).  Each thread keeps its
+// partial normal equations in registers; a warp folds 48 fp64 values with a reduce-scatter butterfly
+// (48+... = 48 double shuffles instead of 240), warps meet in shared memory, and each CTA publishes one
+// partial record; the last CTA of an item (ticket atomic) sums the partials in CTA order and writes the
+// result record directly into mapped pinned host memory followed by a sequence flag the host spins on —
+// no memcpy, no stream synchronise on the LM critical path.
+
+#include "dslam_kernels.h"
+
+namespace dslam {
+
+namespace {
+
+__device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+
+// Warp reduce-scatter over NV register-resident doubles. After run(): lanes with writer(lane) hold KEEP
+// fully reduced values a[0..KEEP) that belong at output indices base(lane)+0..KEEP-1.
+template <int NV>
+struct WarpRS;
+
+template <int N>
+__device__ __forceinline__ void rs_halve(double *a, int mask, bool upper) {
+#pragma unroll
+  for (int i = 0; i < N / 2; i++) {
+    const double send = upper ? a[i] : a[i + N / 2];
+    const double keep = upper ? a[i + N / 2] : a[i];
+    a[i] = keep + shfl_xor_d(send, mask);
+  }
+}
+
+template <>
+struct WarpRS<48> {
+  static constexpr int KEEP = 3;
+  __device__ static __forceinline__ void run(double (&a)[48], int lane) {
+    rs_halve<48>(a, 16, lane & 16);
+    rs_halve<24>(a, 8, lane & 8);
+    rs_halve<12>(a, 4, lane & 4);
+    rs_halve<6>(a, 2, lane & 2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) a[i] = a[i] + shfl_xor_d(a[i], 1);
+  }
+  __device__ static __forceinline__ bool writer(int lane) { return (lane & 1) == 0; }
+  __device__ static __forceinline__ int base(int lane) {
+    return ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
+  }
+};
+
+template <>
+struct WarpRS<8> {
+  static constexpr int KEEP = 1;
+  __device__ static __forceinline__ void run(double (&a)[8], int lane) {
+    rs_halve<8>(a, 16, lane & 16);
+    rs_halve<4>(a, 8, lane & 8);
+    rs_halve<2>(a, 4, lane & 4);
+    a[0] = a[0] + shfl_xor_d(a[0], 2);
+    a[0] = a[0] + shfl_xor_d(a[0], 1);
+  }
+  __device__ static __forceinline__ bool writer(int lane) { return (lane & 3) == 0; }
+  __device__ static __forceinline__ int base(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+};
+
+// Eigen 3.3 coefficient product of three terms: e0 + (e1 + e2), third factor is the literal 1.
+__device__ __forceinline__ float dot3_xy1(float m0, float m1, float m2, float x, float y) { return m0 * x + (m1 * y + m2); }
+
+// getInterpolatedElement33 on float4 texels; .w of the texel (absSquaredGrad) is ignored.
+__device__ __forceinline__ float3 interp33(const float4 *__restrict__ tex, float x, float y, int width) {
+  const int ix = (int)x;
+  const int iy = (int)y;
+  const float dx = x - ix;
+  const float dy = y - iy;
+  const float dxdy = dx * dy;
+  const float4 *bp = tex + ix + iy * width;
+  const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + width), p11 = __ldg(bp + 1 + width);
+  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+  float3 r;
+  r.x = w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x;
+  r.y = w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y;
+  r.z = w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z;
+  return r;
+}
+
+constexpr float kHuberTH = 9.0f;  // setting_huberTH  deps:dso/src/util/settings.cpp:127
+
+template <int MODE, int CAP>
+struct BatchT {
+  EvalItem item[CAP];
+};
+
+// MODE 0 = pose, 1 = scale.  grid = (max nblocks over items, nitems), block = kEvalThreads.
+template <int MODE, int CAP>
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constant__ BatchT<MODE, CAP> batch, EvalScratch scratch,
+                                                           EvalResult *__restrict__ results, unsigned seq) {
+  constexpr int NV = MODE == 0 ? kPoseVals : kScaleVals;
+  constexpr int NW = kEvalThreads / 32;
+  const EvalItem &it = batch.item[blockIdx.y];
+  if ((int)blockIdx.x >= it.nblocks) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4 *__restrict__ tex = it.tex;
+  const float4 *__restrict__ pts = it.pts;
+  const int wl = it.w, hl = it.h;
+  const float fxl = it.fx, fyl = it.fy, cxl = it.cx, cyl = it.cy;
+  const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
+  const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
+  const bool flow = (it.flags & 1) != 0;
+
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) acc[i] = 0.0;
+  int nE = 0, nSat = 0, nInl = 0;
+
+  for (int i = blockIdx.x * kEvalThreads + tid; i < it.n; i += it.ppt_stride) {
+    const float4 p = __ldg(pts + i);
+    const float x = p.x, y = p.y, id = p.z, refColor = p.w;
+    float pt0, pt1, pt2, rx0 = 0.f, rx1 = 0.f, rx2 = 0.f;
+    if (MODE == 0) {
+      // :747  pt = RKi * (x,y,1) + t*id
+      pt0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) + it.t[0] * id;
+      pt1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) + it.t[1] * id;
+      pt2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) + it.t[2] * id;
+    } else {
+      // :1061  pt = (scale*M) * (x,y,1) + t*id ; :1068  rx = M*(x,y,1) / id
+      const float s = it.p0;
+      pt0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y) + it.t[0] * id;
+      pt1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y) + it.t[1] * id;
+      pt2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y) + it.t[2] * id;
+      rx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) / id;
+      rx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) / id;
+      rx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) / id;
+    }
+    const float u = pt0 / pt2;
+    const float v = pt1 / pt2;
+    const float Ku = fxl * u + cxl;
+    const float Kv = fyl * v + cyl;
+    const float new_idepth = id / pt2;
+
+    if (flow && (i & 31) == 0) {  // :754-784 / :1070-1100 flow indicators, every 32nd template point of level 0
+      const float s = MODE == 0 ? 1.0f : it.p0;
+      float kx0, kx1, kx2, mx0, mx1, mx2;
+      if (MODE == 0) {
+        kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
+        kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
+        kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
+        mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
+        mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
+        mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
+      } else {
+        kx0 = dot3_xy1(s * it.Ki[0], s * it.Ki[1], s * it.Ki[2], x, y);
+        kx1 = dot3_xy1(s * it.Ki[3], s * it.Ki[4], s * it.Ki[5], x, y);
+        kx2 = dot3_xy1(s * it.Ki[6], s * it.Ki[7], s * it.Ki[8], x, y);
+        mx0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y);
+        mx1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y);
+        mx2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y);
+      }
+      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
+      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
+      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
+      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
+      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
+      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      constexpr int iT = MODE == 0 ? 46 : 4, iRT = MODE == 0 ? 47 : 5;
+      acc[iT] += (double)sT1;
+      acc[iT] += (double)sT2;
+      acc[iRT] += (double)sRT1;
+      acc[iRT] += (double)sRT2;
+    }
+
+    if (!(Ku > 2 && Kv > 2 && Ku < wlm3 && Kv < hlm3 && new_idepth > 0)) continue;
+    const float3 hit = interp33(tex, Ku, Kv, wl);
+    if (!isfinite(hit.x)) continue;
+    const float residual = MODE == 0 ? hit.x - (it.p0 * refColor + it.p1) : hit.x - refColor;
+    const float absr = fabsf(residual);
+    const float hw = absr < kHuberTH ? 1.0f : kHuberTH / absr;
+    nE++;
+    if (absr > cutoff) {
+      acc[MODE == 0 ? 45 : 3] += (double)maxEnergy;
+      nSat++;
+      continue;
+    }
+    acc[MODE == 0 ? 45 : 3] += (double)(hw * residual * residual * (2 - hw));
+    nInl++;
+
+    if (MODE == 0) {
+      // calcGSSSEPose :658-678, lane arithmetic of the SSE code
+      const float dx = hit.y * fxl, dy = hit.z * fyl;
+      float J[9];
+      J[0] = new_idepth * dx;
+      J[1] = new_idepth * dy;
+      J[2] = 0.0f - (new_idepth * ((u * dx) + (v * dy)));
+      J[3] = 0.0f - (((u * v) * dx) + (dy * (1.0f + (v * v))));
+      J[4] = ((u * v) * dy) + (dx * (1.0f + (u * u)));
+      J[5] = (u * dy) - (v * dx);
+      J[6] = it.p0 * (it.p2 - refColor);
+      J[7] = -1.0f;
+      J[8] = residual;
+      double Jd[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) Jd[c] = (double)J[c];
+      int e = 0;
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        const double Jw = (double)(J[r] * hw);
+#pragma unroll
+        for (int c = r; c < 9; c++, e++) acc[e] = fma(Jw, Jd[c], acc[e]);
+      }
+    } else {
+      // calcGSSSEScale :983-997
+      const float tx = it.t[0], ty = it.t[1], tz = it.t[2];
+      const float dxfx = hit.y * fxl, dyfy = hit.z * fyl;
+      const float deno_sqrt = (it.p0 * rx2) + tz;
+      const float deno = 1.0f / (deno_sqrt * deno_sqrt);
+      const float xno = (rx0 * tz) - (rx2 * tx);
+      const float yno = (rx1 * tz) - (rx2 * ty);
+      const float J = (dxfx * (deno * xno)) + (dyfy * (deno * yno));
+      const double Jw = (double)(J * hw), rw = (double)(residual * hw);
+      acc[0] = fma(Jw, (double)J, acc[0]);
+      acc[1] = fma(Jw, (double)residual, acc[1]);
+      acc[2] = fma(rw, (double)residual, acc[2]);
+    }
+  }
+
+  // ---- CTA reduction ---------------------------------------------------------------------------------
+  __shared__ double sred[NW][NV];
+  __shared__ int scnt[3];
+  __shared__ int s_last;
+  if (tid < 3) scnt[tid] = 0;
+  WarpRS<NV>::run(acc, lane);
+  if (WarpRS<NV>::writer(lane)) {
+    const int b = WarpRS<NV>::base(lane);
+#pragma unroll
+    for (int k = 0; k < WarpRS<NV>::KEEP; k++) sred[warp][b + k] = acc[k];
+  }
+  nE = __reduce_add_sync(0xffffffffu, nE);
+  nSat = __reduce_add_sync(0xffffffffu, nSat);
+  nInl = __reduce_add_sync(0xffffffffu, nInl);
+  __syncthreads();
+  if (lane == 0) {
+    atomicAdd(&scnt[0], nE);
+    atomicAdd(&scnt[1], nSat);
+    atomicAdd(&scnt[2], nInl);
+  }
+  double *part = scratch.partials + ((size_t)blockIdx.y * kMaxBlocksPerItem + blockIdx.x) * kPoseVals;
+  if (tid < NV) {
+    double s = sred[0][tid];
+#pragma unroll
+    for (int wv = 1; wv < NW; wv++) s += sred[wv][tid];
+    __stcg(part + tid, s);
+  }
+  __threadfence();
+  __syncthreads();
+  int *cnt = scratch.counters + blockIdx.y * 4;
+  if (tid == 0) {
+    atomicAdd(cnt + 0, scnt[0]);
+    atomicAdd(cnt + 1, scnt[1]);
+    atomicAdd(cnt + 2, scnt[2]);
+    __threadfence();
+    const int ticket = atomicAdd(cnt + 3, 1);
+    s_last = (ticket == it.nblocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last CTA of the item: ordered sum of the partials, publish to the host ---------------------------
+  __threadfence();
+  EvalResult *res = results + blockIdx.y;
+  const double *pbase = scratch.partials + (size_t)blockIdx.y * kMaxBlocksPerItem * kPoseVals;
+  constexpr int PARTS = kEvalThreads / NV >= 2 ? 2 : 1;
+  __shared__ double sfin[PARTS][NV];
+  if (tid < NV * PARTS) {
+    const int vi = tid % NV, part_i = tid / NV;
+    double s = 0.0;
+    for (int b = part_i; b < it.nblocks; b += PARTS) s += __ldcg(pbase + (size_t)b * kPoseVals + vi);
+    sfin[part_i][vi] = s;
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double s = sfin[0][tid];
+    if (PARTS == 2) s += sfin[1][tid];
+    res->acc[tid] = s;
+  }
+  if (tid == 0) {
+    res->counts[0] = atomicExch(cnt + 0, 0);
+    res->counts[1] = atomicExch(cnt + 1, 0);
+    res->counts[2] = atomicExch(cnt + 2, 0);
+    res->counts[3] = 0;
+    atomicExch(cnt + 3, 0);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    res->seq = seq;
+    __threadfence_system();
+  }
+}
+
+template <int MODE, int CAP>
+cudaError_t launch_cap(const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results, unsigned seq,
+                       cudaStream_t stream) {
+  BatchT<MODE, CAP> b;
+  for (int i = 0; i < nitems; i++) b.item[i] = batch.item[i];
+  eval_kernel<MODE, CAP><<<dim3(grid_x, nitems), kEvalThreads, 0, stream>>>(b, scratch, results, seq);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_mode(const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results, unsigned seq,
+                        cudaStream_t stream) {
+  if (nitems <= 1) return launch_cap<MODE, 1>(batch, nitems, grid_x, scratch, results, seq, stream);
+  if (nitems <= 8) return launch_cap<MODE, 8>(batch, nitems, grid_x, scratch, results, seq, stream);
+  if (nitems <= 32) return launch_cap<MODE, 32>(batch, nitems, grid_x, scratch, results, seq, stream);
+  return launch_cap<MODE, kMaxItemsPerLaunch>(batch, nitems, grid_x, scratch, results, seq, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
+                        unsigned seq, cudaStream_t stream) {
+  if (nitems < 1 || nitems > kMaxItemsPerLaunch || grid_x < 1 || grid_x > kMaxBlocksPerItem) return cudaErrorInvalidValue;
+  return mode == 0 ? launch_mode<0>(batch, nitems, grid_x, scratch, results_dev, seq, stream)
+                   : launch_mode<1>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
+}
+
+}  // namespace dslam

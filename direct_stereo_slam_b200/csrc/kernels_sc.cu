@@ -1,0 +1,384 @@
+// kernels_sc.cu — Scan-Context loop-candidate search on the device.  sm_100a.
+//
+// Replaces the two search stages of src/loop_closure/loop_detection/search_place.h:
+//   search_ringkey :25-57  (FLANN kd-tree kNN on the 20-float ring keys)  -> sc_ringkey_kernel: EXACT brute-force
+//       k-nearest by squared L2 in flann::L2's arithmetic (4 squared differences summed left to right per step,
+//       FLANN 1.9.1 flann/algorithms/dist.h), so the "< RINGKEY_THRES" gate (:35) is bit-exact;
+//   search_sc      :59-85  (sector-cosine distance over the candidates)   -> sc_scan_kernel: the same distance
+//       (1 - sum_sectors cos / sc_width) / 2 evaluated against EVERY database row (dense 60x20 fp32 descriptors,
+//       columns L2-normalised at generation, ScanContext.cpp:137-141, so the sum of cosines is one 1200-long dot
+//       product), keeping the kScTopK best per query.  The host re-scores those K in the reference's exact
+//       arithmetic (float += double*double) so the final argmin is bit-exact (dslam_api.cu).
+//
+// The scan is HBM-bound pointwise work (4,800 B per row, ~0.5 flop/B per query): one warp streams whole rows with
+// 16-B coalesced loads (10 x LDG.128 per lane per row, two rows in flight per warp), the query batch (<= 32
+// queries per pass) sits in shared memory, lane q owns the running top-K of query q.  No tensor cores: the
+// products must stay fp32-exact enough for the host re-rank to see the true winner, and at Q <= 5 the kernel is
+// bandwidth-bound anyway.  Keys are packed (ordered_float_bits(dist) << 32 | global_id), so "min" is the
+// argmin with ties going to the lowest id — the same key a multi-GPU all-reduce(min) combines.
+
+#include "dslam_kernels.h"
+
+namespace dslam {
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr u64 kKeyMax = ~0ull;
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kQChunk = 32;
+
+__device__ __forceinline__ u64 make_key(float dist, int id) {
+  unsigned b = __float_as_uint(dist);
+  b ^= (b >> 31) ? 0xffffffffu : 0x80000000u;  // total order for signed floats
+  return ((u64)b << 32) | (unsigned)id;
+}
+
+struct TopK {
+  u64 k[kScTopK];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) k[i] = kKeyMax;
+  }
+  __device__ __forceinline__ void insert(u64 key) {
+    if (key < k[kScTopK - 1]) {
+      k[kScTopK - 1] = key;
+#pragma unroll
+      for (int i = kScTopK - 1; i > 0; i--) {
+        const u64 a = k[i - 1], b = k[i];
+        const bool sw = b < a;
+        k[i - 1] = sw ? b : a;
+        k[i] = sw ? a : b;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop_front() {
+#pragma unroll
+    for (int i = 0; i < kScTopK - 1; i++) k[i] = k[i + 1];
+    k[kScTopK - 1] = kKeyMax;
+  }
+};
+
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const u64 o = __shfl_xor_sync(0xffffffffu, v, m);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+
+// union of the 32 per-lane sorted lists -> the kScTopK smallest, returned in every lane
+__device__ __forceinline__ void warp_merge(TopK &t, u64 (&out)[kScTopK]) {
+#pragma unroll
+  for (int r = 0; r < kScTopK; r++) {
+    const u64 m = warp_min_u64(t.k[0]);
+    out[r] = m;
+    if (t.k[0] == m && m != kKeyMax) t.pop_front();
+  }
+}
+
+// flann::L2<float>: result += d0*d0 + d1*d1 + d2*d2 + d3*d3 per group of 4 (compiled -fmad=false)
+__device__ __forceinline__ float flann_l2(const float *__restrict__ a, const float *__restrict__ b, int dim) {
+  float result = 0.f;
+  int i = 0;
+  for (; i + 3 < dim; i += 4) {
+    const float d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+    result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (; i < dim; i++) {
+    const float d0 = a[i] - b[i];
+    result += d0 * d0;
+  }
+  return result;
+}
+
+// ---- ring-key kNN: grid (X, nq), block 256; each thread scans rows x*256+tid, stride X*256 -------------------
+__global__ void __launch_bounds__(256) sc_ringkey_kernel(const float *__restrict__ keys, const int *__restrict__ ids, int n_rows, int dim,
+                                                        const float *__restrict__ queries, int max_id, u64 *__restrict__ scratch) {
+  __shared__ float qk[64];
+  __shared__ u64 wl[8][kScTopK];
+  const int q = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < dim) qk[tid] = queries[(size_t)q * dim + tid];
+  __syncthreads();
+  TopK t;
+  t.init();
+  float row[64];
+  for (int r = blockIdx.x * 256 + tid; r < n_rows; r += gridDim.x * 256) {
+    const int id = ids[r];
+    if (id >= max_id) continue;
+    const float *kr = keys + (size_t)r * dim;
+    float result = 0.f;
+    int i = 0;
+    for (; i + 3 < dim; i += 4) {
+      const float4 kv = __ldg(reinterpret_cast<const float4 *>(kr + i));
+      const float d0 = qk[i] - kv.x, d1 = qk[i + 1] - kv.y, d2 = qk[i + 2] - kv.z, d3 = qk[i + 3] - kv.w;
+      result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    for (; i < dim; i++) {
+      const float d0 = qk[i] - __ldg(kr + i);
+      result += d0 * d0;
+    }
+    t.insert(make_key(result, id));
+  }
+  (void)row;
+  u64 out[kScTopK];
+  warp_merge(t, out);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) wl[warp][i] = out[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    TopK m;
+    m.init();
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) m.insert(wl[lane][i]);
+    }
+    warp_merge(m, out);
+    if (lane == 0) {
+      u64 *dst = scratch + ((size_t)q * gridDim.x + blockIdx.x) * kScTopK;
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) dst[i] = out[i];
+    }
+  }
+}
+
+// ---- final merge: grid nq, block 32: scratch[q][nlists][K] -> out[q][K] ---------------------------------------
+__global__ void __launch_bounds__(32) sc_merge_kernel(const u64 *__restrict__ scratch, int nlists, u64 *__restrict__ out) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  TopK t;
+  t.init();
+  const u64 *src = scratch + (size_t)q * nlists * kScTopK;
+  for (int i = lane; i < nlists * kScTopK; i += 32) t.insert(src[i]);
+  u64 o[kScTopK];
+  warp_merge(t, o);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) out[(size_t)q * kScTopK + i] = o[i];
+  }
+}
+
+// ---- sector-cosine scan: persistent grid, 16 warps per CTA, warp streams rows, lane q owns query q ------------
+// dynamic smem: qs[nqc][n_cells] floats followed by qkeys[nqc][key_dim]
+__global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__restrict__ sigs, const float *__restrict__ keys,
+                                                              const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
+                                                              const float *__restrict__ q_sigs, const float *__restrict__ q_keys, int nqc,
+                                                              float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch) {
+  extern __shared__ __align__(16) float smem[];
+  float *qs = smem;
+  float *qk = smem + (size_t)nqc * n_cells;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < nqc * n_cells / 4; i += kScanThreads)
+    reinterpret_cast<float4 *>(qs)[i] = __ldg(reinterpret_cast<const float4 *>(q_sigs) + i);
+  for (int i = tid; i < nqc * key_dim; i += kScanThreads) qk[i] = q_keys[i];
+  __syncthreads();
+
+  const int n4 = n_cells / 4;  // float4 per row (300)
+  constexpr int R4 = 10;       // float4 per lane per row: supports n_cells <= 1280
+  TopK top;
+  top.init();
+  const int gw = blockIdx.x * kScanWarps + warp, nw = gridDim.x * kScanWarps;
+  for (int r0 = gw * 2; r0 < n_rows; r0 += nw * 2) {
+    const bool has1 = r0 + 1 < n_rows;
+    const float4 *ra = reinterpret_cast<const float4 *>(sigs + (size_t)r0 * n_cells);
+    const float4 *rb = reinterpret_cast<const float4 *>(sigs + (size_t)(has1 ? r0 + 1 : r0) * n_cells);
+    float4 a[R4], b[R4];
+#pragma unroll
+    for (int j = 0; j < R4; j++) {
+      const int c = lane + 32 * j;
+      a[j] = c < n4 ? __ldcs(ra + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      b[j] = c < n4 ? __ldcs(rb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int ida = ids[r0], idb = has1 ? ids[r0 + 1] : 0x7fffffff;
+    float my_da = 0.f, my_db = 0.f;  // lane q keeps the distances of query q
+    for (int q = 0; q < nqc; q++) {
+      const float4 *qv = reinterpret_cast<const float4 *>(qs + (size_t)q * n_cells);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int j = 0; j < R4; j++) {
+        const int c = lane + 32 * j;
+        if (c < n4) {
+          const float4 x = qv[c];
+          sa = fmaf(a[j].x, x.x, sa); sa = fmaf(a[j].y, x.y, sa); sa = fmaf(a[j].z, x.z, sa); sa = fmaf(a[j].w, x.w, sa);
+          sb = fmaf(b[j].x, x.x, sb); sb = fmaf(b[j].y, x.y, sb); sb = fmaf(b[j].z, x.z, sb); sb = fmaf(b[j].w, x.w, sb);
+        }
+      }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, m);
+        sb += __shfl_xor_sync(0xffffffffu, sb, m);
+      }
+      if (lane == q) {
+        my_da = (1.0f - sa / sc_width) / 2.0f;
+        my_db = (1.0f - sb / sc_width) / 2.0f;
+      }
+    }
+    if (lane < nqc) {
+      bool oka = ida < max_id, okb = has1 && idb < max_id;
+      if (ringkey_thres >= 0.f) {
+        if (oka) oka = flann_l2(qk + lane * key_dim, keys + (size_t)r0 * key_dim, key_dim) < ringkey_thres;
+        if (okb) okb = flann_l2(qk + lane * key_dim, keys + (size_t)(r0 + 1) * key_dim, key_dim) < ringkey_thres;
+      }
+      if (oka) top.insert(make_key(my_da, r0));
+      if (okb) top.insert(make_key(my_db, r0 + 1));
+    }
+  }
+  // CTA merge: reuse the query smem for the per-warp lists [warp][q][K]
+  __syncthreads();
+  u64 *lists = reinterpret_cast<u64 *>(smem);
+  if (lane < nqc) {
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) lists[((size_t)warp * kQChunk + lane) * kScTopK + i] = top.k[i];
+  }
+  __syncthreads();
+  if (tid < nqc) {
+    TopK m;
+    m.init();
+    for (int wv = 0; wv < kScanWarps; wv++) {
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + tid) * kScTopK + i]);
+    }
+    u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+  }
+}
+
+// ---- exact re-score -------------------------------------------------------------------------------------------
+// search_sc's arithmetic (search_place.h:71-79) on dense descriptors: float cur_prod += double(q)*double(d) over the
+// cells where both are occupied, in ascending cell order; diff = (1 - cur_prod / sc_width) / 2.0.  The chain of
+// float roundings is inherently serial; a warp loads 32 cells at a time (coalesced), forms the exact double
+// products in parallel and walks only the non-zero ones in order (every lane carries the same running value).
+__device__ __forceinline__ float exact_sc_diff(const float *__restrict__ q, const float *__restrict__ d, int n_cells, int sc_width, int lane) {
+  float cur = 0.f;
+  for (int base = 0; base < n_cells; base += 32) {
+    const int k = base + lane;
+    const float qv = k < n_cells ? q[k] : 0.f;
+    const float dv = k < n_cells ? __ldg(d + k) : 0.f;
+    const double p = __dmul_rn((double)qv, (double)dv);
+    unsigned m = __ballot_sync(0xffffffffu, qv != 0.f && dv != 0.f);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const double pl = __shfl_sync(0xffffffffu, p, l);
+      cur = __double2float_rn(__dadd_rn((double)cur, pl));
+    }
+  }
+  const float t = 1.0f - cur / (float)sc_width;
+  return __double2float_rn((double)t / 2.0);
+}
+
+// one CTA per query, one warp per top-K entry: exact distance of each survivor, then the per-query best as a
+// packed (ordered dist bits << 32 | GLOBAL id) key — the value a multi-GPU min-reduction combines.
+__global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64 *__restrict__ topk, const float *__restrict__ sigs,
+                                                                       const int *__restrict__ ids, const float *__restrict__ q_sigs,
+                                                                       int n_cells, int sc_width, u64 *__restrict__ exact_keys,
+                                                                       u64 *__restrict__ best) {
+  __shared__ u64 sk[kScTopK];
+  const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u64 key = topk[(size_t)q * kScTopK + warp];
+  u64 out = kKeyMax;
+  if (key != kKeyMax) {
+    const int row = (int)(unsigned)(key & 0xffffffffull);
+    const float diff = exact_sc_diff(q_sigs + (size_t)q * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane);
+    out = make_key(diff, ids[row]);
+  }
+  if (lane == 0) {
+    sk[warp] = out;
+    if (exact_keys) exact_keys[(size_t)q * kScTopK + warp] = out;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 b = sk[0];
+#pragma unroll
+    for (int i = 1; i < kScTopK; i++) b = sk[i] < b ? sk[i] : b;
+    best[q] = b;
+  }
+}
+
+// explicit (query, row) pairs: diff per pair (row < 0 -> skipped, diff = +inf)
+__global__ void __launch_bounds__(256) sc_rescore_pairs_kernel(const int *__restrict__ pair_q, const int *__restrict__ pair_row, int npairs,
+                                                               const float *__restrict__ sigs, const float *__restrict__ q_sigs, int n_cells,
+                                                               int sc_width, float *__restrict__ diff_out) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= npairs) return;
+  const int row = pair_row[p];
+  float diff = __int_as_float(0x7f800000);
+  if (row >= 0) diff = exact_sc_diff(q_sigs + (size_t)pair_q[p] * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane);
+  if (lane == 0) diff_out[p] = diff;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+constexpr int kRingGridX = 64;
+
+size_t sc_scratch_bytes(int nq) {
+  const int lists = num_sms() > kRingGridX ? num_sms() : kRingGridX;
+  return (size_t)(nq > kQChunk ? nq : kQChunk) * lists * kScTopK * sizeof(u64);
+}
+
+cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
+                              unsigned long long *out, unsigned long long *scratch, cudaStream_t stream) {
+  if (dim > 64 || nq < 1) return cudaErrorInvalidValue;
+  int gx = (n_rows + 255) / 256;
+  if (gx > kRingGridX) gx = kRingGridX;
+  if (gx < 1) gx = 1;
+  sc_ringkey_kernel<<<dim3(gx, nq), 256, 0, stream>>>(keys, ids, n_rows, dim, queries, max_id, scratch);
+  sc_merge_kernel<<<nq, 32, 0, stream>>>(scratch, gx, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
+                           const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *out,
+                           unsigned long long *scratch, cudaStream_t stream) {
+  if (n_cells % 4 != 0 || n_cells > 1280 || key_dim > 64) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  const size_t smem_max = (size_t)kQChunk * n_cells * 4 + kQChunk * key_dim * 4;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = num_sms();
+  for (int q0 = 0; q0 < nq; q0 += kQChunk) {
+    const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
+    size_t smem = (size_t)nqc * n_cells * 4 + (size_t)nqc * key_dim * 4;
+    const size_t lists_bytes = (size_t)kScanWarps * kQChunk * kScTopK * sizeof(u64);
+    if (smem < lists_bytes) smem = lists_bytes;
+    sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
+                                                         q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch);
+    sc_merge_kernel<<<nqc, 32, 0, stream>>>(scratch, grid, out + (size_t)q0 * kScTopK);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const float *sigs, const int *ids, const float *q_sigs, int nq, int n_cells,
+                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, cudaStream_t stream) {
+  if (nq < 1) return cudaSuccess;
+  sc_rescore_topk_kernel<<<nq, 32 * kScTopK, 0, stream>>>(topk, sigs, ids, q_sigs, n_cells, sc_width, exact_keys, best);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const float *sigs, const float *q_sigs, int n_cells,
+                                    int sc_width, float *diff_out, cudaStream_t stream) {
+  if (npairs < 1) return cudaSuccess;
+  sc_rescore_pairs_kernel<<<(npairs + 7) / 8, 256, 0, stream>>>(pair_q, pair_row, npairs, sigs, q_sigs, n_cells, sc_width, diff_out);
+  return cudaGetLastError();
+}
+
+}  // namespace dslam

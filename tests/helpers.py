@@ -1,0 +1,70 @@
+"""Shared builders for the parity tests: one synthetic tracking problem evaluated by the CPU oracle."""
+import numpy as np
+
+import oracle as orc
+from direct_stereo_slam_b200 import synthetic as syn
+
+IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+
+
+def cam_K(cfg):
+    return np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+
+
+class OracleCase:
+    """Keyframe + new left frame + right frame of one synthetic scene, with the oracle's pyramids and template."""
+
+    def __init__(self, o, cfg_name="tiny", seed=3, motion_scale=1.0, scale_error=1.0, levels=None):
+        self.o = o
+        self.case = c = syn.make_tracking_case(cfg_name, seed, motion_scale=motion_scale, scale_error=scale_error)
+        cfg = self.cfg = c["cfg"]
+        self.w, self.h = cfg["w"], cfg["h"]
+        self.levels = orc.pyr_levels_used(self.w, self.h) if levels is None else levels
+        self.K = cam_K(cfg)
+        self.T_stereo = syn.t_stereo(cfg)
+        self.dIp_ref, self.abs_ref = o.make_images(c["img_ref"], self.levels)
+        self.dIp_new, self.abs_new = o.make_images(c["img_new"], self.levels)
+        self.dIp_right, _ = o.make_images(c["img_right"], self.levels)
+        self.trk = o.tracker(self.w, self.h, self.levels, self.K, self.K, self.T_stereo)
+        self.trk.make_coarse_depth(c["pu"], c["pv"], c["pid"], c["pw"], self.dIp_ref)
+        self.trk.set_ref_aff(1.0, 0.0, 0.0)
+        self.trk.set_new_frame(self.dIp_new, 1.0)
+        self.trk.set_right_frame(self.dIp_right)
+        self.ref_levels = [self.trk.get_ref_level(l) for l in range(self.levels)]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+class GpuCase:
+    """The device twin of an OracleCase: frames built by the CUDA pyramid, tracker fed with the oracle's template."""
+
+    def __init__(self, session, oc, template="upload"):
+        from direct_stereo_slam_b200 import api
+
+        self.api = api
+        self.oc = oc
+        c = oc.case
+        self.f_ref = api.FrameHessian(session, oc.w, oc.h, oc.levels)
+        self.f_new = api.FrameHessian(session, oc.w, oc.h, oc.levels)
+        self.f_right = api.FrameHessian(session, oc.w, oc.h, oc.levels)
+        self.f_ref.makeImages(c["img_ref"], host=False)
+        self.f_new.makeImages(c["img_new"], host=False)
+        self.f_right.makeImages(c["img_right"], host=False)
+        self.trk = api.TrackerAndScaler(session, oc.w, oc.h, oc.T_stereo.reshape(-1), oc.K, K0=oc.K, levels=oc.levels)
+        if template == "upload":
+            self.trk.setCoarseTrackingRefArrays(oc.ref_levels, ref_frame=self.f_ref)
+        else:
+            self.pc_n = self.trk.setCoarseTrackingRef(self.f_ref, c["pu"], c["pv"], c["pid"], c["pw"])
+
+    def close(self):
+        for x in (self.trk, self.f_ref, self.f_new, self.f_right):
+            x.close()
+
+
+def perturbed_pose(o, pose7, rng, trans=0.01, rot=0.002):
+    xi = np.concatenate([rng.normal(0, trans, 3), rng.normal(0, rot, 3)])
+    return o.se3_mul(o.se3_exp(xi), pose7)

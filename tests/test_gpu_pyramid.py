@@ -1,0 +1,93 @@
+"""CUDA pyramid (dslam_frame_make_images) vs the oracle's FrameHessian::makeImages restatement: bit-exact."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from direct_stereo_slam_b200 import api
+from direct_stereo_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _image(w, h, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 128 + 60 * np.sin(xx * 0.11 + rng.uniform(0, 6)) * np.cos(yy * 0.07) + rng.normal(0, 8, (h, w))
+    return np.clip(img, 0, 255).astype(np.float32)
+
+
+def _compare(fr, dIp_o, abs_o, levels, w, h):
+    off = orc.level_offsets(w, h, levels)
+    for l in range(levels):
+        wl, hl = w >> l, h >> l
+        d = fr.dIp(l)
+        a = fr.absSquaredGrad(l)
+        do = dIp_o[off[l]:off[l + 1]].reshape(hl, wl, 3)
+        ao = abs_o[off[l]:off[l + 1]].reshape(hl, wl)
+        # intensity: every pixel; gradients: rows 1..h-2 (the reference leaves the first/last row uninitialised)
+        assert np.array_equal(d[..., 0].view(np.uint32), do[..., 0].view(np.uint32)), "I level %d" % l
+        assert np.array_equal(d[1:-1, :, 1:].view(np.uint32), do[1:-1, :, 1:].view(np.uint32)), "dx/dy level %d" % l
+        assert np.array_equal(a[1:-1].view(np.uint32), ao[1:-1].view(np.uint32)), "absSquaredGrad level %d" % l
+        assert not d[0, :, 1:].any() and not d[-1, :, 1:].any() and not a[0].any() and not a[-1].any()
+
+
+@pytest.mark.parametrize("w,h,levels", [(320, 192, 3), (1232, 368, 5), (1024, 768, 5), (154, 46, 2), (77, 23, 1), (150, 94, 2),
+                                        (1920, 1200, 5), (1920, 1184, 6)])
+def test_make_images_bit_exact(session, oracle, w, h, levels):
+    img = _image(w, h, w + h)
+    dIp_o, abs_o = oracle.make_images(img, levels)
+    fr = api.FrameHessian(session, w, h, levels)
+    fr.makeImages(img)
+    _compare(fr, dIp_o, abs_o, levels, w, h)
+    # a second frame through the same object (buffers are reused) and the download-after-build path
+    img2 = _image(w, h, 7)
+    dIp_o, abs_o = oracle.make_images(img2, levels)
+    fr.upload(img2)
+    fr.build()
+    fr.download()
+    _compare(fr, dIp_o, abs_o, levels, w, h)
+    fr.close()
+
+
+def test_make_images_gamma_weight(session, oracle):
+    """HCalib != 0 && setting_gammaWeightsPixelSelect == 1: absSquaredGrad *= (B[c+1]-B[c])^2."""
+    w, h, levels = 640, 480, 5
+    img = _image(w, h, 11)
+    B = (255.0 * (np.arange(256) / 255.0) ** 0.8).astype(np.float32)
+    dIp_o, abs_o = oracle.make_images(img, levels, B256=B)
+    fr = api.FrameHessian(session, w, h, levels)
+    fr.makeImages(img, B256=B)
+    _compare(fr, dIp_o, abs_o, levels, w, h)
+    fr.close()
+
+
+def test_non_finite_input(session, oracle):
+    """non-finite gradients are zeroed (HessianBlocks.cpp:174-177)."""
+    w, h, levels = 128, 96, 2
+    img = _image(w, h, 5)
+    img[40, 50] = np.inf
+    img[10, 0] = np.nan
+    dIp_o, abs_o = oracle.make_images(img, levels)
+    fr = api.FrameHessian(session, w, h, levels)
+    fr.makeImages(img)
+    off = orc.level_offsets(w, h, levels)
+    for l in range(levels):
+        wl, hl = w >> l, h >> l
+        d = fr.dIp(l)[1:-1]
+        do = dIp_o[off[l]:off[l + 1]].reshape(hl, wl, 3)[1:-1]
+        assert np.array_equal(np.isnan(d), np.isnan(do))
+        m = ~np.isnan(do)
+        assert np.array_equal(d[m], do[m])
+    fr.close()
+
+
+def test_synthetic_scene_frames(session, oracle):
+    c = syn.make_tracking_case("tiny", 2)
+    cfg = c["cfg"]
+    levels = orc.pyr_levels_used(cfg["w"], cfg["h"])
+    for key in ("img_ref", "img_new", "img_right"):
+        dIp_o, abs_o = oracle.make_images(c[key], levels)
+        fr = api.FrameHessian(session, cfg["w"], cfg["h"], levels)
+        fr.makeImages(c[key])
+        _compare(fr, dIp_o, abs_o, levels, cfg["w"], cfg["h"])
+        fr.close()

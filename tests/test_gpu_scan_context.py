@@ -1,0 +1,180 @@
+"""Scan-Context database scan vs the oracle's restatement of search_ringkey / search_sc: argmin index bit-exact,
+distance bit-exact (the survivors are re-scored on the device in the reference's float += double*double order)."""
+import numpy as np
+import pytest
+
+from direct_stereo_slam_b200 import api
+from direct_stereo_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_query(oracle, qs, db, candidates=None):
+    idx, diff = [], []
+    for q in qs:
+        i, d = oracle.search_sc_dense(q, db, candidates)
+        idx.append(i)
+        diff.append(d)
+    return np.array(idx, np.int32), np.array(diff, np.float32)
+
+
+@pytest.fixture(scope="module")
+def small_db(session):
+    sig, key = syn.make_sc_database(3000, 7)
+    db = api.ScanContextDB(session, 4096)
+    db.add(key[:1000], sig[:1000])
+    db.add(key[1000:], sig[1000:], global_ids=np.arange(1000, 3000))
+    yield db, sig, key
+    db.close()
+
+
+@pytest.mark.parametrize("nq", [1, 5, 32, 33, 70])
+def test_query_argmin_bit_exact(small_db, oracle, nq):
+    db, sig, key = small_db
+    qs, qk, truth = syn.make_sc_queries(sig, key, nq, 100 + nq)
+    idx, diff = db.query(qs)
+    idx_o, diff_o = _oracle_query(oracle, qs, sig)
+    assert np.array_equal(idx, idx_o)
+    assert np.array_equal(diff.view(np.uint32), diff_o.view(np.uint32))
+    known = truth >= 0
+    assert np.array_equal(idx[known], truth[known])  # perturbed revisits find their row
+
+
+def test_query_max_id_and_ringkey_gate(small_db, oracle):
+    db, sig, key = small_db
+    qs, qk, truth = syn.make_sc_queries(sig, key, 16, 5)
+    # only ids < max_id compete (the LOOP_MARGIN delay of search_ringkey, search_place.h:42-56)
+    idx, diff = db.query(qs, max_id=1500)
+    idx_o, diff_o = _oracle_query(oracle, qs, sig[:1500])
+    assert np.array_equal(idx, idx_o) and np.array_equal(diff.view(np.uint32), diff_o.view(np.uint32))
+    # ring-key gate: rows whose squared-L2 ring-key distance is >= thres are skipped
+    thres = 0.02
+    idx, diff = db.query(qs, ringkeys=qk, ringkey_thres=thres)
+    for q in range(3):
+        d2 = np.array([oracle.search_ringkey(qk[q], key[r:r + 1], k=1, thres=np.inf)[1][0] for r in range(len(key))])
+        cand = np.nonzero(d2 < thres)[0].astype(np.int32)
+        if len(cand) == 0:
+            assert idx[q] == -1
+        else:
+            i_o, d_o = oracle.search_sc_dense(qs[q], sig, cand)
+            assert idx[q] == i_o and diff[q] == np.float32(d_o)
+
+
+def test_query_ties_go_to_lowest_id(session, oracle):
+    sig, key = syn.make_sc_database(64, 3)
+    sig = np.concatenate([sig, sig[10:11], sig[10:11], sig[10:11]])  # rows 64, 65, 66 duplicate row 10
+    key = np.concatenate([key, key[10:11], key[10:11], key[10:11]])
+    db = api.ScanContextDB(session, 128)
+    db.add(key, sig)
+    idx, diff = db.query(sig[10:11])
+    assert idx[0] == 10
+    i_o, d_o = oracle.search_sc_dense(sig[10], sig)
+    assert i_o == 10 and diff[0] == np.float32(d_o)
+    # more duplicates than the device keeps per query (K = 8): still the lowest id
+    sig2 = np.repeat(sig[3:4], 40, 0)
+    db2 = api.ScanContextDB(session, 64)
+    db2.add(np.repeat(key[3:4], 40, 0), sig2, global_ids=np.arange(100, 140))
+    idx, _ = db2.query(sig[3:4])
+    assert idx[0] == 100
+    db.close()
+    db2.close()
+
+
+def test_empty_and_tiny_database(session):
+    db = api.ScanContextDB(session, 16)
+    sig, key = syn.make_sc_database(3, 1)
+    idx, diff = db.query(sig[:2])
+    assert np.array_equal(idx, [-1, -1]) and np.allclose(diff, 1.1)
+    db.add(key[:1], sig[:1])
+    idx, diff = db.query(sig[:2])
+    assert np.array_equal(idx, [0, 0])
+    cand, dist = db.search_ringkey(key[:2], k=3, thres=0.1)
+    assert cand[0, 0] == 0 and dist[0, 0] == 0 and np.all(cand[:, 1:] == -1)
+    db.close()
+
+
+def test_search_ringkey_exact_knn(small_db, oracle):
+    db, sig, key = small_db
+    rng = np.random.default_rng(2)
+    qk = key[rng.integers(0, len(key), 20)] + rng.normal(0, 0.03, (20, 20)).astype(np.float32)
+    cand, dist = db.search_ringkey(qk, k=3, thres=0.1)
+    for q in range(20):
+        c_o, d_o = oracle.search_ringkey(qk[q], key, k=3, thres=0.1)
+        n = len(c_o)
+        assert np.array_equal(cand[q, :n], c_o) and np.all(cand[q, n:] == -1)
+        assert np.array_equal(dist[q, :n].view(np.uint32), d_o.view(np.uint32))
+    cand, dist = db.search_ringkey(qk, k=3, thres=0.1, max_id=500)
+    for q in range(20):
+        c_o, d_o = oracle.search_ringkey(qk[q], key[:500], k=3, thres=0.1)
+        assert np.array_equal(cand[q, :len(c_o)], c_o)
+
+
+def test_search_sc_reference_semantics(session, oracle):
+    """search_sc over explicit candidates, fed in the reference's sparse (index, double) form."""
+    rng = np.random.default_rng(9)
+    db = api.ScanContextDB(session, 256)
+    ptr, idxs, vals, dense = [0], [], [], []
+    for r in range(200):
+        pts = rng.normal(0, 12, (3000, 3))
+        rk, si, sv, _ = oracle.sc_generate(pts)
+        sv32 = sv.astype(np.float32).astype(np.float64)  # the database stores fp32
+        db.add_sparse(rk, si, sv)
+        idxs.append(si)
+        vals.append(sv32)
+        ptr.append(ptr[-1] + len(si))
+        d = np.zeros(1200, np.float32)
+        d[si] = sv.astype(np.float32)
+        dense.append(d)
+    idxs, vals, dense = np.concatenate(idxs), np.concatenate(vals), np.stack(dense)
+    for q in range(10):
+        cands = rng.choice(200, 3, replace=False).astype(np.int32)
+        qd = dense[rng.integers(0, 200)] * 1.0
+        qd[rng.integers(0, 1200, 50)] = 0
+        qi = np.nonzero(qd)[0].astype(np.int32)
+        i_o, d_o = oracle.search_sc(qi, qd[qi].astype(np.float64), ptr, idxs, vals, cands)
+        i_g, d_g = db.search_sc(qd, cands)
+        assert i_g[0] == i_o and d_g[0] == np.float32(d_o)
+    # skipped candidates (-1) and the "first candidate, 1.1" default
+    i_g, d_g = db.search_sc(dense[0], np.array([-1, 5, -1], np.int32))
+    i_o, d_o = oracle.search_sc_dense(dense[0], dense, np.array([5], np.int32))
+    assert i_g[0] == 5 and d_g[0] == np.float32(d_o)
+    db.close()
+
+
+def test_sharded_query_equals_single(session, oracle):
+    """Two shards (row i on shard i % 2) combined by min over packed keys == the unsharded answer."""
+    sig, key = syn.make_sc_database(2001, 21)
+    qs, qk, _ = syn.make_sc_queries(sig, key, 24, 8)
+    shards = []
+    for r in range(2):
+        rows = api.shard_rows(len(sig), 2, r)
+        db = api.ScanContextDB(session, 1024)
+        db.add(key[rows], sig[rows], global_ids=rows)
+        shards.append(db)
+    keys = np.minimum(shards[0].query_keys(qs), shards[1].query_keys(qs))
+    diff, idx = api.unpack_key(keys)
+    idx_o, diff_o = _oracle_query(oracle, qs, sig)
+    assert np.array_equal(idx, idx_o) and np.array_equal(diff.view(np.uint32), diff_o.view(np.uint32))
+    assert np.array_equal(api.pack_key(diff, idx), keys)
+    for db in shards:
+        db.close()
+
+
+def test_full_size_database_properties(session):
+    """BASELINE config 4 size (100k descriptors): self-queries return themselves with distance ~0, perturbed revisits
+    return their source row, and the result does not depend on the query batch size."""
+    n = 100_000
+    sig, key = syn.make_sc_database(n, 2024)
+    db = api.ScanContextDB(session, n)
+    db.add(key, sig)
+    rows = np.array([0, 1, 4999, 50_000, 99_999])
+    idx, diff = db.query(sig[rows])
+    assert np.array_equal(idx, rows) and np.all(np.abs(diff) < 1e-6)
+    qs, qk, truth = syn.make_sc_queries(sig, key, 64, 77)
+    idx64, diff64 = db.query(qs)
+    known = truth >= 0
+    assert np.array_equal(idx64[known], truth[known])
+    idx1 = np.array([db.query(qs[i:i + 1])[0][0] for i in range(0, 64, 9)])
+    assert np.array_equal(idx1, idx64[::9])
+    assert 0.0 < db.last_scan_ms() < 1000.0
+    db.close()
