@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py — stereo frames/s of the photometric Gauss-Newton hot path at KITTI size on B200 (BASELINE.json configs[1]).
+
+One "step" = one stereo frame for each of S independent stereo streams resident on the GPU, every frame doing the full
+per-keyframe work of the reference's path:
+    FrameHessian::makeImages(left) -> TrackerAndScaler::trackNewestCoarse -> makeImages(right) -> optimizeScale(seed 1.0)
+The S streams advance in lock step: every Levenberg-Marquardt round of all streams is ONE launch of the fused residual /
+Jacobian kernel.  Workload: synthetic stereo pairs 1232x368 (KITTI 1241x376 after the calibration crop), 2000 active
+points -> ~10k template pixels at level 0, 5 pyramid levels.
+
+  value  : frames/s with the raw images already resident in HBM (pyramid build + tracking + scale optimisation timed)
+  e2e    : the same through the C ABI with HOST buffers: pinned-host images uploaded inside the timed region, the left
+           pyramid mirrored back into the reference's host layouts (dIp / absSquaredGrad, what untouched DSO code reads),
+           poses / scales returned to the host
+  roofline : fused pose residual kernel, algorithmic bytes (64 B per template point per evaluation) over the
+           CUDA-event duration of every launch, measured live in a separate profiled pass of the same steps
+  cpu_baseline : the CPU oracle (-O3 -march=native, the reference's SSE accumulation order) on ONE core — the reference's
+           tracker / scale optimiser / pyramid are single-threaded
+  --impl reference : the same CPU path on all host cores (independent frames per thread)
+Multi-GPU (--gpus N under torchrun): the tracking path does not shard — N independent replicas (weak scaling, no
+collective); the Scan-Context database scan is the sharded piece and is reported in the "scan_context" object of the same
+JSON line (100k descriptors row-sharded over the N ranks, one NCCL all-reduce(min) of packed keys per query batch).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from direct_stereo_slam_b200 import synthetic as syn  # noqa: E402
+
+WORKLOAD = "kitti_1232x368_tracker+scaleopt_2000pts_5lvl"
+BYTES_PER_POINT = 64  # 16 B template record + 4 taps x 12 B
+IDENT7 = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the pose kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("pose_eval_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], None, set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------------
+def make_cases(n_cases, seed0=1000):
+    """Distinct synthetic stereo problems (keyframe, two new left frames, right frame, active points with a scale error)."""
+    cases = []
+    for k in range(n_cases):
+        rng = np.random.default_rng(seed0 + k)
+        c = syn.make_tracking_case("kitti", seed0 + k, motion_scale=1.0, scale_error=float(rng.uniform(0.8, 1.25)))
+        # a second new frame of the same keyframe (other motion) so consecutive steps of a stream see different images
+        R2, t2 = syn.se3_exp_mat(c["xi_true"] * 0.6)
+        c["img_new2"], _ = c["scene"].render(R2, t2, noise_seed=(seed0 + k) * 3 + 7, aff=c["aff_true"])
+        c["pose_init"] = [syn.pose7(*syn.se3_exp_mat(c["xi_true"] * 0.9)), syn.pose7(*syn.se3_exp_mat(c["xi_true"] * 0.6 * 0.9))]
+        cases.append(c)
+    return cases
+
+
+class GpuStreams:
+    """S independent stereo streams of one rank (device twins of S TrackerAndScaler objects and their frames)."""
+
+    def __init__(self, api, session, cases, n_streams):
+        self.api, self.s = api, session
+        cfg = cases[0]["cfg"]
+        self.w, self.h = cfg["w"], cfg["h"]
+        self.levels = api.pyr_levels_used(self.w, self.h)
+        K = np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+        T = syn.t_stereo(cfg).reshape(-1)
+        self.n = n_streams
+        self.trk, self.f_new, self.f_right, self.case_of = [], [], [], []
+        self.h_new, self.h_right = [], []
+        ref = api.FrameHessian(session, self.w, self.h, self.levels)
+        for i in range(n_streams):
+            c = cases[i % len(cases)]
+            self.case_of.append(c)
+            t = api.TrackerAndScaler(session, self.w, self.h, T, K, K0=K, levels=self.levels)
+            ref.makeImages(c["img_ref"], host=False)
+            t.setCoarseTrackingRef(ref, c["pu"], c["pv"], c["pid"], c["pw"])
+            self.trk.append(t)
+            fn = [api.FrameHessian(session, self.w, self.h, self.levels) for _ in range(2)]
+            fr = api.FrameHessian(session, self.w, self.h, self.levels)
+            # pinned host copies of the inputs (e2e) and pinned host mirrors of the left pyramid
+            hn = [session.pinned((self.h, self.w)) for _ in range(2)]
+            hn[0][:] = c["img_new"]
+            hn[1][:] = c["img_new2"]
+            hr = session.pinned((self.h, self.w))
+            hr[:] = c["img_right"]
+            for f in fn:
+                f.alloc_host(pinned=True)
+            self.f_new.append(fn)
+            self.f_right.append(fr)
+            self.h_new.append(hn)
+            self.h_right.append(hr)
+        ref.close()
+        session.sync()
+        self.pc_n0 = [t.ref_level(0)[0].size for t in self.trk]
+
+    def upload_inputs(self):
+        """Raw images into HBM (outside the timed region of the device-resident measurement)."""
+        for i in range(self.n):
+            for v in range(2):
+                self.f_new[i][v].upload(self.h_new[i][v])
+            self.f_right[i].upload(self.h_right[i])
+        self.s.sync()
+
+    def step(self, k, e2e):
+        api = self.api
+        v = k & 1
+        left = [self.f_new[i][v] for i in range(self.n)]
+        if e2e:
+            for i in range(self.n):
+                left[i].makeImages(self.h_new[i][v], host=True, wait=False)  # H2D + build + async D2H of the host mirrors
+        else:
+            for f in left:
+                f.build()
+        poses = np.stack([self.case_of[i]["pose_init"][v] for i in range(self.n)])
+        ok, poses, affs, last = api.track_newest_coarse_batch(self.trk, left, poses, np.zeros((self.n, 2)), self.levels - 1)
+        if e2e:
+            for i in range(self.n):
+                self.f_right[i].makeImages(self.h_right[i], host=False)
+        else:
+            for f in self.f_right:
+                f.build()
+        rmse, scales = api.optimize_scale_batch(self.trk, self.f_right, np.ones(self.n, np.float32), self.levels - 1)
+        if e2e:
+            for f in left:
+                f.wait_host()
+        return ok, poses, scales, rmse
+
+    def h2d_bytes(self):
+        return self.n * 2 * self.w * self.h * 4
+
+    def d2h_bytes(self):
+        tot = sum((self.w >> l) * (self.h >> l) for l in range(self.levels))
+        return self.n * (tot * 16 + 7 * 8 + 2 * 8 + 5 * 8 + 4 + 4)
+
+
+def timed_steps(streams, session, steps, warmup, e2e, dist_barrier):
+    for k in range(warmup):
+        streams.step(k, e2e)
+    session.sync()
+    dist_barrier()
+    l0 = session.launch_count()
+    session.mark(0)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        streams.step(warmup + k, e2e)
+    session.mark(1)
+    session.sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = session.elapsed_ms()
+    dist_barrier()
+    # the LM loop is host-sequenced: the device span (CUDA events) and the host span agree to a few microseconds; take
+    # the larger so that no host-side work of a step is left outside the number
+    return max(dev_ms, wall_ms), session.launch_count() - l0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arms (oracle = restatement of the reference's CPU algorithm; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+class CpuStream:
+    def __init__(self, orc_mod, o, case):
+        cfg = case["cfg"]
+        self.o, self.case = o, case
+        self.w, self.h = cfg["w"], cfg["h"]
+        self.levels = orc_mod.pyr_levels_used(self.w, self.h)
+        K = np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+        self.trk = o.tracker(self.w, self.h, self.levels, K, K, syn.t_stereo(cfg))
+        dIp_ref, _ = o.make_images(case["img_ref"], self.levels)
+        self.trk.make_coarse_depth(case["pu"], case["pv"], case["pid"], case["pw"], dIp_ref)
+        self.trk.set_ref_aff(1.0, 0.0, 0.0)
+
+    def frame(self, k):
+        v = k & 1
+        c = self.case
+        dIp_new, _ = self.o.make_images(c["img_new"] if v == 0 else c["img_new2"], self.levels)
+        self.trk.set_new_frame(dIp_new, 1.0)
+        ok, pose, aff, last, flow = self.trk.track_newest_coarse(0, c["pose_init"][v], (0.0, 0.0), self.levels - 1)
+        dIp_r, _ = self.o.make_images(c["img_right"], self.levels)
+        self.trk.set_right_frame(dIp_r)
+        rmse, scale = self.trk.optimize_scale(0, 1.0, self.levels - 1)
+        return ok, pose, scale
+
+
+def cpu_single_core(cases, budget_s=12.0):
+    import oracle as orc
+
+    o = orc.Oracle(native=True)
+    st = CpuStream(orc, o, cases[0])
+    st.frame(0)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        st.frame(n)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 400:
+            break
+    ev, gs = st.trk.counters()
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "%d stereo frames of %s on one core (oracle -O3 -march=native, SSE accumulation order), %.1f s" % (n, WORKLOAD, dt)}
+
+
+def cpu_all_cores(cases, steps, warmup, threads):
+    import oracle as orc
+
+    o = orc.Oracle(native=True)
+    sts = [CpuStream(orc, o, cases[i % len(cases)]) for i in range(threads)]
+
+    def run(k0, k1):
+        def work(st):
+            for k in range(k0, k1):
+                st.frame(k)
+        th = [threading.Thread(target=work, args=(st,)) for st in sts]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    run(0, warmup)
+    dt = run(warmup, warmup + steps)
+    return threads * steps / dt, dt
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Scan-Context shard (the only piece that shards): 100k descriptors over the ranks, query batch of 32
+# ----------------------------------------------------------------------------------------------------------------------
+def bench_scan_context(api, session, rank, world, dist, n_db=100_000, nq=32, reps=20):
+    sig, key = syn.make_sc_database(n_db, 2024)
+    qs, qk, truth = syn.make_sc_queries(sig, key, nq, 77)
+    rows = api.shard_rows(n_db, world, rank)
+    db = api.ScanContextDB(session, len(rows) + 8)
+    db.add(key[rows], sig[rows], global_ids=rows)
+    if world > 1:
+        import torch
+
+        ident = [api.ScanContextDB.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        db.attach_comm(ident[0], world, rank)
+    for _ in range(3):
+        idx, diff = db.query(qs)
+    lat, scan = [], []
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        idx, diff = db.query(qs)
+        lat.append((time.perf_counter() - t0) * 1e3)
+        scan.append(db.last_scan_ms())
+    lat_ms, scan_ms = float(np.median(lat)), float(np.median(scan))
+    if world > 1:
+        import torch
+
+        t = torch.tensor([lat_ms, scan_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lat_ms, scan_ms = float(t[0]), float(t[1])
+    known = truth >= 0
+    out = {"db_rows": n_db, "rows_per_gpu": int(len(rows)), "query_batch": nq, "query_latency_ms": lat_ms, "scan_kernel_ms": scan_ms,
+           "scan_gbs_per_gpu": len(rows) * (db.n_cells + db.n_rings) * 4 / (scan_ms * 1e-3) / 1e9,
+           "revisits_found": int(np.sum(idx[known] == truth[known])), "revisits": int(known.sum()),
+           "collective": "ncclAllReduce(min, uint64 x %d)" % nq if world > 1 else "none"}
+    db.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=32, help="independent stereo streams per GPU advanced in lock step")
+    ap.add_argument("--cases", type=int, default=4, help="distinct synthetic scenes (streams cycle through them)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scan-context", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        cases = make_cases(min(args.cases, 4))
+        fps, dt = cpu_all_cores(cases, args.steps, warmup, threads)
+        line = {"metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": WORKLOAD, "frames_per_step": threads, "note": "CPU restatement of the reference path (the reference "
+                           "needs Eigen/Boost/OpenCV/ROS and cannot be built here), one independent stereo stream per host thread"},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                 "sample": "%d threads x %d stereo frames of %s" % (threads, args.steps, WORKLOAD)},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    from direct_stereo_slam_b200 import api
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    session = api.Session(local_rank)
+    cases = make_cases(args.cases, seed0=1000 + 16 * rank)
+    streams = GpuStreams(api, session, cases, args.streams)
+
+    # ---- value: device-resident inputs ------------------------------------------------------------------------------------
+    streams.upload_inputs()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed_steps(streams, session, args.steps, warmup, False, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------------------
+    ms_e2e, _ = timed_steps(streams, session, args.steps, warmup, True, barrier)
+    # ---- roofline: per-launch CUDA-event timing of the fused pose kernel over the same steps -----------------------------------
+    session.profile(True)
+    for k in range(min(args.steps, 5)):
+        streams.step(k, False)
+    prof = session.profile_read()
+    session.profile(False)
+    counters = [t.counters() for t in streams.trk]
+
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tl)
+        launches = int(tl[0])
+
+    sc = None
+    if not args.no_scan_context:
+        sc = bench_scan_context(api, session, rank, world, dist)
+
+    if rank == 0:
+        frames = args.streams * world * args.steps
+        peak, peak_src = measured_peak()
+        p = prof["pose"]
+        achieved = BYTES_PER_POINT * p["points"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+        line = {"metric": "stereo_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frames_per_step": args.streams * world,
+                           "template_points_lvl0": int(np.mean(streams.pc_n0)), "keyframe_every": 1,
+                           "l2": "working set %d MB per step > 126 MB L2 (every stream has its own pyramids)" % (args.streams * 2 * 12),
+                           "multi_gpu": "replicas only (tracking does not shard); scan_context is the sharded piece",
+                           "timing": "max(CUDA events on the session stream, host clock) over the K steps, max over ranks"},
+                "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes(),
+                        "d2h_bytes_per_step": streams.d2h_bytes()},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "eval_kernel<pose> (fused calcResPose+calcGSSSEPose)", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                             "launches_timed": p["launches"], "avg_launch_us": (p["ms"] * 1e3 / p["launches"]) if p["launches"] else None,
+                             "points_per_launch": (p["points"] / p["launches"]) if p["launches"] else None,
+                             "scale_kernel_gbs": (BYTES_PER_POINT * prof["scale"]["points"] / (prof["scale"]["ms"] * 1e-3) / 1e9)
+                             if prof["scale"]["ms"] > 0 else None},
+                "clocks": clocks,
+                "lm": {"evals_per_frame": float(np.sum([c["evals"] for c in counters])) / (args.streams * (2 * warmup + 2 * args.steps + min(args.steps, 5))),
+                       "note": "fused residual+Jacobian evaluations (pose + scale LM rounds) per stereo frame"}}
+        if sc is not None:
+            line["scan_context"] = sc
+        if not args.no_cpu_baseline and world >= 1:
+            line["cpu_baseline"] = cpu_single_core(cases)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -85,6 +85,16 @@ class Session:
         check(self.lib.dslam_session_elapsed_ms(self.p, C.byref(ms)))
         return ms.value
 
+    def profile(self, enable):
+        check(self.lib.dslam_session_profile(self.p, 1 if enable else 0))
+
+    def profile_read(self):
+        """Per-launch CUDA-event timing of the residual kernels since the last read."""
+        out = np.zeros(8)
+        check(self.lib.dslam_session_profile_read(self.p, _dp(out)))
+        return dict(pose=dict(launches=int(out[0]), ms=out[1], points=int(out[2]), max_ms=out[3]),
+                    scale=dict(launches=int(out[4]), ms=out[5], points=int(out[6]), max_ms=out[7]))
+
     def stream(self):
         p = C.c_void_p()
         check(self.lib.dslam_session_stream(self.p, C.byref(p)))
@@ -497,3 +507,33 @@ def combine_keys_torch(keys, group=None):
     k = torch.from_numpy((np.asarray(keys, np.uint64) ^ np.uint64(1 << 63)).view(np.int64).copy())
     dist.all_reduce(k, op=dist.ReduceOp.MIN, group=group)
     return k.numpy().view(np.uint64) ^ np.uint64(1 << 63)
+
+
+# ---- independent stereo streams in lock step (one kernel launch per LM round for all of them) ---------------------
+def track_newest_coarse_batch(trackers, frames, poses, affs, coarsestLvl, minResForAbort=None):
+    n = len(trackers)
+    lib = trackers[0].lib
+    ctxs = (C.c_void_p * n)(*[t.p for t in trackers])
+    frs = (C.c_void_p * n)(*[f.p for f in frames])
+    expo = np.ascontiguousarray([f.ab_exposure for f in frames], np.float32)
+    poses = np.array(poses, np.float64).reshape(n, 7)
+    affs = np.array(affs, np.float64).reshape(n, 2)
+    mr = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+    last = np.empty((n, 5))
+    flow = np.empty((n, 3))
+    ok = np.zeros(n, np.int32)
+    check(lib.dslam_track_newest_coarse_batch(n, ctxs, frs, _fp(expo), _dp(poses), _dp(affs), coarsestLvl, _dp(mr), _dp(last), _dp(flow), _ip(ok)))
+    for i, t in enumerate(trackers):
+        t.lastFlowIndicators = flow[i]
+    return ok.astype(bool), poses, affs, last
+
+
+def optimize_scale_batch(trackers, frames_right, scales, coarsestLvl):
+    n = len(trackers)
+    lib = trackers[0].lib
+    ctxs = (C.c_void_p * n)(*[t.p for t in trackers])
+    frs = (C.c_void_p * n)(*[f.p for f in frames_right])
+    scales = np.array(scales, np.float32).reshape(n)
+    rmse = np.empty(n, np.float32)
+    check(lib.dslam_optimize_scale_batch(n, ctxs, frs, _fp(scales), coarsestLvl, _fp(rmse)))
+    return rmse, scales

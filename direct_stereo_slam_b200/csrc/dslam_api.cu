@@ -102,7 +102,7 @@ int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vec
     int gx = 1;
     for (int i = 0; i < cnt; i++) {
       EvalItem &it = items[base + i];
-      it.nblocks = choose_blocks(it.n, n, s->num_sms);
+      it.nblocks = choose_blocks(it.n, cnt, s->num_sms);
       it.ppt_stride = it.nblocks * kEvalThreads;
       if (it.nblocks > gx) gx = it.nblocks;
       batch.item[i] = it;
@@ -132,26 +132,48 @@ int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vec
   outs.resize(n);
   const auto t0 = std::chrono::steady_clock::now();
   unsigned long spins = 0;
+  const int nv = mode == 0 ? kPoseVals : kScaleVals;
   for (int i = 0; i < n; i++) {
-    volatile dslam::EvalResult *r = s->results_host + i;
-    while (r->seq != seq) {
-      if ((++spins & 0x3fff) == 0) {
-        const cudaError_t q = cudaStreamQuery(s->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "evaluation kernel");
-        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (dt > s->timeout_s) return fail(DSLAM_ETIMEOUT, "evaluation kernel did not publish its result within %.1f s", s->timeout_s);
-      }
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const volatile unsigned long long *w = s->results_host[i].w;
     EvalOut &o = outs[i];
-    const int nv = mode == 0 ? kPoseVals : kScaleVals;
-    for (int k = 0; k < nv; k++) o.acc[k] = r->acc[k];
-    o.nE = r->counts[0];
-    o.nSat = r->counts[1];
-    o.nInl = r->counts[2];
+    // every word of the record carries the sequence number of the launch that wrote it
+    auto wait_word = [&](int k, unsigned long long *out) -> int {
+      unsigned long long v;
+      while ((unsigned)((v = w[k]) & 0xffffffffull) != seq) {
+        if ((++spins & 0x3fff) == 0) {
+          const cudaError_t q = cudaStreamQuery(s->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "evaluation kernel");
+          const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          if (dt > s->timeout_s) return fail(DSLAM_ETIMEOUT, "evaluation kernel did not publish its result within %.1f s", s->timeout_s);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      *out = v;
+      return DSLAM_OK;
+    };
+    int cnts[3];
+    for (int k = 2; k >= 0; k--) {  // the counters are written last by the kernel: wait for them first
+      unsigned long long v = 0;
+      const int rc = wait_word(kResultCountBase + k, &v);
+      if (rc != DSLAM_OK) return rc;
+      cnts[k] = (int)(unsigned)(v >> 32);
+    }
+    for (int k = 0; k < nv; k++) {
+      unsigned long long hi = 0, lo = 0;
+      int rc = wait_word(2 * k, &hi);
+      if (rc != DSLAM_OK) return rc;
+      rc = wait_word(2 * k + 1, &lo);
+      if (rc != DSLAM_OK) return rc;
+      const unsigned long long bits = (hi & 0xffffffff00000000ull) | (lo >> 32);
+      double d;
+      std::memcpy(&d, &bits, 8);
+      o.acc[k] = d;
+    }
+    o.nE = cnts[0];
+    o.nSat = cnts[1];
+    o.nInl = cnts[2];
     o.n_padded = (o.nInl + 3) & ~3;  // zero padding to a multiple of 4  (:824-835, :1147-1158)
     const EvalItem &it = items[i];
     const int iE = mode == 0 ? 45 : 3, iT = mode == 0 ? 46 : 4, iRT = mode == 0 ? 47 : 5;
@@ -568,7 +590,7 @@ int dslam_session_create(int device, dslam_session **out) {
   if (s->num_sms <= 0) s->num_sms = 148;
   DSLAM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   DSLAM_CUDA(cudaHostAlloc((void **)&s->results_host, sizeof(EvalResult) * kResultSlots, cudaHostAllocMapped));
-  std::memset(s->results_host, 0, sizeof(EvalResult) * kResultSlots);
+  std::memset(s->results_host, 0, sizeof(EvalResult) * kResultSlots);  // sequence numbers start at 1
   DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->results_dev, s->results_host, 0));
   DSLAM_CUDA(cudaMalloc((void **)&s->scratch.partials, sizeof(double) * kMaxItemsPerLaunch * kMaxBlocksPerItem * kPoseVals));
   DSLAM_CUDA(cudaMalloc((void **)&s->scratch.counters, sizeof(int) * kMaxItemsPerLaunch * 4));
@@ -717,6 +739,8 @@ int dslam_frame_create(dslam_session *s, int w, int h, int levels, dslam_frame *
   }
   for (int l = levels; l < kMaxLevels; l++) f->maps.map[l] = f->maps.map[0];
   e = cudaEventCreateWithFlags(&f->host_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->built_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     cudaFree(f->block);
     delete f;
@@ -734,7 +758,12 @@ int dslam_frame_destroy(dslam_frame *f) {
   cudaFree(f->stage_dIp);
   cudaFree(f->stage_abs);
   cudaFree(f->B_dev);
+  if (f->copy_stream) {
+    cudaStreamSynchronize(f->copy_stream);
+    cudaStreamDestroy(f->copy_stream);
+  }
   cudaEventDestroy(f->host_ready);
+  cudaEventDestroy(f->built_ev);
   delete f;
   return DSLAM_OK;
 }
@@ -767,6 +796,10 @@ static int frame_build_impl(dslam_frame *f, const float *B256, bool stage_dIp, b
   }
   const int rc = frame_ensure_staging(f, stage_dIp, stage_abs);
   if (rc != DSLAM_OK) return rc;
+  if (f->host_pending) {  // the previous frame's mirrors may still be draining from the staging copies
+    DSLAM_CUDA(cudaStreamWaitEvent(s->stream, f->host_ready, 0));
+    f->host_pending = false;
+  }
   PyramidLevels L = f->L;
   for (int l = 0; l < f->levels; l++) {
     L.host_dIp[l] = stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
@@ -790,6 +823,9 @@ int dslam_frame_build(dslam_frame *f, const float *B256) {
 
 static int frame_copy_out(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad) {
   dslam_session *s = f->s;
+  // the copies run on the frame's own stream, behind the kernels that filled the staging buffers
+  DSLAM_CUDA(cudaEventRecord(f->built_ev, s->stream));
+  DSLAM_CUDA(cudaStreamWaitEvent(f->copy_stream, f->built_ev, 0));
   // contiguous destination (one block for all levels) -> one DMA per array instead of one per level
   for (int pass = 0; pass < 2; pass++) {
     float *const *dst = pass == 0 ? host_dIp : host_absgrad;
@@ -800,15 +836,16 @@ static int frame_copy_out(dslam_frame *f, float *const *host_dIp, float *const *
     for (int l = 0; l < f->levels; l++)
       if (!dst[l] || dst[l] != dst[0] + mul * f->px_off[l]) contiguous = false;
     if (contiguous) {
-      DSLAM_CUDA(cudaMemcpyAsync(dst[0], src, mul * f->px_off[f->levels] * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+      DSLAM_CUDA(cudaMemcpyAsync(dst[0], src, mul * f->px_off[f->levels] * sizeof(float), cudaMemcpyDeviceToHost, f->copy_stream));
     } else {
       for (int l = 0; l < f->levels; l++)
         if (dst[l])
           DSLAM_CUDA(cudaMemcpyAsync(dst[l], src + mul * f->px_off[l], mul * (f->px_off[l + 1] - f->px_off[l]) * sizeof(float),
-                                     cudaMemcpyDeviceToHost, s->stream));
+                                     cudaMemcpyDeviceToHost, f->copy_stream));
     }
   }
-  DSLAM_CUDA(cudaEventRecord(f->host_ready, s->stream));
+  DSLAM_CUDA(cudaEventRecord(f->host_ready, f->copy_stream));
+  f->host_pending = true;
   return DSLAM_OK;
 }
 
@@ -826,6 +863,10 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
       L.host_dIp[l] = f->stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
       L.host_abs[l] = f->stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
     }
+    if (f->host_pending) {
+      DSLAM_CUDA(cudaStreamWaitEvent(f->s->stream, f->host_ready, 0));
+      f->host_pending = false;
+    }
     DSLAM_CUDA(launch_unpack(L, f->s->stream));
     f->s->launches++;
     f->staged = true;
@@ -835,7 +876,7 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
 
 int dslam_frame_wait_host(dslam_frame *f) {
   if (!f) return fail(DSLAM_EINVAL, "null frame");
-  DSLAM_CUDA(cudaEventSynchronize(f->host_ready));
+  if (f->host_pending) DSLAM_CUDA(cudaEventSynchronize(f->host_ready));
   return DSLAM_OK;
 }
 
@@ -845,7 +886,6 @@ int dslam_frame_make_images(dslam_frame *f, const float *color, const float *B25
   rc = frame_build_impl(f, B256, host_dIp != nullptr, host_absgrad != nullptr);
   if (rc != DSLAM_OK) return rc;
   if (host_dIp || host_absgrad) return frame_copy_out(f, host_dIp, host_absgrad);
-  DSLAM_CUDA(cudaEventRecord(f->host_ready, f->s->stream));
   return DSLAM_OK;
 }
 

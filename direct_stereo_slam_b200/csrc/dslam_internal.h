@@ -62,7 +62,10 @@ struct dslam_frame {
   float *B_dev = nullptr;      // 256-float gamma table (lazy)
   size_t px_off[dslam::kMaxLevels + 1]{};
   bool uploaded = false, built = false, staged = false;
-  cudaEvent_t host_ready = nullptr;
+  cudaEvent_t host_ready = nullptr;  // recorded on copy_stream after the D2H of the host mirrors
+  cudaEvent_t built_ev = nullptr;    // recorded on the session stream after the kernels that fill the staging copies
+  cudaStream_t copy_stream = nullptr;  // D2H of the host mirrors overlaps the tracking kernels of the session stream
+  bool host_pending = false;
 };
 
 struct dslam_ctx {

@@ -12,7 +12,7 @@ constexpr int kMaxLevels = 6;
 // residual / Jacobian / normal-equation kernels (kernels_residual.cu)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kEvalThreads = 128;        // threads per CTA of the evaluation kernels
-constexpr int kMaxBlocksPerItem = 128;   // partial-sum slots per work item
+constexpr int kMaxBlocksPerItem = 64;    // partial-sum slots per work item
 constexpr int kMaxItemsPerLaunch = 128;  // work items carried in kernel-parameter space per launch
 constexpr int kPoseVals = 48;            // 45 upper-triangle sums + E + shiftT + shiftRT
 constexpr int kScaleVals = 8;            // JwJ, Jwr, rwr, E, shiftT, shiftRT, 0, 0
@@ -39,14 +39,18 @@ struct EvalBatch {
   EvalItem item[kMaxItemsPerLaunch];
 };
 
-// Result record written by the last CTA of an item straight into mapped pinned host memory.
+// Result record written by the last CTA of an item straight into mapped pinned host memory.  Every 8-byte word
+// carries the launch sequence number in its low half and 32 payload bits in its high half, so the host needs no
+// flag and the kernel needs no system-scope fence (which costs ~10 us of idle GPU per launch): the host simply
+// waits until every word of the record shows the current sequence number.  8-byte aligned stores are not torn.
+//   w[2*i], w[2*i+1] : high / low 32 bits of acc[i]  (i < kPoseVals)
+//   w[96..98]        : numTermsInE, numSaturated, numTermsInWarped (unpadded)
+constexpr int kResultWords = 128;
+constexpr int kResultCountBase = 2 * kPoseVals;
 struct alignas(128) EvalResult {
-  double acc[kPoseVals];
-  int counts[4];  // numTermsInE, numSaturated, numTermsInWarped (unpadded), reserved
-  volatile unsigned seq;  // written last; host spins on it
-  unsigned pad_[27];
+  unsigned long long w[kResultWords];
 };
-static_assert(sizeof(EvalResult) == 512, "EvalResult layout");
+static_assert(sizeof(EvalResult) == 1024, "EvalResult layout");
 
 // device scratch of a session: per item-slot partial sums, counters and tickets
 struct EvalScratch {

@@ -89,6 +89,12 @@ class Oracle:
         L.orc_get_warped.restype = C.c_int
         L.orc_get_warped.argtypes = [C.c_void_p, C.c_int, c_f]
         L.orc_calc_gs_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, c_d, c_d, c_d]
+        L.orc_pose_rows.restype = C.c_int
+        L.orc_pose_rows.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, c_f, c_f]
+        L.orc_scale_rows.restype = C.c_int
+        L.orc_scale_rows.argtypes = [C.c_void_p, C.c_int, C.c_float, c_f, c_f, c_f]
+        L.orc_accumulator9.argtypes = [c_f, c_f, C.c_int, c_f]
+        L.orc_scale_accumulator.argtypes = [c_f, c_f, c_f, C.c_int, c_f]
         L.orc_track_newest_coarse.restype = C.c_int
         L.orc_track_newest_coarse.argtypes = [C.c_void_p, C.c_int, c_d, c_d, C.c_int, c_d, c_d, c_d]
         L.orc_calc_res_scale.restype = C.c_int
@@ -152,6 +158,19 @@ class Oracle:
         x = np.zeros(8, np.float64)
         self.lib.orc_ldlt_solve(n, _dp(A8), _dp(rhs), _dp(x))
         return x[:n]
+
+    def accumulator9(self, J, w):
+        J = np.ascontiguousarray(J, np.float32)
+        w = np.ascontiguousarray(w, np.float32)
+        out = np.zeros(45, np.float32)
+        self.lib.orc_accumulator9(_fp(J), _fp(w), J.shape[1], _fp(out))
+        return out
+
+    def scale_accumulator(self, J, r, w):
+        J, r, w = (np.ascontiguousarray(a, np.float32) for a in (J, r, w))
+        out = np.zeros(3, np.float32)
+        self.lib.orc_scale_accumulator(_fp(J), _fp(r), _fp(w), len(J), _fp(out))
+        return out
 
     # ---- Scan Context ---------------------------------------------------------------------------------
     def sc_generate(self, pts, lidar_range=40.0, num_s=60, num_r=20):
@@ -281,6 +300,20 @@ class OracleTracker:
         self.L.orc_calc_gs_pose(self.p, lvl, mode, aff[0], aff[1], _dp(H), _dp(b), _dp(acc))
         return H.reshape(8, 8), b, acc
 
+    def pose_rows(self, lvl, aff):
+        """(J [9, n], w [n]) of the last calc_res_pose, as calcGSSSEPose forms them."""
+        n = self.L.orc_pose_rows(self.p, lvl, aff[0], aff[1], None, None)
+        J = np.zeros((9, n), np.float32)
+        w = np.zeros(n, np.float32)
+        self.L.orc_pose_rows(self.p, lvl, aff[0], aff[1], _fp(J), _fp(w))
+        return J, w
+
+    def scale_rows(self, lvl, scale):
+        n = self.L.orc_scale_rows(self.p, lvl, scale, None, None, None)
+        J, r, w = (np.zeros(n, np.float32) for _ in range(3))
+        self.L.orc_scale_rows(self.p, lvl, scale, _fp(J), _fp(r), _fp(w))
+        return J, r, w
+
     def track_newest_coarse(self, mode, pose7, aff, coarsest, min_res=None):
         pose7 = np.array(pose7, np.float64)
         aff = np.array(aff, np.float64)
@@ -318,3 +351,57 @@ class OracleTracker:
         out = (C.c_long * 2)()
         self.L.orc_get_counters(self.p, out)
         return out[0], out[1]
+
+
+class ReferencePieces:
+    """oracle/_ref/libdslam_ref.so: the reference's OWN Accumulator9 / ScaleAccumulator / search_place.h compiled in place by
+    oracle/ref_build.py.  Used to pin the restatements above."""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(_HERE, "_ref", "libdslam_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = self.lib = C.CDLL(path)
+        L.ref_accumulator9.argtypes = [c_f, c_f, C.c_int, c_f]
+        L.ref_scale_accumulator.argtypes = [c_f, c_f, c_f, C.c_int, c_f]
+        L.ref_search_sc.argtypes = [c_i, c_d, C.c_int, c_i, c_i, c_d, C.c_int, c_i, C.c_int, C.c_int, c_i, c_f]
+        L.ref_search_ringkey_sequence.argtypes = [c_f, C.c_int, C.c_int, c_i, c_i]
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libdslam_ref.so"))
+
+    def accumulator9(self, J, w):
+        J = np.ascontiguousarray(J, np.float32)
+        w = np.ascontiguousarray(w, np.float32)
+        out = np.zeros(45, np.float32)
+        self.lib.ref_accumulator9(_fp(J), _fp(w), J.shape[1], _fp(out))
+        return out
+
+    def scale_accumulator(self, J, r, w):
+        J, r, w = (np.ascontiguousarray(a, np.float32) for a in (J, r, w))
+        out = np.zeros(3, np.float32)
+        self.lib.ref_scale_accumulator(_fp(J), _fp(r), _fp(w), len(J), _fp(out))
+        return out
+
+    def search_sc(self, q_idx, q_val, sig_ptr, sig_idx, sig_val, candidates, sc_width=60):
+        q_idx = np.ascontiguousarray(q_idx, np.int32)
+        q_val = np.ascontiguousarray(q_val, np.float64)
+        sig_ptr = np.ascontiguousarray(sig_ptr, np.int32)
+        sig_idx = np.ascontiguousarray(sig_idx, np.int32)
+        sig_val = np.ascontiguousarray(sig_val, np.float64)
+        candidates = np.ascontiguousarray(candidates, np.int32)
+        ri = C.c_int(-1)
+        rd = C.c_float(0)
+        self.lib.ref_search_sc(_ip(q_idx), _dp(q_val), len(q_idx), _ip(sig_ptr), _ip(sig_idx), _dp(sig_val), len(sig_ptr) - 1, _ip(candidates),
+                               len(candidates), sc_width, C.byref(ri), C.byref(rd))
+        return ri.value, rd.value
+
+    def search_ringkey_sequence(self, keys):
+        """Run the keys through the reference's search_ringkey in order (once per process: it keeps static state)."""
+        keys = np.ascontiguousarray(keys, np.float32)
+        n, dim = keys.shape
+        cand = np.full((n, 3), -1, np.int32)
+        ncand = np.zeros(n, np.int32)
+        self.lib.ref_search_ringkey_sequence(_fp(keys), n, dim, _ip(cand), _ip(ncand))
+        return cand, ncand

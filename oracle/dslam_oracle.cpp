@@ -975,6 +975,59 @@ int orc_get_warped(void *p, int which /*0 pose, 1 scale*/, float *out8n) {
 void orc_calc_gs_pose(void *p, int lvl, int mode, double aff_a, double aff_b, double H64[64], double b8[8], double acc45[45]) {
   calc_gs_pose(*(Tracker *)p, lvl, mode, aff_a, aff_b, H64, b8, acc45);
 }
+// Jacobian rows of the last calcResPose as calcGSSSEPose forms them (:658-678): J9n = 9 arrays of n floats (J0..J7, r), w[n].
+// Lets tests feed the very same rows to the reference's own Accumulator9 (oracle/_ref).
+int orc_pose_rows(void *p, int lvl, double aff_a, double aff_b, float *J9n, float *w) {
+  Tracker &T = *(Tracker *)p;
+  const int n = T.pose_n;
+  if (!J9n) return n;
+  double affd[2]; aff_from_to(T.ref_exposure, T.new_exposure, T.ref_a, T.ref_b, aff_a, aff_b, affd);
+  const float a = (float)affd[0], b0 = (float)T.ref_b;
+  for (int i = 0; i < n; i++) {
+    float J[8];
+    pose_jacobian(T.pbuf[0][i], T.pbuf[1][i], T.pbuf[2][i], T.pbuf[3][i], T.pbuf[4][i], T.pbuf[7][i], T.fx[lvl], T.fy[lvl], a, b0, J);
+    for (int j = 0; j < 8; j++) J9n[(size_t)j * n + i] = J[j];
+    J9n[(size_t)8 * n + i] = T.pbuf[5][i];
+    w[i] = T.pbuf[6][i];
+  }
+  return n;
+}
+int orc_scale_rows(void *p, int lvl, float scale, float *J, float *r, float *w) {
+  Tracker &T = *(Tracker *)p;
+  const int n = T.scale_n;
+  if (!J) return n;
+  const float tx = (float)T.tfm_f1_f0.t[0], ty = (float)T.tfm_f1_f0.t[1], tz = (float)T.tfm_f1_f0.t[2];
+  for (int i = 0; i < n; i++) {
+    J[i] = scale_jacobian(T.sbuf[0][i], T.sbuf[1][i], T.sbuf[2][i], T.sbuf[3][i], T.sbuf[4][i], T.fx1[lvl], T.fy1[lvl], scale, tx, ty, tz);
+    r[i] = T.sbuf[5][i];
+    w[i] = T.sbuf[6][i];
+  }
+  return n;
+}
+// The tiered 4-lane accumulators on caller-provided rows (same layout as oracle/_ref's ref_accumulator9 / ref_scale_accumulator)
+void orc_accumulator9(const float *J9n, const float *w, int n, float *out45) {
+  static thread_local TieredAcc<9> A;
+  A.initialize();
+  for (int i = 0; i < n; i += 4) {
+    float J[9][4], ww[4];
+    for (int l = 0; l < 4; l++) {
+      for (int j = 0; j < 9; j++) J[j][l] = J9n[(size_t)j * n + i + l];
+      ww[l] = w[i + l];
+    }
+    A.update(J, ww);
+  }
+  A.finish(out45);
+}
+void orc_scale_accumulator(const float *Jin, const float *r, const float *w, int n, float *out3) {
+  static thread_local TieredAcc<2> A;
+  A.initialize();
+  for (int i = 0; i < n; i += 4) {
+    float J[2][4], ww[4];
+    for (int l = 0; l < 4; l++) { J[0][l] = Jin[i + l]; J[1][l] = r[i + l]; ww[l] = w[i + l]; }
+    A.update(J, ww);
+  }
+  A.finish(out3);
+}
 int orc_track_newest_coarse(void *p, int mode, double pose7_io[7], double aff_io[2], int coarsestLvl, const double minResForAbort[5], double lastResiduals[5], double flow3[3]) {
   Tracker &T = *(Tracker *)p;
   SE3 s = se3_from7(pose7_io);

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Compile the pieces of the REFERENCE that build from their own few source files, in place, into oracle/_ref/.
+
+What builds here (g++ only; the reference's cmake / catkin build is not run and cannot be — no Eigen, Boost, OpenCV,
+FLANN, PCL, ROS in this image):
+  * deps:dso/src/OptimizationBackend/MatrixAccumulators.h  (Accumulator9; lives inside /root/reference/dependencies.zip and is
+    extracted to a temporary directory outside the repository for the duration of the compile)
+  * src/scale_optimization/ScaleAccumulator.h
+  * src/loop_closure/loop_detection/search_place.h
+against the shims in oracle/shim (Eigen/Core, util/NumType.h) and oracle/ref_driver.cpp.  Output: oracle/_ref/libdslam_ref.so
+(git-ignored; travels to the GPU box with the snapshot).  No reference source is copied into the repository.
+The warp / residual / LM code (TrackerAndScaler.cpp) needs real Eigen + Sophus + DSO and is NOT buildable: those
+functions stay "parity unpinned" (see oracle/dslam_oracle.cpp header).
+"""
+import os
+import subprocess
+import sys
+import tempfile
+import zipfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("DSLAM_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+
+def main():
+    if not os.path.isdir(REF):
+        print("reference tree %s not present: nothing to build (a prebuilt oracle/_ref is used if it travelled)" % REF)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory(prefix="dslam_ref_") as tmp:
+        with zipfile.ZipFile(os.path.join(REF, "dependencies.zip")) as z:
+            z.extract("dso/src/OptimizationBackend/MatrixAccumulators.h", tmp)
+        cmd = ["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-w",
+               "-I", os.path.join(HERE, "shim"),          # Eigen/Core, util/NumType.h stand-ins (searched first)
+               "-I", os.path.join(tmp, "dso", "src"),      # OptimizationBackend/MatrixAccumulators.h
+               "-I", os.path.join(REF, "src"),             # scale_optimization/..., loop_closure/...
+               os.path.join(HERE, "ref_driver.cpp"), "-o", os.path.join(OUT, "libdslam_ref.so")]
+        subprocess.run(cmd, check=True)
+    print("built", os.path.join(OUT, "libdslam_ref.so"))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
