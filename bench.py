@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py — stereo frames/s of the photometric Gauss-Newton hot path at KITTI size on B200 (BASELINE.json configs[1]).
 
-One "step" = one stereo frame for each of S independent stereo streams resident on the GPU, every frame doing the full
-per-keyframe work of the reference's path:
-    FrameHessian::makeImages(left) -> TrackerAndScaler::trackNewestCoarse -> makeImages(right) -> optimizeScale(seed 1.0)
-The S streams advance in lock step: every Levenberg-Marquardt round of all streams is ONE launch of the fused residual /
-Jacobian kernel.  Workload: synthetic stereo pairs 1232x368 (KITTI 1241x376 after the calibration crop), 2000 active
+One "step" = one stereo frame for each of S independent stereo streams resident on the GPU.  Every frame runs
+    FrameHessian::makeImages(left) -> TrackerAndScaler::trackNewestCoarse
+and every 5th frame of a stream is a keyframe that additionally runs
+    makeImages(right) -> TrackerAndScaler::optimizeScale(seed 1.0)
+("frames/s = 1/(pyramid L + tracker + amortised pyramid R + scale-opt every 5th frame)"; the streams are
+staggered so that every step carries S/5 keyframes).  The S streams advance in lock step: the pyramids of a step are two
+kernel launches, and every Levenberg-Marquardt round of all pose trackers AND scale optimisers is ONE launch of the fused
+residual / Jacobian kernel.  Workload: synthetic stereo pairs 1232x368 (KITTI 1241x376 after the calibration crop), 2000 active
 points -> ~10k template pixels at level 0, 5 pyramid levels.
 
   value  : frames/s with the raw images already resident in HBM (pyramid build + tracking + scale optimisation timed)
   e2e    : the same through the C ABI with HOST buffers: pinned-host images uploaded inside the timed region, the left
-           pyramid mirrored back into the reference's host layouts (dIp / absSquaredGrad, what untouched DSO code reads),
-           poses / scales returned to the host
+           pyramid mirrored back into the reference's host layouts for the untouched DSO code that reads it (level-0 dI on
+           every frame — ImmaturePoint::traceOn; all levels of dIp + absSquaredGrad on keyframes — pixel selector, BA,
+           LoopHandler), poses / scales returned to the host
   roofline : fused pose residual kernel, algorithmic bytes (64 B per template point per evaluation) over the
            CUDA-event duration of every launch, measured live in a separate profiled pass of the same steps
   cpu_baseline : the CPU oracle (-O3 -march=native, the reference's SSE accumulation order) on ONE core — the reference's
@@ -126,8 +130,9 @@ def make_cases(n_cases, seed0=1000):
 class GpuStreams:
     """S independent stereo streams of one rank (device twins of S TrackerAndScaler objects and their frames)."""
 
-    def __init__(self, api, session, cases, n_streams):
+    def __init__(self, api, session, cases, n_streams, kf_every=5):
         self.api, self.s = api, session
+        self.kf_every = kf_every
         cfg = cases[0]["cfg"]
         self.w, self.h = cfg["w"], cfg["h"]
         self.levels = api.pyr_levels_used(self.w, self.h)
@@ -170,36 +175,45 @@ class GpuStreams:
             self.f_right[i].upload(self.h_right[i])
         self.s.sync()
 
+    def is_kf(self, i, k):
+        return (k + i) % self.kf_every == 0
+
     def step(self, k, e2e):
         api = self.api
         v = k & 1
         left = [self.f_new[i][v] for i in range(self.n)]
+        kf = [i for i in range(self.n) if self.is_kf(i, k)]
+        right = [self.f_right[i] for i in kf]
         if e2e:
             for i in range(self.n):
-                left[i].makeImages(self.h_new[i][v], host=True, wait=False)  # H2D + build + async D2H of the host mirrors
-        else:
-            for f in left:
-                f.build()
+                left[i].upload(self.h_new[i][v])
+            for i in kf:
+                self.f_right[i].upload(self.h_right[i])
+        api.build_frames(left, stage_host=3 if e2e else 0)   # two launches for all left pyramids
+        if right:
+            api.build_frames(right)
+        if e2e:  # host mirrors drain on the frames' copy streams while the LM rounds run
+            for i in range(self.n):
+                if self.is_kf(i, k):
+                    left[i].download(wait=False)
+                else:
+                    left[i].download(wait=False, levels=[0], abs_grad=False)
         poses = np.stack([self.case_of[i]["pose_init"][v] for i in range(self.n)])
-        ok, poses, affs, last = api.track_newest_coarse_batch(self.trk, left, poses, np.zeros((self.n, 2)), self.levels - 1)
-        if e2e:
-            for i in range(self.n):
-                self.f_right[i].makeImages(self.h_right[i], host=False)
-        else:
-            for f in self.f_right:
-                f.build()
-        rmse, scales = api.optimize_scale_batch(self.trk, self.f_right, np.ones(self.n, np.float32), self.levels - 1)
+        ok, poses, affs, last, rmse, scales = api.lm_batch(self.trk, left, poses, np.zeros((self.n, 2)), self.levels - 1,
+                                                           [self.trk[i] for i in kf], right, np.ones(len(kf), np.float32))
         if e2e:
             for f in left:
                 f.wait_host()
         return ok, poses, scales, rmse
 
     def h2d_bytes(self):
-        return self.n * 2 * self.w * self.h * 4
+        return int(self.n * (1 + 1.0 / self.kf_every) * self.w * self.h * 4)
 
     def d2h_bytes(self):
         tot = sum((self.w >> l) * (self.h >> l) for l in range(self.levels))
-        return self.n * (tot * 16 + 7 * 8 + 2 * 8 + 5 * 8 + 4 + 4)
+        per_kf = tot * 16
+        per_nonkf = self.w * self.h * 12
+        return int(self.n * (per_kf / self.kf_every + per_nonkf * (1 - 1.0 / self.kf_every)) + self.n * (7 * 8 + 2 * 8 + 5 * 8 + 4))
 
 
 def timed_steps(streams, session, steps, warmup, e2e, dist_barrier):
@@ -226,8 +240,9 @@ def timed_steps(streams, session, steps, warmup, e2e, dist_barrier):
 # CPU arms (oracle = restatement of the reference's CPU algorithm; the only place bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------------------------------
 class CpuStream:
-    def __init__(self, orc_mod, o, case):
+    def __init__(self, orc_mod, o, case, phase=0, kf_every=5):
         cfg = case["cfg"]
+        self.phase, self.kf_every = phase, kf_every
         self.o, self.case = o, case
         self.w, self.h = cfg["w"], cfg["h"]
         self.levels = orc_mod.pyr_levels_used(self.w, self.h)
@@ -243,17 +258,19 @@ class CpuStream:
         dIp_new, _ = self.o.make_images(c["img_new"] if v == 0 else c["img_new2"], self.levels)
         self.trk.set_new_frame(dIp_new, 1.0)
         ok, pose, aff, last, flow = self.trk.track_newest_coarse(0, c["pose_init"][v], (0.0, 0.0), self.levels - 1)
-        dIp_r, _ = self.o.make_images(c["img_right"], self.levels)
-        self.trk.set_right_frame(dIp_r)
-        rmse, scale = self.trk.optimize_scale(0, 1.0, self.levels - 1)
+        scale = None
+        if (k + self.phase) % self.kf_every == 0:  # keyframe: right pyramid + scale optimisation
+            dIp_r, _ = self.o.make_images(c["img_right"], self.levels)
+            self.trk.set_right_frame(dIp_r)
+            rmse, scale = self.trk.optimize_scale(0, 1.0, self.levels - 1)
         return ok, pose, scale
 
 
-def cpu_single_core(cases, budget_s=12.0):
+def cpu_single_core(cases, kf_every=5, budget_s=12.0):
     import oracle as orc
 
     o = orc.Oracle(native=True)
-    st = CpuStream(orc, o, cases[0])
+    st = CpuStream(orc, o, cases[0], phase=0, kf_every=kf_every)
     st.frame(0)  # warm-up
     n, t0 = 0, time.perf_counter()
     while True:
@@ -267,11 +284,11 @@ def cpu_single_core(cases, budget_s=12.0):
             "sample": "%d stereo frames of %s on one core (oracle -O3 -march=native, SSE accumulation order), %.1f s" % (n, WORKLOAD, dt)}
 
 
-def cpu_all_cores(cases, steps, warmup, threads):
+def cpu_all_cores(cases, steps, warmup, threads, kf_every=5):
     import oracle as orc
 
     o = orc.Oracle(native=True)
-    sts = [CpuStream(orc, o, cases[i % len(cases)]) for i in range(threads)]
+    sts = [CpuStream(orc, o, cases[i % len(cases)], phase=i, kf_every=kf_every) for i in range(threads)]
 
     def run(k0, k1):
         def work(st):
@@ -338,6 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=32, help="independent stereo streams per GPU advanced in lock step")
+    ap.add_argument("--keyframe-every", type=int, default=5, help="every k-th frame of a stream also builds the right pyramid and optimises the scale")
     ap.add_argument("--cases", type=int, default=4, help="distinct synthetic scenes (streams cycle through them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan-context", action="store_true")
@@ -352,7 +370,7 @@ def main():
             return 0
         threads = os.cpu_count() or 1
         cases = make_cases(min(args.cases, 4))
-        fps, dt = cpu_all_cores(cases, args.steps, warmup, threads)
+        fps, dt = cpu_all_cores(cases, args.steps, warmup, threads, args.keyframe_every)
         line = {"metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "impl": "reference",
@@ -380,7 +398,7 @@ def main():
 
     session = api.Session(local_rank)
     cases = make_cases(args.cases, seed0=1000 + 16 * rank)
-    streams = GpuStreams(api, session, cases, args.streams)
+    streams = GpuStreams(api, session, cases, args.streams, kf_every=args.keyframe_every)
 
     # ---- value: device-resident inputs ------------------------------------------------------------------------------------
     streams.upload_inputs()
@@ -416,20 +434,22 @@ def main():
     if rank == 0:
         frames = args.streams * world * args.steps
         peak, peak_src = measured_peak()
-        p = prof["pose"]
+        p = max((prof["pose"], prof["mixed"]), key=lambda d: d["ms"])
+        p = dict(launches=prof["pose"]["launches"] + prof["mixed"]["launches"], ms=prof["pose"]["ms"] + prof["mixed"]["ms"],
+                 points=prof["pose"]["points"] + prof["mixed"]["points"])
         achieved = BYTES_PER_POINT * p["points"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
         line = {"metric": "stereo_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "frames_per_step": args.streams * world,
-                           "template_points_lvl0": int(np.mean(streams.pc_n0)), "keyframe_every": 1,
-                           "l2": "working set %d MB per step > 126 MB L2 (every stream has its own pyramids)" % (args.streams * 2 * 12),
+                           "template_points_lvl0": int(np.mean(streams.pc_n0)), "keyframe_every": args.keyframe_every,
+                           "l2": "working set ~%d MB per step > 126 MB L2 (every stream has its own pyramids)" % int(args.streams * 12 * (1 + 1.0 / args.keyframe_every)),
                            "multi_gpu": "replicas only (tracking does not shard); scan_context is the sharded piece",
                            "timing": "max(CUDA events on the session stream, host clock) over the K steps, max over ranks"},
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes(),
                         "d2h_bytes_per_step": streams.d2h_bytes()},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "eval_kernel<pose> (fused calcResPose+calcGSSSEPose)", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "eval_kernel (fused calcRes*+calcGSSSE* of all pose / scale items of an LM round)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                              "launches_timed": p["launches"], "avg_launch_us": (p["ms"] * 1e3 / p["launches"]) if p["launches"] else None,
                              "points_per_launch": (p["points"] / p["launches"]) if p["launches"] else None,
@@ -441,7 +461,7 @@ def main():
         if sc is not None:
             line["scan_context"] = sc
         if not args.no_cpu_baseline and world >= 1:
-            line["cpu_baseline"] = cpu_single_core(cases)
+            line["cpu_baseline"] = cpu_single_core(cases, args.keyframe_every)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

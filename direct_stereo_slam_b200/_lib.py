@@ -49,6 +49,7 @@ SIGNATURES = {
     "dslam_frame_destroy": [vp],
     "dslam_frame_upload": [vp, c_f],
     "dslam_frame_build": [vp, c_f],
+    "dslam_frame_build_batch": [C.c_int, c_pp, c_f, C.c_int],
     "dslam_frame_download": [vp, c_fpp, c_fpp],
     "dslam_frame_wait_host": [vp],
     "dslam_frame_make_images": [vp, c_f, c_f, c_fpp, c_fpp],
@@ -69,6 +70,7 @@ SIGNATURES = {
     "dslam_track_newest_coarse_multi": [vp, vp, C.c_float, C.c_int, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i],
     "dslam_track_newest_coarse_batch": [C.c_int, c_pp, c_pp, c_f, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i],
     "dslam_optimize_scale_batch": [C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
+    "dslam_lm_batch": [C.c_int, c_pp, c_pp, c_f, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i, C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
     "dslam_get_trace": [vp, c_d, C.c_int, c_i],
     "dslam_ctx_counters": [vp, C.POINTER(C.c_longlong)],
     "dslam_sc_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],

@@ -90,10 +90,10 @@ class Session:
 
     def profile_read(self):
         """Per-launch CUDA-event timing of the residual kernels since the last read."""
-        out = np.zeros(8)
+        out = np.zeros(12)
         check(self.lib.dslam_session_profile_read(self.p, _dp(out)))
-        return dict(pose=dict(launches=int(out[0]), ms=out[1], points=int(out[2]), max_ms=out[3]),
-                    scale=dict(launches=int(out[4]), ms=out[5], points=int(out[6]), max_ms=out[7]))
+        return {k: dict(launches=int(out[4 * i]), ms=out[4 * i + 1], points=int(out[4 * i + 2]), max_ms=out[4 * i + 3])
+                for i, k in enumerate(("pose", "scale", "mixed"))}
 
     def stream(self):
         p = C.c_void_p()
@@ -193,11 +193,18 @@ class FrameHessian:
             Bp = _fp(B256)
         check(self.lib.dslam_frame_build(self.p, Bp))
 
-    def download(self, wait=True):
+    def download(self, wait=True, levels=None, abs_grad=True):
+        """D2H of the host mirrors; `levels` restricts the copy (e.g. [0] = only dI of level 0, what traceOn reads)."""
         if self.dIp_all is None:
             self.alloc_host()
         d = self._level_ptrs(self.dIp_all, 3)
-        a = self._level_ptrs(self.absSquaredGrad_all, 1)
+        a = self._level_ptrs(self.absSquaredGrad_all, 1) if abs_grad else None
+        if levels is not None:
+            for l in range(self.levels):
+                if l not in levels:
+                    d[l] = None
+                    if a is not None:
+                        a[l] = None
         check(self.lib.dslam_frame_download(self.p, d, a))
         if wait:
             self.wait_host()
@@ -537,3 +544,41 @@ def optimize_scale_batch(trackers, frames_right, scales, coarsestLvl):
     rmse = np.empty(n, np.float32)
     check(lib.dslam_optimize_scale_batch(n, ctxs, frs, _fp(scales), coarsestLvl, _fp(rmse)))
     return rmse, scales
+
+
+def lm_batch(pose_trackers, pose_frames, poses, affs, coarsestLvl, scale_trackers, scale_frames, scales, scale_coarsestLvl=None,
+             minResForAbort=None):
+    """n tracking jobs and m scale-optimisation jobs in ONE lock step (dslam_lm_batch): the pose and the scale LM loops are
+    independent, so every round of all of them is one launch.  Returns (ok, poses, affs, lastResiduals, rmse, scales)."""
+    n, m = len(pose_trackers), len(scale_trackers)
+    lib = (pose_trackers or scale_trackers)[0].lib
+    pc = (C.c_void_p * max(n, 1))(*[t.p for t in pose_trackers])
+    pf = (C.c_void_p * max(n, 1))(*[f.p for f in pose_frames])
+    sc = (C.c_void_p * max(m, 1))(*[t.p for t in scale_trackers])
+    sf = (C.c_void_p * max(m, 1))(*[f.p for f in scale_frames])
+    expo = np.ascontiguousarray([f.ab_exposure for f in pose_frames] or [1.0], np.float32)
+    poses = np.array(poses, np.float64).reshape(max(n, 0), 7) if n else np.zeros((0, 7))
+    affs = np.array(affs, np.float64).reshape(n, 2) if n else np.zeros((0, 2))
+    mr = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+    last = np.empty((n, 5))
+    flow = np.empty((n, 3))
+    ok = np.zeros(max(n, 1), np.int32)
+    scales = np.array(scales, np.float32).reshape(m) if m else np.zeros(0, np.float32)
+    rmse = np.empty(max(m, 1), np.float32)
+    check(lib.dslam_lm_batch(n, pc, pf, _fp(expo), _dp(poses) if n else None, _dp(affs) if n else None, coarsestLvl, _dp(mr), _dp(last) if n else None,
+                             _dp(flow) if n else None, _ip(ok), m, sc, sf, _fp(scales) if m else None,
+                             coarsestLvl if scale_coarsestLvl is None else scale_coarsestLvl, _fp(rmse)))
+    for i, t in enumerate(pose_trackers):
+        t.lastFlowIndicators = flow[i]
+    return ok[:n].astype(bool), poses, affs, last, rmse[:m], scales
+
+
+def build_frames(frames, B256=None, stage_host=0):
+    """Pyramids of all (uploaded) frames in two kernel launches (dslam_frame_build_batch)."""
+    n = len(frames)
+    arr = (C.c_void_p * n)(*[f.p for f in frames])
+    Bp = None
+    if B256 is not None:
+        B256 = np.ascontiguousarray(B256, np.float32)
+        Bp = _fp(B256)
+    check(frames[0].lib.dslam_frame_build_batch(n, arr, Bp, stage_host))

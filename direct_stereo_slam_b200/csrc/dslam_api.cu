@@ -91,9 +91,13 @@ int choose_blocks(int n, int nitems, int num_sms) {
 }
 
 // Launch `n` prepared items (any count up to kResultSlots) and wait for their result records.
-int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vector<EvalOut> &outs, long long *launch_counter) {
+int run_items(dslam_session *s, std::vector<EvalItem> &items, std::vector<EvalOut> &outs, long long *launch_counter) {
   const int n = (int)items.size();
   if (n < 1) return DSLAM_OK;
+  // kernel flavour: 0 = all pose, 1 = all scale, 2 = mixed (bit 1 of EvalItem::flags marks a scale item)
+  int n_scale = 0;
+  for (const EvalItem &it : items) n_scale += (it.flags & 2) ? 1 : 0;
+  const int mode = n_scale == 0 ? 0 : (n_scale == n ? 1 : 2);
   if (n > kResultSlots) return fail(DSLAM_EINVAL, "too many evaluation items in one round (%d > %d)", n, kResultSlots);
   const unsigned seq = ++s->seq;
   EvalBatch batch;
@@ -132,8 +136,9 @@ int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vec
   outs.resize(n);
   const auto t0 = std::chrono::steady_clock::now();
   unsigned long spins = 0;
-  const int nv = mode == 0 ? kPoseVals : kScaleVals;
   for (int i = 0; i < n; i++) {
+    const bool is_scale = (items[i].flags & 2) != 0;
+    const int nv = is_scale ? kScaleVals : kPoseVals;
     const volatile unsigned long long *w = s->results_host[i].w;
     EvalOut &o = outs[i];
     // every word of the record carries the sequence number of the launch that wrote it
@@ -176,7 +181,7 @@ int run_items(dslam_session *s, int mode, std::vector<EvalItem> &items, std::vec
     o.nInl = cnts[2];
     o.n_padded = (o.nInl + 3) & ~3;  // zero padding to a multiple of 4  (:824-835, :1147-1158)
     const EvalItem &it = items[i];
-    const int iE = mode == 0 ? 45 : 3, iT = mode == 0 ? 46 : 4, iRT = mode == 0 ? 47 : 5;
+    const int iE = is_scale ? 3 : 45, iT = is_scale ? 4 : 46, iRT = is_scale ? 5 : 47;
     const float shiftNum = (it.flags & 1) ? 2.0f * (float)((it.n + 31) / 32) : 0.0f;  // sumSquaredShiftNum
     o.res6[0] = o.acc[iE];
     o.res6[1] = o.nE;
@@ -229,6 +234,7 @@ void fill_scale_item(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, int
   for (int k = 0; k < 3; k++) it.t[k] = (float)c->T_f1_f0.t[k];
   it.p0 = scale;
   it.p1 = it.p2 = 0.f;
+  it.flags |= 2;  // scale item
 }
 
 // calcGSSSEPose epilogue :682-696 from the raw sums
@@ -515,27 +521,53 @@ struct ScaleLM {
   }
 };
 
-template <class LM>
-int run_lock_step(dslam_session *s, int mode, std::vector<LM> &lms, dslam_ctx *counters) {
+// All machines (pose and scale alike) advance one evaluation per round; a round is one kernel launch.
+int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<ScaleLM> &scale, dslam_ctx *counters) {
   std::vector<EvalItem> items;
   std::vector<EvalOut> outs;
-  std::vector<int> who;
+  std::vector<int> who;  // >= 0: pose machine index, < 0: ~index of a scale machine
   for (;;) {
     items.clear();
     who.clear();
-    for (size_t i = 0; i < lms.size(); i++)
-      if (lms[i].phase != LM::DONE) {
+    for (size_t i = 0; i < pose.size(); i++)
+      if (pose[i].phase != PoseLM::DONE) {
         items.emplace_back();
-        lms[i].request(items.back());
+        pose[i].request(items.back());
         who.push_back((int)i);
       }
+    for (size_t i = 0; i < scale.size(); i++)
+      if (scale[i].phase != ScaleLM::DONE) {
+        items.emplace_back();
+        scale[i].request(items.back());
+        who.push_back(~(int)i);
+      }
     if (items.empty()) break;
-    const int rc = run_items(s, mode, items, outs, counters ? &counters->n_launches : nullptr);
+    const int rc = run_items(s, items, outs, counters ? &counters->n_launches : nullptr);
     if (rc != DSLAM_OK) return rc;
     if (counters) counters->n_evals += (long long)items.size();
-    for (size_t k = 0; k < who.size(); k++) lms[who[k]].consume(outs[k]);
+    for (size_t k = 0; k < who.size(); k++) {
+      if (who[k] >= 0) pose[who[k]].consume(outs[k]);
+      else scale[~who[k]].consume(outs[k]);
+    }
   }
   return DSLAM_OK;
+}
+
+// trackNewestCoarse epilogue :612-637 for one finished machine
+bool finish_pose(const dslam_ctx *c, PoseLM &m, float new_exposure, double *pose7_io, double *aff) {
+  bool good = m.ok;
+  if (!good) return false;
+  m.cur.to7(pose7_io);  // outputs are only written when the level loop ran to completion
+  aff[0] = m.aff_cur[0];
+  aff[1] = m.aff_cur[1];
+  if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) return false;
+  double rel[2];
+  hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], rel);
+  const float relA = (float)rel[0], relB = (float)rel[1];
+  if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) return false;
+  if (c->affModeA < 0) aff[0] = 0;
+  if (c->affModeB < 0) aff[1] = 0;
+  return true;
 }
 
 int check_ctx_frame(const dslam_ctx *c, const dslam_frame *f, int coarsestLvl) {
@@ -656,14 +688,14 @@ int dslam_session_profile(dslam_session *s, int enable) {
   return DSLAM_OK;
 }
 
-int dslam_session_profile_read(dslam_session *s, double out[8]) {
+int dslam_session_profile_read(dslam_session *s, double out[12]) {
   if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
   DSLAM_CUDA(cudaStreamSynchronize(s->stream));
-  for (int i = 0; i < 8; i++) out[i] = 0;
+  for (int i = 0; i < 12; i++) out[i] = 0;
   for (size_t k = 0; k < s->prof_used; k++) {
     float ms = 0;
     DSLAM_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * k], s->prof_ev[2 * k + 1]));
-    const int m = s->prof_mode[k] ? 4 : 0;
+    const int m = 4 * s->prof_mode[k];
     out[m + 0] += 1;
     out[m + 1] += ms;
     out[m + 2] += (double)s->prof_points[k];
@@ -728,7 +760,7 @@ int dslam_frame_create(dslam_session *s, int w, int h, int levels, dslam_frame *
     const cuuint64_t gstride[1] = {(cuuint64_t)L.pitch[l] * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)kGradBoxW, (cuuint32_t)kGradBoxH};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&f->maps.map[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.plane[l], gdim, gstride, box, estr,
+    const CUresult r = enc(&f->devh.map[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.plane[l], gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -737,7 +769,24 @@ int dslam_frame_create(dslam_session *s, int w, int h, int levels, dslam_frame *
       return fail(DSLAM_ECUDA, "cuTensorMapEncodeTiled failed (%d) for level %d", (int)r, l);
     }
   }
-  for (int l = levels; l < kMaxLevels; l++) f->maps.map[l] = f->maps.map[0];
+  for (int l = levels; l < kMaxLevels; l++) f->devh.map[l] = f->devh.map[0];
+  f->geom.levels = levels;
+  for (int l = 0; l < kMaxLevels; l++) {
+    f->geom.w[l] = L.w[l]; f->geom.h[l] = L.h[l]; f->geom.pitch[l] = L.pitch[l]; f->geom.tiles_x[l] = L.tiles_x[l];
+    f->devh.plane[l] = l < levels ? L.plane[l] : nullptr;
+    f->devh.tex[l] = l < levels ? L.tex[l] : nullptr;
+    f->devh.host_dIp[l] = nullptr;
+    f->devh.host_abs[l] = nullptr;
+  }
+  for (int l = 0; l <= kMaxLevels; l++) f->geom.tile_begin[l] = L.tile_begin[l];
+  f->devh.B256 = nullptr;
+  e = cudaMalloc((void **)&f->dev, sizeof(FrameDev));
+  if (e != cudaSuccess) {
+    cudaFree(f->block);
+    delete f;
+    return cuda_fail(e, "cudaMalloc(frame descriptor)");
+  }
+  f->dev_dirty = true;
   e = cudaEventCreateWithFlags(&f->host_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->built_ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
@@ -755,6 +804,7 @@ int dslam_frame_destroy(dslam_frame *f) {
   cudaSetDevice(f->s->device);
   cudaStreamSynchronize(f->s->stream);
   cudaFree(f->block);
+  cudaFree(f->dev);
   cudaFree(f->stage_dIp);
   cudaFree(f->stage_abs);
   cudaFree(f->B_dev);
@@ -785,8 +835,10 @@ static int frame_ensure_staging(dslam_frame *f, bool want_dIp, bool want_abs) {
   return DSLAM_OK;
 }
 
-static int frame_build_impl(dslam_frame *f, const float *B256, bool stage_dIp, bool stage_abs) {
-  if (!f->uploaded) return fail(DSLAM_ESTATE, "dslam_frame_build before dslam_frame_upload");
+static bool same_geometry(const dslam_frame *a, const dslam_frame *b) { return a->w == b->w && a->h == b->h && a->levels == b->levels; }
+
+// point the device descriptor of a frame at its staging copies / gamma table and upload it if anything changed
+static int frame_prepare(dslam_frame *f, const float *B256, bool stage_dIp, bool stage_abs) {
   dslam_session *s = f->s;
   const float *Bd = nullptr;
   if (B256) {
@@ -800,25 +852,65 @@ static int frame_build_impl(dslam_frame *f, const float *B256, bool stage_dIp, b
     DSLAM_CUDA(cudaStreamWaitEvent(s->stream, f->host_ready, 0));
     f->host_pending = false;
   }
-  PyramidLevels L = f->L;
+  FrameDev &d = f->devh;
   for (int l = 0; l < f->levels; l++) {
-    L.host_dIp[l] = stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
-    L.host_abs[l] = stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
+    float *hd = stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
+    float *ha = stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
+    if (d.host_dIp[l] != hd || d.host_abs[l] != ha) f->dev_dirty = true;
+    d.host_dIp[l] = hd;
+    d.host_abs[l] = ha;
   }
-  if (f->levels > 1) {
-    DSLAM_CUDA(launch_downsample(L, s->stream));
+  if (d.B256 != Bd) f->dev_dirty = true;
+  d.B256 = Bd;
+  if (f->dev_dirty) {
+    DSLAM_CUDA(cudaMemcpyAsync(f->dev, &f->devh, sizeof(FrameDev), cudaMemcpyHostToDevice, s->stream));
+    f->dev_dirty = false;
+  }
+  return DSLAM_OK;
+}
+
+// two launches for every run of <= kMaxFramesPerLaunch frames with the same geometry
+static int frames_build(int n, dslam_frame *const *frames, const float *B256, bool stage_dIp, bool stage_abs) {
+  for (int i = 0; i < n; i++) {
+    if (!frames[i]) return fail(DSLAM_EINVAL, "null frame");
+    if (!frames[i]->uploaded) return fail(DSLAM_ESTATE, "dslam_frame_build before dslam_frame_upload");
+    if (frames[i]->s != frames[0]->s) return fail(DSLAM_EINVAL, "all frames of a batch must live in one session");
+    const int rc = frame_prepare(frames[i], B256, stage_dIp, stage_abs);
+    if (rc != DSLAM_OK) return rc;
+  }
+  dslam_session *s = frames[0]->s;
+  int i = 0;
+  while (i < n) {
+    FrameBatch B;
+    B.G = frames[i]->geom;
+    int cnt = 0;
+    while (i + cnt < n && cnt < kMaxFramesPerLaunch && same_geometry(frames[i], frames[i + cnt])) {
+      B.f[cnt] = frames[i + cnt]->dev;
+      cnt++;
+    }
+    if (B.G.levels > 1) {
+      DSLAM_CUDA(launch_downsample(B, cnt, s->stream));
+      s->launches++;
+    }
+    DSLAM_CUDA(launch_gradients(B, cnt, s->stream));
     s->launches++;
+    for (int k = 0; k < cnt; k++) {
+      frames[i + k]->built = true;
+      frames[i + k]->staged = stage_dIp || stage_abs;
+    }
+    i += cnt;
   }
-  DSLAM_CUDA(launch_gradients(L, f->maps, Bd, s->stream));
-  s->launches++;
-  f->built = true;
-  f->staged = stage_dIp || stage_abs;
   return DSLAM_OK;
 }
 
 int dslam_frame_build(dslam_frame *f, const float *B256) {
   if (!f) return fail(DSLAM_EINVAL, "null frame");
-  return frame_build_impl(f, B256, false, false);
+  return frames_build(1, &f, B256, false, false);
+}
+
+int dslam_frame_build_batch(int n, dslam_frame *const *frames, const float *B256, int stage_host) {
+  if (n < 1 || !frames) return fail(DSLAM_EINVAL, "bad argument");
+  return frames_build(n, frames, B256, (stage_host & 1) != 0, (stage_host & 2) != 0);
 }
 
 static int frame_copy_out(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad) {
@@ -858,16 +950,12 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
   if (!have) {
     const int rc = frame_ensure_staging(f, need_d, need_a);
     if (rc != DSLAM_OK) return rc;
-    PyramidLevels L = f->L;
-    for (int l = 0; l < f->levels; l++) {
-      L.host_dIp[l] = f->stage_dIp ? f->stage_dIp + 3 * f->px_off[l] : nullptr;
-      L.host_abs[l] = f->stage_abs ? f->stage_abs + f->px_off[l] : nullptr;
-    }
-    if (f->host_pending) {
-      DSLAM_CUDA(cudaStreamWaitEvent(f->s->stream, f->host_ready, 0));
-      f->host_pending = false;
-    }
-    DSLAM_CUDA(launch_unpack(L, f->s->stream));
+    const int rp = frame_prepare(f, nullptr, f->stage_dIp != nullptr, f->stage_abs != nullptr);
+    if (rp != DSLAM_OK) return rp;
+    FrameBatch B;
+    B.G = f->geom;
+    B.f[0] = f->dev;
+    DSLAM_CUDA(launch_unpack(B, 1, f->s->stream));
     f->s->launches++;
     f->staged = true;
   }
@@ -883,7 +971,7 @@ int dslam_frame_wait_host(dslam_frame *f) {
 int dslam_frame_make_images(dslam_frame *f, const float *color, const float *B256, float *const *host_dIp, float *const *host_absgrad) {
   int rc = dslam_frame_upload(f, color);
   if (rc != DSLAM_OK) return rc;
-  rc = frame_build_impl(f, B256, host_dIp != nullptr, host_absgrad != nullptr);
+  rc = frames_build(1, &f, B256, host_dIp != nullptr, host_absgrad != nullptr);
   if (rc != DSLAM_OK) return rc;
   if (host_dIp || host_absgrad) return frame_copy_out(f, host_dIp, host_absgrad);
   return DSLAM_OK;
@@ -1094,7 +1182,7 @@ int dslam_pose_eval(dslam_ctx *c, dslam_frame *f, float new_exposure, int lvl, i
     items.assign((size_t)cnt, EvalItem());
     for (int i = 0; i < cnt; i++)
       fill_pose_item(items[i], c, f, new_exposure, lvl, hm::Se3::from7(pose7 + 7 * (size_t)(base + i)), aff_ab + 2 * (size_t)(base + i), cutoffTH);
-    rc = run_items(c->s, 0, items, outs, &c->n_launches);
+    rc = run_items(c->s, items, outs, &c->n_launches);
     if (rc != DSLAM_OK) return rc;
     c->n_evals += cnt;
     for (int i = 0; i < cnt; i++) {
@@ -1123,7 +1211,7 @@ int dslam_scale_eval(dslam_ctx *c, dslam_frame *f_right, int lvl, int nb, const 
     const int cnt = nb - base < kResultSlots ? nb - base : kResultSlots;
     items.assign((size_t)cnt, EvalItem());
     for (int i = 0; i < cnt; i++) fill_scale_item(items[i], c, f_right, lvl, scales[base + i], cutoffTH);
-    rc = run_items(c->s, 1, items, outs, &c->n_launches);
+    rc = run_items(c->s, items, outs, &c->n_launches);
     if (rc != DSLAM_OK) return rc;
     c->n_evals += cnt;
     for (int i = 0; i < cnt; i++) {
@@ -1138,6 +1226,72 @@ int dslam_scale_eval(dslam_ctx *c, dslam_frame *f_right, int lvl, int nb, const 
 }
 
 // ---- Levenberg-Marquardt drivers ---------------------------------------------------------------------
+// n_pose tracking jobs and n_scale scale-optimisation jobs (independent of each other: different tracker objects,
+// frames or streams) advanced in lock step; every round of ALL of them is one kernel launch.
+int dslam_lm_batch(int n_pose, dslam_ctx *const *pose_ctxs, dslam_frame *const *pose_frames, const float *new_exposure, double *pose7_io,
+                   double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3, int *ok, int n_scale,
+                   dslam_ctx *const *scale_ctxs, dslam_frame *const *scale_frames, float *scales_io, int scale_coarsestLvl, float *rmse_out) {
+  if (n_pose < 0 || n_scale < 0 || n_pose + n_scale < 1 || n_pose + n_scale > kResultSlots) return fail(DSLAM_EINVAL, "bad job counts");
+  if (n_pose > 0 && (!pose_ctxs || !pose_frames || !pose7_io || !aff_io || !minResForAbort)) return fail(DSLAM_EINVAL, "null pose argument");
+  if (n_scale > 0 && (!scale_ctxs || !scale_frames || !scales_io)) return fail(DSLAM_EINVAL, "null scale argument");
+  dslam_session *s = n_pose > 0 ? (pose_ctxs[0] ? pose_ctxs[0]->s : nullptr) : (scale_ctxs[0] ? scale_ctxs[0]->s : nullptr);
+  for (int i = 0; i < n_pose; i++) {
+    const int rc = check_ctx_frame(pose_ctxs[i], pose_frames[i], coarsestLvl);
+    if (rc != DSLAM_OK) return rc;
+    if (pose_ctxs[i]->s != s) return fail(DSLAM_EINVAL, "all jobs of a batch must live in one session");
+  }
+  for (int i = 0; i < n_scale; i++) {
+    const int rc = check_ctx_frame(scale_ctxs[i], scale_frames[i], scale_coarsestLvl);
+    if (rc != DSLAM_OK) return rc;
+    if (scale_ctxs[i]->s != s) return fail(DSLAM_EINVAL, "all jobs of a batch must live in one session");
+  }
+  std::vector<PoseLM> pose((size_t)n_pose);
+  std::vector<ScaleLM> scale((size_t)n_scale);
+  for (int i = 0; i < n_pose; i++) pose_ctxs[i]->trace.clear();
+  for (int i = 0; i < n_scale; i++) scale_ctxs[i]->trace.clear();
+  for (int i = 0; i < n_pose; i++)
+    pose[i].begin(pose_ctxs[i], pose_frames[i], new_exposure ? new_exposure[i] : 1.0f, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort,
+                  &pose_ctxs[i]->trace);
+  for (int i = 0; i < n_scale; i++) {
+    // a tracker object that also tracks in this batch keeps the pose trace; its scale trace is not recorded
+    bool also_pose = false;
+    for (int j = 0; j < n_pose; j++) also_pose |= pose_ctxs[j] == scale_ctxs[i];
+    scale[i].begin(scale_ctxs[i], scale_frames[i], scales_io[i], scale_coarsestLvl, also_pose ? nullptr : &scale_ctxs[i]->trace);
+  }
+  dslam_ctx *counters = n_pose > 0 ? pose_ctxs[0] : scale_ctxs[0];
+  const int rc = run_lock_step(s, pose, scale, counters);
+  if (rc != DSLAM_OK) return rc;
+  for (int i = 0; i < n_pose; i++) {
+    pose_ctxs[i]->n_iters += pose[i].iters;
+    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, pose[i].lastResiduals, sizeof(double) * 5);
+    if (flow3) std::memcpy(flow3 + 3 * i, pose[i].flow, sizeof(double) * 3);
+    const bool good = finish_pose(pose_ctxs[i], pose[i], new_exposure ? new_exposure[i] : 1.0f, pose7_io + 7 * i, aff_io + 2 * i);
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+  for (int i = 0; i < n_scale; i++) {
+    scale_ctxs[i]->n_iters += scale[i].iters;
+    scales_io[i] = scale[i].scale_current;                 // :954
+    if (rmse_out) rmse_out[i] = scale[i].last_residuals[0];  // :963
+  }
+  return DSLAM_OK;
+}
+
+int dslam_track_newest_coarse_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames, const float *new_exposure, double *pose7_io,
+                                    double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3,
+                                    int *ok) {
+  if (n < 1) return fail(DSLAM_EINVAL, "bad argument");
+  return dslam_lm_batch(n, ctxs, frames, new_exposure, pose7_io, aff_io, coarsestLvl, minResForAbort, lastResiduals, flow3, ok, 0, nullptr, nullptr,
+                        nullptr, 0, nullptr);
+}
+
+int dslam_optimize_scale_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames_right, float *scales_io, int coarsestLvl,
+                               float *rmse_out) {
+  if (n < 1) return fail(DSLAM_EINVAL, "bad argument");
+  return dslam_lm_batch(0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, n, ctxs, frames_right, scales_io,
+                        coarsestLvl, rmse_out);
+}
+
+// several pose hypotheses of ONE tracker object / frame (the retry loop of FrontEnd::trackNewCoarse, src/FrontEnd.cpp:147-247)
 int dslam_track_newest_coarse_multi(dslam_ctx *c, dslam_frame *f, float new_exposure, int nhyp, double *pose7_io, double *aff_io,
                                     int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3, int *ok) {
   int rc = check_ctx_frame(c, f, coarsestLvl);
@@ -1145,33 +1299,15 @@ int dslam_track_newest_coarse_multi(dslam_ctx *c, dslam_frame *f, float new_expo
   if (nhyp < 1 || nhyp > kResultSlots || !pose7_io || !aff_io || !minResForAbort) return fail(DSLAM_EINVAL, "bad argument");
   c->trace.clear();
   std::vector<PoseLM> lms((size_t)nhyp);
+  std::vector<ScaleLM> none;
   for (int i = 0; i < nhyp; i++) lms[i].begin(c, f, new_exposure, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort, i == 0 ? &c->trace : nullptr);
-  rc = run_lock_step(c->s, 0, lms, c);
+  rc = run_lock_step(c->s, lms, none, c);
   if (rc != DSLAM_OK) return rc;
   for (int i = 0; i < nhyp; i++) {
-    PoseLM &m = lms[i];
-    c->n_iters += m.iters;
-    bool good = m.ok;
-    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, m.lastResiduals, sizeof(double) * 5);
-    if (flow3) std::memcpy(flow3 + 3 * i, m.flow, sizeof(double) * 3);
-    if (good) {
-      // :612-637  outputs are only written when the level loop ran to completion
-      m.cur.to7(pose7_io + 7 * i);
-      double *aff = aff_io + 2 * i;
-      aff[0] = m.aff_cur[0];
-      aff[1] = m.aff_cur[1];
-      if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) good = false;
-      if (good) {
-        double rel[2];
-        hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], rel);
-        const float relA = (float)rel[0], relB = (float)rel[1];
-        if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) good = false;
-      }
-      if (good) {
-        if (c->affModeA < 0) aff[0] = 0;
-        if (c->affModeB < 0) aff[1] = 0;
-      }
-    }
+    c->n_iters += lms[i].iters;
+    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, lms[i].lastResiduals, sizeof(double) * 5);
+    if (flow3) std::memcpy(flow3 + 3 * i, lms[i].flow, sizeof(double) * 3);
+    const bool good = finish_pose(c, lms[i], new_exposure, pose7_io + 7 * i, aff_io + 2 * i);
     if (ok) ok[i] = good ? 1 : 0;
   }
   return DSLAM_OK;
@@ -1182,91 +1318,21 @@ int dslam_track_newest_coarse(dslam_ctx *c, dslam_frame *f, float new_exposure, 
   return dslam_track_newest_coarse_multi(c, f, new_exposure, 1, pose7_io, aff_io, coarsestLvl, minResForAbort, lastResiduals, flow3, ok);
 }
 
+// several scale seeds of ONE tracker object / right frame (the seed loop of FrontEnd::optimizeScale, src/FrontEnd.cpp:995-1003)
 int dslam_optimize_scale_multi(dslam_ctx *c, dslam_frame *f_right, int nseeds, float *scales_io, int coarsestLvl, float *rmse_out) {
   int rc = check_ctx_frame(c, f_right, coarsestLvl);
   if (rc != DSLAM_OK) return rc;
   if (nseeds < 1 || nseeds > kResultSlots || !scales_io) return fail(DSLAM_EINVAL, "bad argument");
   c->trace.clear();
+  std::vector<PoseLM> none;
   std::vector<ScaleLM> lms((size_t)nseeds);
   for (int i = 0; i < nseeds; i++) lms[i].begin(c, f_right, scales_io[i], coarsestLvl, i == 0 ? &c->trace : nullptr);
-  rc = run_lock_step(c->s, 1, lms, c);
+  rc = run_lock_step(c->s, none, lms, c);
   if (rc != DSLAM_OK) return rc;
   for (int i = 0; i < nseeds; i++) {
     c->n_iters += lms[i].iters;
-    scales_io[i] = lms[i].scale_current;               // :954
+    scales_io[i] = lms[i].scale_current;                   // :954
     if (rmse_out) rmse_out[i] = lms[i].last_residuals[0];  // :963
-  }
-  return DSLAM_OK;
-}
-
-// Independent stereo streams (one tracker object + one frame each) advanced in lock step: every LM round of all of
-// them is one kernel launch.  Same results as n sequential calls.
-int dslam_track_newest_coarse_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames, const float *new_exposure, double *pose7_io,
-                                    double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3,
-                                    int *ok) {
-  if (n < 1 || n > kResultSlots || !ctxs || !frames || !pose7_io || !aff_io || !minResForAbort) return fail(DSLAM_EINVAL, "bad argument");
-  for (int i = 0; i < n; i++) {
-    const int rc = check_ctx_frame(ctxs[i], frames[i], coarsestLvl);
-    if (rc != DSLAM_OK) return rc;
-    if (ctxs[i]->s != ctxs[0]->s) return fail(DSLAM_EINVAL, "all streams of a batch must live in one session");
-  }
-  std::vector<PoseLM> lms((size_t)n);
-  for (int i = 0; i < n; i++) {
-    ctxs[i]->trace.clear();
-    lms[i].begin(ctxs[i], frames[i], new_exposure ? new_exposure[i] : 1.0f, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort,
-                 &ctxs[i]->trace);
-  }
-  const int rc = run_lock_step(ctxs[0]->s, 0, lms, ctxs[0]);
-  if (rc != DSLAM_OK) return rc;
-  for (int i = 0; i < n; i++) {
-    PoseLM &m = lms[i];
-    dslam_ctx *c = ctxs[i];
-    c->n_iters += m.iters;
-    bool good = m.ok;
-    if (lastResiduals) std::memcpy(lastResiduals + 5 * i, m.lastResiduals, sizeof(double) * 5);
-    if (flow3) std::memcpy(flow3 + 3 * i, m.flow, sizeof(double) * 3);
-    if (good) {
-      m.cur.to7(pose7_io + 7 * i);
-      double *aff = aff_io + 2 * i;
-      aff[0] = m.aff_cur[0];
-      aff[1] = m.aff_cur[1];
-      const float ne = new_exposure ? new_exposure[i] : 1.0f;
-      if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) good = false;
-      if (good) {
-        double rel[2];
-        hm::aff_from_to(c->ref_exposure, ne, c->ref_a, c->ref_b, aff[0], aff[1], rel);
-        const float relA = (float)rel[0], relB = (float)rel[1];
-        if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) good = false;
-      }
-      if (good) {
-        if (c->affModeA < 0) aff[0] = 0;
-        if (c->affModeB < 0) aff[1] = 0;
-      }
-    }
-    if (ok) ok[i] = good ? 1 : 0;
-  }
-  return DSLAM_OK;
-}
-
-int dslam_optimize_scale_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames_right, float *scales_io, int coarsestLvl,
-                               float *rmse_out) {
-  if (n < 1 || n > kResultSlots || !ctxs || !frames_right || !scales_io) return fail(DSLAM_EINVAL, "bad argument");
-  for (int i = 0; i < n; i++) {
-    const int rc = check_ctx_frame(ctxs[i], frames_right[i], coarsestLvl);
-    if (rc != DSLAM_OK) return rc;
-    if (ctxs[i]->s != ctxs[0]->s) return fail(DSLAM_EINVAL, "all streams of a batch must live in one session");
-  }
-  std::vector<ScaleLM> lms((size_t)n);
-  for (int i = 0; i < n; i++) {
-    ctxs[i]->trace.clear();
-    lms[i].begin(ctxs[i], frames_right[i], scales_io[i], coarsestLvl, &ctxs[i]->trace);
-  }
-  const int rc = run_lock_step(ctxs[0]->s, 1, lms, ctxs[0]);
-  if (rc != DSLAM_OK) return rc;
-  for (int i = 0; i < n; i++) {
-    ctxs[i]->n_iters += lms[i].iters;
-    scales_io[i] = lms[i].scale_current;
-    if (rmse_out) rmse_out[i] = lms[i].last_residuals[0];
   }
   return DSLAM_OK;
 }

@@ -54,8 +54,11 @@ struct dslam_session {
 struct dslam_frame {
   dslam_session *s = nullptr;
   int w = 0, h = 0, levels = 0;
-  dslam::PyramidLevels L{};
-  dslam::PyramidMaps maps{};
+  dslam::PyramidLevels L{};    // host view: sizes, pitches, device pointers
+  dslam::PyramidGeom geom{};   // the part of it the kernels take by value
+  dslam::FrameDev devh{};      // host copy of the device-resident descriptor (pointers + tensor maps)
+  dslam::FrameDev *dev = nullptr;
+  bool dev_dirty = true;
   void *block = nullptr;       // one allocation: intensity planes + texels
   float *stage_dIp = nullptr;  // device staging in the reference host layout, all levels contiguous (lazy)
   float *stage_abs = nullptr;

@@ -76,18 +76,38 @@ struct PyramidLevels {
   int tile_begin[kMaxLevels + 1];  // prefix of gradient tiles per level (kernel B)
   int tiles_x[kMaxLevels];
 };
-struct PyramidMaps {
-  CUtensorMap map[kMaxLevels];  // 2-D fp32 tensor maps over plane[l], box = (kGradBoxW x kGradBoxH)
-};
 constexpr int kGradTileW = 64, kGradTileH = 16;
 constexpr int kGradBoxW = kGradTileW + 8;  // 72 floats = 288 B; the box starts at x0-4 because TMA needs a 16-B aligned source address
 constexpr int kGradBoxH = kGradTileH + 2;
 constexpr int kDownTileW = 64, kDownTileH = 32;  // level-0 tile of the box-mean chain
 
-cudaError_t launch_downsample(const PyramidLevels &L, cudaStream_t stream);
-cudaError_t launch_gradients(const PyramidLevels &L, const PyramidMaps &maps, const float *B256_dev, cudaStream_t stream);
+// Device-resident description of one frame (pointers + tensor maps); the pyramid kernels take a batch of these so
+// that all frames of a step are built by two launches in total.
+struct alignas(128) FrameDev {
+  CUtensorMap map[kMaxLevels];  // first: keeps the 64-B descriptor alignment
+  float *plane[kMaxLevels];
+  float4 *tex[kMaxLevels];
+  float *host_dIp[kMaxLevels];  // staging copies in the reference host layouts, or null
+  float *host_abs[kMaxLevels];
+  const float *B256;            // gamma table or null
+};
+constexpr int kMaxFramesPerLaunch = 64;
+struct PyramidGeom {
+  int levels;
+  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  int tile_begin[kMaxLevels + 1];
+  int tiles_x[kMaxLevels];
+};
+struct FrameBatch {
+  PyramidGeom G;
+  const FrameDev *f[kMaxFramesPerLaunch];
+};
+// all frames of the batch share the geometry G
+cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t stream);
+cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream);
 // texels -> the reference's host layouts (Vector3f AoS + float plane) for a frame built without staging
-cudaError_t launch_unpack(const PyramidLevels &L, cudaStream_t stream);
+cudaError_t launch_unpack(const FrameBatch &B, int nframes, cudaStream_t stream);
+cudaError_t launch_scale_idepth(float4 *pts, int n, float scale, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------
 // template kernels (kernels_template.cu): makeCoarseDepthL0 / scaleCoarseDepthL0 on the device

@@ -1,4 +1,4 @@
-// kernels_pyramid.cu — image pyramid of one frame on the device.  sm_100a.
+// kernels_pyramid.cu — image pyramids of a batch of frames on the device.  sm_100a.
 //
 // Replaces FrameHessian::makeImages  deps:dso/src/FullSystem/HessianBlocks.cpp:128-191:
 //   level 0 channel 0 = input; level k channel 0 = 0.25f * (((a + b) + c) + d) of the 2x2 block of level k-1
@@ -9,15 +9,17 @@
 //   (:182-188, getBGradOnly deps:dso/src/FullSystem/HessianBlocks.h:384-390) when a B table is given.
 //   Rows 0 and h-1 (uninitialised in the reference) are written as dx = dy = absSquaredGrad = 0.
 //
-// Two launches per frame, both bit-exact (compiled -fmad=false; only adds, multiplies by 0.25f/0.5f and the
-// squared-gradient sum are involved):
+// Two launches for ALL frames of a batch (blockIdx.z / blockIdx.y = frame), both bit-exact (compiled -fmad=false;
+// only adds, multiplies by 0.25f/0.5f and the squared-gradient sum are involved):
 //   A  downsample_chain_kernel : one CTA per 64x32 level-0 tile builds the intensity of levels 1..L-1 through
 //      shared memory (float2 coalesced loads, every level written once);
 //   B  gradient_kernel         : one CTA per 64x16 tile of ANY level (all levels in one grid); the (64+8)x(16+2)
 //      halo box of the intensity plane is staged into shared memory by TMA (cp.async.bulk.tensor.2d, zero
-//      fill outside the image, completion on an mbarrier); each thread emits one float4 texel
-//      (I, dx, dy, absSquaredGrad) per pixel — 16-B coalesced stores — plus, when the host wants the
-//      reference's layouts, the Vector3f AoS / float plane staging copies that are then DMA'd to the host.
+//      fill outside the image, completion on an mbarrier; the box starts at x0-4 because the TMA source address
+//      must be 16-byte aligned); each thread emits one float4 texel (I, dx, dy, absSquaredGrad) per pixel —
+//      16-B coalesced stores — plus, when the host wants the reference's layouts, the Vector3f AoS / float plane
+//      staging copies that are then DMA'd to the host.
+// Per-frame pointers and tensor maps live in a device-resident FrameDev record; the launch carries only pointers to them.
 // Algorithmic traffic: read 4*P0, write 16*sum(P_l) (+16*sum(P_l) staging when host copies are requested).
 
 #include "dslam_kernels.h"
@@ -29,12 +31,6 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 // A: box-mean chain
 // ---------------------------------------------------------------------------------------------------
-struct DownParams {
-  int levels;
-  int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
-  float *plane[kMaxLevels];
-};
-
 template <int TW, int TH>  // tile of the level being produced; source in shared memory has size 2TW x 2TH
 __device__ __forceinline__ void down_from_smem(const float *src, float *dst_s, float *dst_g, int pitch, int x0, int y0, int w, int h,
                                                int tid) {
@@ -49,13 +45,18 @@ __device__ __forceinline__ void down_from_smem(const float *src, float *dst_s, f
   }
 }
 
-__global__ void __launch_bounds__(256) downsample_chain_kernel(const __grid_constant__ DownParams P) {
+__global__ void __launch_bounds__(256) downsample_chain_kernel(const __grid_constant__ FrameBatch B) {
   __shared__ float s1[32 * 16], s2[16 * 8], s3[8 * 4], s4[4 * 2], s5[2];
+  __shared__ float *s_plane[kMaxLevels];
   const int tid = threadIdx.x;
+  const PyramidGeom &P = B.G;
+  if (tid < kMaxLevels) s_plane[tid] = B.f[blockIdx.z]->plane[tid];
+  __syncthreads();
   const int X0 = blockIdx.x * kDownTileW, Y0 = blockIdx.y * kDownTileH;  // level-0 origin of the tile
   // level 1 from global level 0 (float2 loads; pitch is a multiple of 4 floats, x even -> 8-B aligned)
   {
-    const float *src = P.plane[0];
+    const float *src = s_plane[0];
+    float *dst = s_plane[1];
     const int pitch0 = P.pitch[0], w0 = P.w[0], h0 = P.h[0];
     const int w1 = P.w[1], h1 = P.h[1], x10 = X0 >> 1, y10 = Y0 >> 1;
     for (int p = tid; p < 32 * 16; p += 256) {
@@ -66,23 +67,23 @@ __global__ void __launch_bounds__(256) downsample_chain_kernel(const __grid_cons
         const float2 r0 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(2 * y) * pitch0 + 2 * x));
         const float2 r1 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(2 * y + 1) * pitch0 + 2 * x));
         v = 0.25f * (r0.x + r0.y + r1.x + r1.y);
-        if (x < w1 && y < h1) P.plane[1][(size_t)y * P.pitch[1] + x] = v;
+        if (x < w1 && y < h1) dst[(size_t)y * P.pitch[1] + x] = v;
       }
       s1[p] = v;
     }
   }
   if (P.levels <= 2) return;
   __syncthreads();
-  down_from_smem<16, 8>(s1, s2, P.plane[2], P.pitch[2], X0 >> 2, Y0 >> 2, P.w[2], P.h[2], tid);
+  down_from_smem<16, 8>(s1, s2, s_plane[2], P.pitch[2], X0 >> 2, Y0 >> 2, P.w[2], P.h[2], tid);
   if (P.levels <= 3) return;
   __syncthreads();
-  down_from_smem<8, 4>(s2, s3, P.plane[3], P.pitch[3], X0 >> 3, Y0 >> 3, P.w[3], P.h[3], tid);
+  down_from_smem<8, 4>(s2, s3, s_plane[3], P.pitch[3], X0 >> 3, Y0 >> 3, P.w[3], P.h[3], tid);
   if (P.levels <= 4) return;
   __syncthreads();
-  down_from_smem<4, 2>(s3, s4, P.plane[4], P.pitch[4], X0 >> 4, Y0 >> 4, P.w[4], P.h[4], tid);
+  down_from_smem<4, 2>(s3, s4, s_plane[4], P.pitch[4], X0 >> 4, Y0 >> 4, P.w[4], P.h[4], tid);
   if (P.levels <= 5) return;
   __syncthreads();
-  down_from_smem<2, 1>(s4, s5, P.plane[5], P.pitch[5], X0 >> 5, Y0 >> 5, P.w[5], P.h[5], tid);
+  down_from_smem<2, 1>(s4, s5, s_plane[5], P.pitch[5], X0 >> 5, Y0 >> 5, P.w[5], P.h[5], tid);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -109,6 +110,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
       "r"(phase)
       : "memory");
 }
+// The tensor map lives in global memory (written by the host before the launch): make it visible to the
+// tensor-map proxy of this SM before the first use.
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap *map) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst)),
@@ -116,25 +122,21 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                : "memory");
 }
 
-struct GradParams {
-  PyramidLevels L;
-  const float *B256;  // device gamma table or null
-};
-
-__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ GradParams P, const __grid_constant__ PyramidMaps maps) {
+__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ FrameBatch B) {
   __shared__ __align__(128) float box[kGradBoxH * kGradBoxW];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
+  const PyramidGeom &G = B.G;
+  const FrameDev *__restrict__ F = B.f[blockIdx.y];
   // which level / tile
   int lvl = 0;
 #pragma unroll
   for (int l = 1; l < kMaxLevels; l++)
-    if (l < P.L.levels && (int)blockIdx.x >= P.L.tile_begin[l]) lvl = l;
-  const int t = blockIdx.x - P.L.tile_begin[lvl];
-  const int tx = t % P.L.tiles_x[lvl], ty = t / P.L.tiles_x[lvl];
+    if (l < G.levels && (int)blockIdx.x >= G.tile_begin[l]) lvl = l;
+  const int t = blockIdx.x - G.tile_begin[lvl];
+  const int tx = t % G.tiles_x[lvl], ty = t / G.tiles_x[lvl];
   const int x0 = tx * kGradTileW, y0 = ty * kGradTileH;
-  const int w = P.L.w[lvl], h = P.L.h[lvl], pitch = P.L.pitch[lvl];
-  const float *__restrict__ plane = P.L.plane[lvl];
+  const int w = G.w[lvl], h = G.h[lvl], pitch = G.pitch[lvl];
 
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -142,15 +144,18 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ G
   }
   __syncthreads();
   if (tid == 0) {
+    const CUtensorMap *map = &F->map[lvl];
+    tensormap_acquire(map);
     mbar_expect_tx(&bar, kGradBoxH * kGradBoxW * sizeof(float));
-    tma_load_2d(box, &maps.map[lvl], x0 - 4, y0 - 1, &bar);
+    tma_load_2d(box, map, x0 - 4, y0 - 1, &bar);
   }
+  const float *__restrict__ plane = F->plane[lvl];
+  float4 *__restrict__ tex = F->tex[lvl];
+  float *__restrict__ hd = F->host_dIp[lvl];
+  float *__restrict__ ha = F->host_abs[lvl];
+  const float *__restrict__ Bt = F->B256;
   mbar_wait(&bar, 0);
 
-  float4 *__restrict__ tex = P.L.tex[lvl];
-  float *__restrict__ hd = P.L.host_dIp[lvl];
-  float *__restrict__ ha = P.L.host_abs[lvl];
-  const float *__restrict__ B = P.B256;
 #pragma unroll
   for (int k = 0; k < kGradTileH / 4; k++) {
     const int lx = tid % kGradTileW, ly = tid / kGradTileW + 4 * k;
@@ -168,11 +173,11 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ G
       if (!isfinite(dx)) dx = 0.f;
       if (!isfinite(dy)) dy = 0.f;
       ag = dx * dx + dy * dy;
-      if (B != nullptr) {
+      if (Bt != nullptr) {
         int ci = (int)(c + 0.5f);
         if (ci < 5) ci = 5;
         if (ci > 250) ci = 250;
-        const float gw = __ldg(B + ci + 1) - __ldg(B + ci);
+        const float gw = __ldg(Bt + ci + 1) - __ldg(Bt + ci);
         ag *= gw * gw;
       }
     }
@@ -189,19 +194,21 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ G
 
 // texels -> staging copies in the reference's host layouts, all levels in one grid (for frames that were
 // built before the host asked for its copies)
-__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ GradParams P, int total) {
+__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ FrameBatch B, int total) {
+  const PyramidGeom &G = B.G;
+  const FrameDev *__restrict__ F = B.f[blockIdx.y];
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
     int lvl = 0, base = 0, acc = 0;
 #pragma unroll
     for (int l = 0; l < kMaxLevels; l++) {
-      if (l < P.L.levels) {
+      if (l < G.levels) {
         if (i >= acc) { lvl = l; base = acc; }
-        acc += P.L.w[l] * P.L.h[l];
+        acc += G.w[l] * G.h[l];
       }
     }
     const int idx = i - base;
-    const float4 t = P.L.tex[lvl][idx];
-    float *hd = P.L.host_dIp[lvl], *ha = P.L.host_abs[lvl];
+    const float4 t = F->tex[lvl][idx];
+    float *hd = F->host_dIp[lvl], *ha = F->host_abs[lvl];
     if (hd != nullptr) {
       hd[3 * (size_t)idx + 0] = t.x;
       hd[3 * (size_t)idx + 1] = t.y;
@@ -211,9 +218,6 @@ __global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ Gra
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// template helpers
-// ---------------------------------------------------------------------------------------------------
 // scaleCoarseDepthL0  src/scale_optimization/TrackerAndScaler.cpp:329-336  (IEEE division, like the host loop)
 __global__ void scale_idepth_kernel(float4 *__restrict__ pts, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,35 +226,26 @@ __global__ void scale_idepth_kernel(float4 *__restrict__ pts, int n, float scale
 
 }  // namespace
 
-cudaError_t launch_downsample(const PyramidLevels &L, cudaStream_t stream) {
-  if (L.levels < 2) return cudaSuccess;
-  DownParams P;
-  P.levels = L.levels;
-  for (int l = 0; l < kMaxLevels; l++) {
-    P.w[l] = L.w[l]; P.h[l] = L.h[l]; P.pitch[l] = L.pitch[l]; P.plane[l] = L.plane[l];
-  }
-  dim3 grid((L.w[0] + kDownTileW - 1) / kDownTileW, (L.h[0] + kDownTileH - 1) / kDownTileH);
-  downsample_chain_kernel<<<grid, 256, 0, stream>>>(P);
+cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t stream) {
+  if (B.G.levels < 2 || nframes < 1) return cudaSuccess;
+  dim3 grid((B.G.w[0] + kDownTileW - 1) / kDownTileW, (B.G.h[0] + kDownTileH - 1) / kDownTileH, nframes);
+  downsample_chain_kernel<<<grid, 256, 0, stream>>>(B);
   return cudaGetLastError();
 }
 
-cudaError_t launch_gradients(const PyramidLevels &L, const PyramidMaps &maps, const float *B256_dev, cudaStream_t stream) {
-  GradParams P;
-  P.L = L;
-  P.B256 = B256_dev;
-  gradient_kernel<<<L.tile_begin[L.levels], 256, 0, stream>>>(P, maps);
+cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream) {
+  if (nframes < 1) return cudaSuccess;
+  gradient_kernel<<<dim3(B.G.tile_begin[B.G.levels], nframes), 256, 0, stream>>>(B);
   return cudaGetLastError();
 }
 
-cudaError_t launch_unpack(const PyramidLevels &L, cudaStream_t stream) {
-  GradParams P;
-  P.L = L;
-  P.B256 = nullptr;
+cudaError_t launch_unpack(const FrameBatch &B, int nframes, cudaStream_t stream) {
+  if (nframes < 1) return cudaSuccess;
   int total = 0;
-  for (int l = 0; l < L.levels; l++) total += L.w[l] * L.h[l];
-  int grid = (total + 255) / 256;
-  if (grid > 148 * 8) grid = 148 * 8;
-  unpack_kernel<<<grid, 256, 0, stream>>>(P, total);
+  for (int l = 0; l < B.G.levels; l++) total += B.G.w[l] * B.G.h[l];
+  int gx = (total + 255) / 256;
+  if (gx > 148 * 8) gx = 148 * 8;
+  unpack_kernel<<<dim3(gx, nframes), 256, 0, stream>>>(B, total);
   return cudaGetLastError();
 }
 

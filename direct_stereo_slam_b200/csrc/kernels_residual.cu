@@ -105,36 +105,30 @@ __device__ __forceinline__ float3 interp33(const float4 *__restrict__ tex, float
 
 constexpr float kHuberTH = 9.0f;  // setting_huberTH  deps:dso/src/util/settings.cpp:127
 
-template <int MODE, int CAP>
+template <int CAP>
 struct BatchT {
   EvalItem item[CAP];
 };
 
-// MODE 0 = pose, 1 = scale.  grid = (max nblocks over items, nitems), block = kEvalThreads.
-template <int MODE, int CAP>
-__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constant__ BatchT<MODE, CAP> batch, EvalScratch scratch,
-                                                           EvalResult *__restrict__ results, unsigned seq) {
-  constexpr int NV = MODE == 0 ? kPoseVals : kScaleVals;
-  constexpr int NW = kEvalThreads / 32;
-  const EvalItem &it = batch.item[blockIdx.y];
-  if ((int)blockIdx.x >= it.nblocks) return;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Per-point work of one item.  MODE 0 = pose (calcResPose + calcGSSSEPose), 1 = scale (calcResScale + calcGSSSEScale).
+// acc layout: pose  [0..44] upper triangle of [J0..J7 r]^T w [J0..J7 r], [45] E, [46] shiftT, [47] shiftRT
+//             scale [0] JwJ, [1] Jwr, [2] rwr, [3] E, [4] shiftT, [5] shiftRT
+template <int MODE, int NV>
+__device__ __forceinline__ void eval_points(const EvalItem &it, double (&acc)[NV], int &nE, int &nSat, int &nInl) {
+  const int tid = threadIdx.x;
   const float4 *__restrict__ tex = it.tex;
   const float4 *__restrict__ pts = it.pts;
-  const int wl = it.w, hl = it.h;
+  const int wl = it.w, hl = it.h, n = it.n, stride = it.ppt_stride;
   const float fxl = it.fx, fyl = it.fy, cxl = it.cx, cyl = it.cy;
   const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
   const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
-  const bool flow = (it.flags & 1) != 0;
+  constexpr int iE = MODE == 0 ? 45 : 3, iT = MODE == 0 ? 46 : 4, iRT = MODE == 0 ? 47 : 5;
 
-  double acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; i++) acc[i] = 0.0;
-  int nE = 0, nSat = 0, nInl = 0;
-
-  for (int i = blockIdx.x * kEvalThreads + tid; i < it.n; i += it.ppt_stride) {
-    const float4 p = __ldg(pts + i);
+  int i = blockIdx.x * kEvalThreads + tid;
+  float4 p_next = i < n ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; i < n; i += stride) {
+    const float4 p = p_next;
+    if (i + stride < n) p_next = __ldg(pts + i + stride);  // the next record is in flight while this point is processed
     const float x = p.x, y = p.y, id = p.z, refColor = p.w;
     float pt0, pt1, pt2, rx0 = 0.f, rx1 = 0.f, rx2 = 0.f;
     if (MODE == 0) {
@@ -148,49 +142,12 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
       pt0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y) + it.t[0] * id;
       pt1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y) + it.t[1] * id;
       pt2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y) + it.t[2] * id;
-      rx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) / id;
-      rx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) / id;
-      rx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) / id;
     }
     const float u = pt0 / pt2;
     const float v = pt1 / pt2;
     const float Ku = fxl * u + cxl;
     const float Kv = fyl * v + cyl;
     const float new_idepth = id / pt2;
-
-    if (flow && (i & 31) == 0) {  // :754-784 / :1070-1100 flow indicators, every 32nd template point of level 0
-      const float s = MODE == 0 ? 1.0f : it.p0;
-      float kx0, kx1, kx2, mx0, mx1, mx2;
-      if (MODE == 0) {
-        kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
-        kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
-        kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
-        mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
-        mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
-        mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
-      } else {
-        kx0 = dot3_xy1(s * it.Ki[0], s * it.Ki[1], s * it.Ki[2], x, y);
-        kx1 = dot3_xy1(s * it.Ki[3], s * it.Ki[4], s * it.Ki[5], x, y);
-        kx2 = dot3_xy1(s * it.Ki[6], s * it.Ki[7], s * it.Ki[8], x, y);
-        mx0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y);
-        mx1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y);
-        mx2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y);
-      }
-      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
-      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
-      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
-      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
-      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
-      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-      constexpr int iT = MODE == 0 ? 46 : 4, iRT = MODE == 0 ? 47 : 5;
-      acc[iT] += (double)sT1;
-      acc[iT] += (double)sT2;
-      acc[iRT] += (double)sRT1;
-      acc[iRT] += (double)sRT2;
-    }
 
     if (!(Ku > 2 && Kv > 2 && Ku < wlm3 && Kv < hlm3 && new_idepth > 0)) continue;
     const float3 hit = interp33(tex, Ku, Kv, wl);
@@ -200,11 +157,11 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
     const float hw = absr < kHuberTH ? 1.0f : kHuberTH / absr;
     nE++;
     if (absr > cutoff) {
-      acc[MODE == 0 ? 45 : 3] += (double)maxEnergy;
+      acc[iE] += (double)maxEnergy;
       nSat++;
       continue;
     }
-    acc[MODE == 0 ? 45 : 3] += (double)(hw * residual * residual * (2 - hw));
+    acc[iE] += (double)(hw * residual * residual * (2 - hw));
     nInl++;
 
     if (MODE == 0) {
@@ -231,7 +188,10 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
         for (int c = r; c < 9; c++, e++) acc[e] = fma(Jw, Jd[c], acc[e]);
       }
     } else {
-      // calcGSSSEScale :983-997
+      // calcGSSSEScale :983-997 (rx = M*(x,y,1) / id, :1068)
+      rx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) / id;
+      rx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) / id;
+      rx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) / id;
       const float tx = it.t[0], ty = it.t[1], tz = it.t[2];
       const float dxfx = hit.y * fxl, dyfy = hit.z * fyl;
       const float deno_sqrt = (it.p0 * rx2) + tz;
@@ -244,6 +204,75 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
       acc[1] = fma(Jw, (double)residual, acc[1]);
       acc[2] = fma(rw, (double)residual, acc[2]);
     }
+  }
+
+  // Flow indicators (:754-784 / :1070-1100): every 32nd template point of level 0, whether or not it projects into
+  // the image.  Done as a separate dense pass — inside the main loop one lane per warp would drag the whole warp
+  // through ~200 extra instructions per point.
+  if (it.flags & 1) {
+    const int nflow = (n + 31) >> 5;
+    for (int k = blockIdx.x * kEvalThreads + tid; k < nflow; k += stride) {
+      const float4 p = __ldg(pts + 32 * k);
+      const float x = p.x, y = p.y, id = p.z;
+      const float s = MODE == 0 ? 1.0f : it.p0;
+      float kx0, kx1, kx2, mx0, mx1, mx2;
+      if (MODE == 0) {
+        kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
+        kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
+        kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
+        mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
+        mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
+        mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
+      } else {
+        kx0 = dot3_xy1(s * it.Ki[0], s * it.Ki[1], s * it.Ki[2], x, y);
+        kx1 = dot3_xy1(s * it.Ki[3], s * it.Ki[4], s * it.Ki[5], x, y);
+        kx2 = dot3_xy1(s * it.Ki[6], s * it.Ki[7], s * it.Ki[8], x, y);
+        mx0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y);
+        mx1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y);
+        mx2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y);
+      }
+      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
+      // the point itself (pt = M*(x,y,1) + t*id), as in the main loop
+      const float ptz = mx2 + tT2;
+      const float Ku = fxl * ((mx0 + tT0) / ptz) + cxl, Kv = fyl * ((mx1 + tT1) / ptz) + cyl;
+      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
+      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
+      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
+      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
+      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      acc[iT] += (double)sT1;
+      acc[iT] += (double)sT2;
+      acc[iRT] += (double)sRT1;
+      acc[iRT] += (double)sRT2;
+    }
+  }
+}
+
+// MODE 0 = pose items only, 1 = scale items only, 2 = mixed (bit 1 of EvalItem::flags selects scale; used when the pose
+// tracker and the scale optimiser of a stereo frame advance in the same launch).  grid = (max nblocks, nitems).
+template <int MODE, int CAP>
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
+                                                           EvalResult *__restrict__ results, unsigned seq) {
+  constexpr int NV = MODE == 1 ? kScaleVals : kPoseVals;
+  constexpr int NW = kEvalThreads / 32;
+  const EvalItem &it = batch.item[blockIdx.y];
+  if ((int)blockIdx.x >= it.nblocks) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) acc[i] = 0.0;
+  int nE = 0, nSat = 0, nInl = 0;
+  if (MODE == 0) {
+    eval_points<0, NV>(it, acc, nE, nSat, nInl);
+  } else if (MODE == 1) {
+    eval_points<1, NV>(it, acc, nE, nSat, nInl);
+  } else {
+    if (it.flags & 2) eval_points<1, NV>(it, acc, nE, nSat, nInl);
+    else eval_points<0, NV>(it, acc, nE, nSat, nInl);
   }
 
   // ---- CTA reduction ---------------------------------------------------------------------------------
@@ -333,7 +362,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
 template <int MODE, int CAP>
 cudaError_t launch_cap(const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results, unsigned seq,
                        cudaStream_t stream) {
-  BatchT<MODE, CAP> b;
+  BatchT<CAP> b;
   for (int i = 0; i < nitems; i++) b.item[i] = batch.item[i];
   eval_kernel<MODE, CAP><<<dim3(grid_x, nitems), kEvalThreads, 0, stream>>>(b, scratch, results, seq);
   return cudaGetLastError();
@@ -353,8 +382,9 @@ cudaError_t launch_mode(const EvalBatch &batch, int nitems, int grid_x, EvalScra
 cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream) {
   if (nitems < 1 || nitems > kMaxItemsPerLaunch || grid_x < 1 || grid_x > kMaxBlocksPerItem) return cudaErrorInvalidValue;
-  return mode == 0 ? launch_mode<0>(batch, nitems, grid_x, scratch, results_dev, seq, stream)
-                   : launch_mode<1>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
+  if (mode == 0) return launch_mode<0>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
+  if (mode == 1) return launch_mode<1>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
+  return launch_mode<2>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
 }
 
 }  // namespace dslam

@@ -59,10 +59,10 @@ int dslam_session_launch_count(dslam_session *s, long long *count);
 int dslam_session_mark(dslam_session *s, int which);
 int dslam_session_elapsed_ms(dslam_session *s, float *ms);
 /* per-launch profiling of the residual kernels: CUDA events on the session stream around every launch.
- * read -> out[0..3] pose kernel (launches, total ms, template points evaluated, max ms), out[4..7] scale kernel;
- * reading resets the counters. */
+ * read -> out[0..3] pose-only launches (launches, total ms, template points evaluated, max ms), out[4..7] scale-only
+ * launches, out[8..11] mixed pose+scale launches; reading resets the counters. */
 int dslam_session_profile(dslam_session *s, int enable);
-int dslam_session_profile_read(dslam_session *s, double out[8]);
+int dslam_session_profile_read(dslam_session *s, double out[12]);
 /* pinned host memory helpers (cudaHostAlloc) so callers can make H2D/D2H truly asynchronous */
 int dslam_host_alloc(unsigned long long bytes, void **out);
 int dslam_host_free(void *p);
@@ -78,6 +78,10 @@ int dslam_frame_upload(dslam_frame *f, const float *color);
 /* build all levels on the device from the uploaded image.  B256 = CalibHessian::B (256 floats) applies the
  * gamma weight gw^2 to absSquaredGrad ("HCalib != 0 && setting_gammaWeightsPixelSelect == 1"); NULL = none. */
 int dslam_frame_build(dslam_frame *f, const float *B256);
+/* the same for n uploaded frames of one session in two kernel launches in total (per run of 64 frames of equal geometry);
+ * stage_host bit 0 / bit 1 also fill the device-side staging copies of dIp / absSquaredGrad so that a following
+ * dslam_frame_download is a plain D2H copy */
+int dslam_frame_build_batch(int n, dslam_frame *const *frames, const float *B256, int stage_host);
 /* asynchronous D2H into the reference's host layouts: host_dIp[l] = Eigen::Vector3f[w_l*h_l] (I,dx,dy AoS),
  * host_absgrad[l] = float[w_l*h_l]; either array (or single entries) may be NULL. */
 int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad);
@@ -149,6 +153,12 @@ int dslam_track_newest_coarse_batch(int n, dslam_ctx *const *ctxs, dslam_frame *
                                     double *lastResiduals, double *flow3, int *ok);
 int dslam_optimize_scale_batch(int n, dslam_ctx *const *ctxs, dslam_frame *const *frames_right, float *scales_io, int coarsestLvl,
                                float *rmse_out);
+/* n_pose tracking jobs AND n_scale scale-optimisation jobs in the same lock step: the two LM loops are independent
+ * (optimizeScale reads only its template and the right image), so pose and scale items share every launch. */
+int dslam_lm_batch(int n_pose, dslam_ctx *const *pose_ctxs, dslam_frame *const *pose_frames, const float *new_exposure, double *pose7_io,
+                   double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3, int *ok,
+                   int n_scale, dslam_ctx *const *scale_ctxs, dslam_frame *const *scale_frames, float *scales_io, int scale_coarsestLvl,
+                   float *rmse_out);
 /* per-iteration trace of the last track / optimizeScale call on this ctx (first start only for *_multi):
  * rows of 15 doubles (lvl, iteration (-1 = level start), accept, n_padded, lambda, E/n old, E/n new, inc[8]).
  * Returns the number of rows through *rows_out. */

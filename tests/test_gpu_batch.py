@@ -1,0 +1,79 @@
+"""Batched entry points (the B200-first levers): all pyramids of a step in two launches, pose trackers and scale
+optimisers of many streams in one lock step.  Each must reproduce the one-at-a-time calls."""
+import numpy as np
+import pytest
+
+from helpers import IDENT7, GpuCase, OracleCase, rel_err
+from direct_stereo_slam_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def test_build_frames_batch_equals_single(session):
+    rng = np.random.default_rng(0)
+    w, h, levels = 320, 192, 3
+    imgs = [np.clip(rng.normal(128, 40, (h, w)), 0, 255).astype(np.float32) for _ in range(5)]
+    single = []
+    for im in imgs:
+        f = api.FrameHessian(session, w, h, levels)
+        f.makeImages(im)
+        single.append((f.dIp_all.copy(), f.absSquaredGrad_all.copy()))
+        f.close()
+    frames = [api.FrameHessian(session, w, h, levels) for _ in imgs]
+    for f, im in zip(frames, imgs):
+        f.upload(im)
+    api.build_frames(frames, stage_host=3)
+    for f, (d, a) in zip(frames, single):
+        f.download()
+        assert np.array_equal(f.dIp_all.view(np.uint32), d.view(np.uint32)) and np.array_equal(f.absSquaredGrad_all.view(np.uint32), a.view(np.uint32))
+    # partial mirror: only level 0 of dIp
+    frames[0].dIp_all[:] = -1
+    frames[0].absSquaredGrad_all[:] = -1
+    frames[0].download(levels=[0], abs_grad=False)
+    n0 = w * h
+    assert np.array_equal(frames[0].dIp_all[:n0].view(np.uint32), single[0][0][:n0].view(np.uint32))
+    assert np.all(frames[0].dIp_all[n0:] == -1) and np.all(frames[0].absSquaredGrad_all == -1)
+    # mixed geometries fall into separate launches
+    g = api.FrameHessian(session, 160, 96, 2)
+    g.upload(imgs[0][:96, :160])
+    api.build_frames([frames[1], g, frames[2]])
+    g.download()
+    g2 = api.FrameHessian(session, 160, 96, 2)
+    g2.makeImages(imgs[0][:96, :160])
+    assert np.array_equal(g.dIp_all.view(np.uint32), g2.dIp_all.view(np.uint32))
+    for f in frames + [g, g2]:
+        f.close()
+
+
+def test_lm_batch_equals_separate_calls(session, oracle):
+    """3 streams: all track, two of them also optimise the scale in the same launches."""
+    ocs = [OracleCase(oracle, "tiny", sd, scale_error=se) for sd, se in ((3, 1.0), (4, 2.5), (9, 0.6))]
+    gcs = [GpuCase(session, oc) for oc in ocs]
+    trk = [g.trk for g in gcs]
+    left = [g.f_new for g in gcs]
+    sep = []
+    for g, oc in zip(gcs, ocs):
+        ok, pose, aff, last = g.trk.trackNewestCoarse(g.f_new, IDENT7, (0, 0), oc.levels - 1)
+        rmse, s = g.trk.optimizeScale(g.f_right, 1.0, oc.levels - 1)
+        sep.append((ok, pose, aff, last, rmse, s))
+    before = session.launch_count()
+    ok, poses, affs, last, rmse, scales = api.lm_batch(trk, left, np.tile(IDENT7, (3, 1)), np.zeros((3, 2)), ocs[0].levels - 1,
+                                                       [trk[1], trk[2]], [gcs[1].f_right, gcs[2].f_right], [1.0, 1.0])
+    launches = session.launch_count() - before
+    for i in range(3):
+        assert ok[i] == sep[i][0] and rel_err(poses[i], sep[i][1]) < 1e-9 and np.allclose(affs[i], sep[i][2], rtol=1e-8, atol=1e-10)
+        assert np.allclose(last[i], sep[i][3], rtol=1e-7, equal_nan=True)
+    assert scales[0] == np.float32(sep[1][5]) and scales[1] == np.float32(sep[2][5])
+    assert rmse[0] == np.float32(sep[1][4]) and rmse[1] == np.float32(sep[2][4])
+    # one launch per round: no more launches than the longest machine needs evaluations
+    worst = max(len(g.trk.trace()) for g in gcs) + 60
+    assert launches <= worst
+    # and against the oracle
+    for i, oc in enumerate(ocs):
+        ok_o, pose_o, aff_o, _, _ = oc.trk.track_newest_coarse(1, IDENT7, (0, 0), oc.levels - 1)
+        assert ok_o == ok[i] and rel_err(poses[i], pose_o) < 1e-8
+    for k, i in enumerate((1, 2)):
+        rmse_o, s_o = ocs[i].trk.optimize_scale(1, 1.0, ocs[i].levels - 1)
+        assert abs(scales[k] - s_o) <= 1e-6 * abs(s_o)
+    for g in gcs:
+        g.close()
