@@ -336,7 +336,7 @@ def bench_scan_context(api, session, rank, world, dist, n_db=100_000, nq=32, rep
     if world > 1:
         import torch
 
-        t = torch.tensor([lat_ms, scan_ms], dtype=torch.float64)
+        t = torch.tensor([lat_ms, scan_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lat_ms, scan_ms = float(t[0]), float(t[1])
     known = truth >= 0
@@ -386,6 +386,7 @@ def main():
 
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug banner must not share stdout with the JSON line
         import torch
         import torch.distributed as dist
 
@@ -446,8 +447,8 @@ def main():
                            "l2": "working set ~%d MB per step > 126 MB L2 (every stream has its own pyramids)" % int(args.streams * 12 * (1 + 1.0 / args.keyframe_every)),
                            "multi_gpu": "replicas only (tracking does not shard); scan_context is the sharded piece",
                            "timing": "max(CUDA events on the session stream, host clock) over the K steps, max over ranks"},
-                "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes(),
-                        "d2h_bytes_per_step": streams.d2h_bytes()},
+                "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes() * world,
+                        "d2h_bytes_per_step": streams.d2h_bytes() * world},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "eval_kernel (fused calcRes*+calcGSSSE* of all pose / scale items of an LM round)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,

@@ -49,10 +49,14 @@ __global__ void tmpl_dilate_kernel(const __grid_constant__ TemplateGrids G) {
     float wv = bak[i];
     if (i >= wl && i < n - wl && wv <= 0) {
       float sum = 0, num = 0, numn = 0;
-      if (bak[i + o0] > 0) { sum += idl[i + o0]; num += bak[i + o0]; numn++; }
-      if (bak[i + o1] > 0) { sum += idl[i + o1]; num += bak[i + o1]; numn++; }
-      if (bak[i + o2] > 0) { sum += idl[i + o2]; num += bak[i + o2]; numn++; }
-      if (bak[i + o3] > 0) { sum += idl[i + o3]; num += bak[i + o3]; numn++; }
+      // the reference reads one element before / after the grid at the two corner pixels (x = 0, y = 1) and
+      // (x = w-1, y = h-2) (:207, :203); those pixels lie outside the interior the template is taken from, so an
+      // out-of-range neighbour simply counts as empty here
+      const int j0 = i + o0, j1 = i + o1, j2 = i + o2, j3 = i + o3;
+      if (j0 < n && bak[j0] > 0) { sum += idl[j0]; num += bak[j0]; numn++; }
+      if (j1 >= 0 && bak[j1] > 0) { sum += idl[j1]; num += bak[j1]; numn++; }
+      if (j2 < n && bak[j2] > 0) { sum += idl[j2]; num += bak[j2]; numn++; }
+      if (j3 >= 0 && bak[j3] > 0) { sum += idl[j3]; num += bak[j3]; numn++; }
       if (numn > 0) {
         idl[i] = sum / numn;
         wv = num / numn;

@@ -923,8 +923,13 @@ void orc_tracker_make_coarse_depth(void *p, int npts, const int *pu, const int *
     for (int i = wl; i < wh; i++) {
       if (wbak[i] <= 0) {
         float sum = 0, num = 0, numn = 0;
-        for (int k = 0; k < 4; k++)
-          if (wbak[i + oo[k]] > 0) { sum += idl[i + oo[k]]; num += wbak[i + oo[k]]; numn++; }
+        for (int k = 0; k < 4; k++) {
+          // the reference indexes one element outside the grid at (x=0, y=1) and (x=w-1, y=h-2); those pixels are outside
+          // the interior [2, w-2) x [2, h-2) the template is read from, so an out-of-range neighbour counts as empty
+          const int j = i + oo[k];
+          if (j < 0 || j >= wl * T.h[lvl]) continue;
+          if (wbak[j] > 0) { sum += idl[j]; num += wbak[j]; numn++; }
+        }
         if (numn > 0) { idl[i] = sum / numn; wsl[i] = num / numn; }
       }
     }

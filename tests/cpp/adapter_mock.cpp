@@ -1,0 +1,90 @@
+// Compiles include/dslam_b200_adapter.hpp against mock stand-ins of the reference's types (this image has no Eigen /
+// Sophus / DSO headers) and, when a GPU is present, runs one tracking + scale call through it.
+// Build: g++ -std=c++14 -I include tests/cpp/adapter_mock.cpp -L direct_stereo_slam_b200 -ldslam_b200 -o adapter_mock
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "dslam_b200_adapter.hpp"
+
+namespace mock {
+struct Vector3f { float v[3]; };
+struct AffLight { double a = 0, b = 0; };
+struct SE3 {  // Sophus::SE3d::data(): quaternion (x,y,z,w) + translation
+  double d[7] = {0, 0, 0, 1, 0, 0, 0};
+  double *data() { return d; }
+};
+struct Vec5 { double v[5]; double &operator[](int i) { return v[i]; } const double &operator[](int i) const { return v[i]; } };
+struct Vec3 { double v[3]; double &operator[](int i) { return v[i]; } };
+struct FrameShell { int id = 0; };
+struct FrameHessian {
+  Vector3f *dIp[6] = {nullptr};
+  float *absSquaredGrad[6] = {nullptr};
+  float ab_exposure = 1.f;
+  FrameShell *shell = nullptr;
+  AffLight aff;
+  AffLight aff_g2l() const { return aff; }
+};
+struct CalibHessian {
+  float fx, fy, cx, cy;
+  float B[256];
+  float fxl() const { return fx; } float fyl() const { return fy; } float cxl() const { return cx; } float cyl() const { return cy; }
+};
+}  // namespace mock
+
+using Tracker = dslam_b200::TrackerAndScaler<mock::FrameHessian, mock::SE3, mock::AffLight, mock::Vec5, mock::Vec3>;
+
+int main() {
+  int ndev = 0;
+  if (dslam_device_count(&ndev) != DSLAM_OK || ndev < 1) {
+    std::printf("adapter_mock: no CUDA device, compile/link check only (%s)\n", dslam_last_error());
+    return 0;
+  }
+  const int w = 320, h = 192, levels = 3;
+  dslam_b200::Session session(0);
+  dslam_b200::FramePyramids<mock::FrameHessian> frames(session, w, h, levels);
+  mock::CalibHessian calib{200.f, 200.f, 159.5f, 95.5f, {0}};
+  const float K1[4] = {200.f, 200.f, 159.5f, 95.5f};
+  std::vector<double> tfm = {1, 0, 0, -0.3, 0, 1, 0, 0, 0, 0, 1, 1e-9, 0, 0, 0, 1};
+  Tracker tracker(session, frames, w, h, levels, tfm, K1);
+  tracker.makeK(&calib);
+  // a textured plane at 10 m seen by the keyframe, the new frame (shifted 2 px) and the right camera
+  auto render = [&](float shift, std::vector<float> &img) {
+    img.resize((size_t)w * h);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) img[(size_t)y * w + x] = 128.f + 60.f * std::sin(0.11f * (x + shift)) * std::cos(0.07f * y) + 20.f * std::sin(0.31f * (x + shift) + 0.2f * y);
+  };
+  std::vector<float> img;
+  mock::FrameShell shell[3];
+  mock::FrameHessian fh[3];
+  std::vector<std::vector<float>> store;
+  for (int k = 0; k < 3; k++) {
+    fh[k].shell = &shell[k];
+    for (int l = 0; l < levels; l++) {
+      store.emplace_back((size_t)3 * (w >> l) * (h >> l));
+      fh[k].dIp[l] = reinterpret_cast<mock::Vector3f *>(store.back().data());
+      store.emplace_back((size_t)(w >> l) * (h >> l));
+      fh[k].absSquaredGrad[l] = store.back().data();
+    }
+    render(k == 0 ? 0.f : (k == 1 ? 2.f : 6.f), img);  // disparity f*b/z = 200*0.3/10 = 6 px for the right camera
+    frames.makeImages(&fh[k], img.data(), &calib, false);
+    frames.wait_host(&fh[k]);
+  }
+  dslam_b200::ActivePoints pts;
+  for (int y = 8; y < h - 8; y += 6)
+    for (int x = 8; x < w - 8; x += 6) pts.push(x, y, 0.1f, 1.0f);
+  tracker.setCoarseTrackingRef({&fh[0]}, pts);
+  mock::SE3 pose;
+  mock::AffLight aff;
+  mock::Vec5 minres, last;
+  for (int i = 0; i < 5; i++) minres[i] = NAN;
+  const bool ok = tracker.trackNewestCoarse(&fh[1], pose, aff, levels - 1, minres, last);
+  float scale = 1.f;
+  const float rmse = tracker.optimizeScale(&fh[2], scale, levels - 1);
+  // a 2 px shift of a plane at 10 m with f = 200 is a translation of -0.1 m (the scene moved +x, so the camera moved -x)
+  std::printf("adapter_mock: ok=%d tx=%.4f (expect about -0.1) rmse0=%.3f scale=%.3f (expect about 1) scale_rmse=%.3f pc_n0=%d\n", (int)ok,
+              pose.data()[4], last[0], scale, rmse, tracker.pc_n()[0]);
+  const bool pass = ok && std::fabs(pose.data()[4] + 0.1) < 0.01 && std::fabs(scale - 1.f) < 0.05f;
+  frames.release(&fh[1]);
+  return pass ? 0 : 1;
+}
