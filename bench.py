@@ -310,9 +310,9 @@ def cpu_all_cores(cases, steps, warmup, threads, kf_every=5):
 # ----------------------------------------------------------------------------------------------------------------------
 # Scan-Context shard (the only piece that shards): 100k descriptors over the ranks, query batch of 32
 # ----------------------------------------------------------------------------------------------------------------------
-def bench_scan_context(api, session, rank, world, dist, n_db=100_000, nq=32, reps=20):
+def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1, 32), reps=20):
+    """100k descriptors row-sharded over the ranks; per query batch: scan + exact re-score (+ one NCCL all-reduce(min))."""
     sig, key = syn.make_sc_database(n_db, 2024)
-    qs, qk, truth = syn.make_sc_queries(sig, key, nq, 77)
     rows = api.shard_rows(n_db, world, rank)
     db = api.ScanContextDB(session, len(rows) + 8)
     db.add(key[rows], sig[rows], global_ids=rows)
@@ -322,28 +322,31 @@ def bench_scan_context(api, session, rank, world, dist, n_db=100_000, nq=32, rep
         ident = [api.ScanContextDB.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         db.attach_comm(ident[0], world, rank)
-    for _ in range(3):
-        idx, diff = db.query(qs)
-    lat, scan = [], []
-    for _ in range(reps):
+    peak, _ = measured_peak()
+    out = {"db_rows": n_db, "rows_per_gpu": int(len(rows)), "collective": "ncclAllReduce(min, uint64 x Q)" if world > 1 else "none", "batches": {}}
+    for nq in batches:
+        qs, qk, truth = syn.make_sc_queries(sig, key, nq, 77)
+        for _ in range(3):
+            idx, diff = db.query(qs)
+        lat, scan = [], []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            idx, diff = db.query(qs)
+            lat.append((time.perf_counter() - t0) * 1e3)
+            scan.append(db.last_scan_ms())
+        lat_ms, scan_ms = float(np.median(lat)), float(np.median(scan))
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        idx, diff = db.query(qs)
-        lat.append((time.perf_counter() - t0) * 1e3)
-        scan.append(db.last_scan_ms())
-    lat_ms, scan_ms = float(np.median(lat)), float(np.median(scan))
-    if world > 1:
-        import torch
+            import torch
 
-        t = torch.tensor([lat_ms, scan_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        lat_ms, scan_ms = float(t[0]), float(t[1])
-    known = truth >= 0
-    out = {"db_rows": n_db, "rows_per_gpu": int(len(rows)), "query_batch": nq, "query_latency_ms": lat_ms, "scan_kernel_ms": scan_ms,
-           "scan_gbs_per_gpu": len(rows) * (db.n_cells + db.n_rings) * 4 / (scan_ms * 1e-3) / 1e9,
-           "revisits_found": int(np.sum(idx[known] == truth[known])), "revisits": int(known.sum()),
-           "collective": "ncclAllReduce(min, uint64 x %d)" % nq if world > 1 else "none"}
+            t = torch.tensor([lat_ms, scan_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lat_ms, scan_ms = float(t[0]), float(t[1])
+        known = truth >= 0
+        gbs = len(rows) * (db.n_cells + db.n_rings) * 4 / (scan_ms * 1e-3) / 1e9
+        out["batches"]["Q%d" % nq] = {"query_latency_ms": lat_ms, "scan_kernel_ms": scan_ms, "scan_gbs_per_gpu": gbs, "scan_frac_of_hbm_peak": gbs / peak,
+                                      "revisits_found": int(np.sum(idx[known] == truth[known])), "revisits": int(known.sum())}
     db.close()
     return out
 
@@ -354,7 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=32, help="independent stereo streams per GPU advanced in lock step")
+    ap.add_argument("--streams", type=int, default=128, help="independent stereo streams per GPU advanced in lock step")
     ap.add_argument("--keyframe-every", type=int, default=5, help="every k-th frame of a stream also builds the right pyramid and optimises the scale")
     ap.add_argument("--cases", type=int, default=4, help="distinct synthetic scenes (streams cycle through them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -406,7 +409,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    session.host_times()
     ms, launches = timed_steps(streams, session, args.steps, warmup, False, barrier)
+    host_times = session.host_times()
     clocks = sampler.stop() if rank == 0 else None
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------------------
     ms_e2e, _ = timed_steps(streams, session, args.steps, warmup, True, barrier)
@@ -457,6 +462,7 @@ def main():
                              "scale_kernel_gbs": (BYTES_PER_POINT * prof["scale"]["points"] / (prof["scale"]["ms"] * 1e-3) / 1e9)
                              if prof["scale"]["ms"] > 0 else None},
                 "clocks": clocks,
+                "host_ms_per_step": {k: (v / (args.steps + warmup) if k != "launches" else v) for k, v in host_times.items()},
                 "lm": {"evals_per_frame": float(np.sum([c["evals"] for c in counters])) / (args.streams * (2 * warmup + 2 * args.steps + min(args.steps, 5))),
                        "note": "fused residual+Jacobian evaluations (pose + scale LM rounds) per stereo frame"}}
         if sc is not None:

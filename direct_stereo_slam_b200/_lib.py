@@ -43,6 +43,7 @@ SIGNATURES = {
     "dslam_session_elapsed_ms": [vp, c_f],
     "dslam_session_profile": [vp, C.c_int],
     "dslam_session_profile_read": [vp, c_d],
+    "dslam_session_host_times": [vp, c_d],
     "dslam_host_alloc": [C.c_ulonglong, c_pp],
     "dslam_host_free": [vp],
     "dslam_frame_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],

@@ -95,6 +95,11 @@ class Session:
         return {k: dict(launches=int(out[4 * i]), ms=out[4 * i + 1], points=int(out[4 * i + 2]), max_ms=out[4 * i + 3])
                 for i, k in enumerate(("pose", "scale", "mixed"))}
 
+    def host_times(self):
+        out = np.zeros(4)
+        check(self.lib.dslam_session_host_times(self.p, _dp(out)))
+        return dict(prep_ms=out[0], launch_ms=out[1], wait_ms=out[2], launches=int(out[3]))
+
     def stream(self):
         p = C.c_void_p()
         check(self.lib.dslam_session_stream(self.p, C.byref(p)))

@@ -11,6 +11,7 @@
 // There is no CPU fallback in this file: without a CUDA device every entry point fails with DSLAM_ENODEVICE.
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "dslam_internal.h"
@@ -90,32 +91,34 @@ int choose_blocks(int n, int nitems, int num_sms) {
   return per;
 }
 
-// Launch `n` prepared items (any count up to kResultSlots) and wait for their result records.
-int run_items(dslam_session *s, std::vector<EvalItem> &items, std::vector<EvalOut> &outs, long long *launch_counter) {
+// Launch `n` prepared items (result slots [slot0, slot0 + n)) on `stream`; returns the sequence number through *seq_out.
+int launch_items(dslam_session *s, std::vector<EvalItem> &items, int slot0, cudaStream_t stream, EvalScratch scratch, unsigned *seq_out,
+                 long long *launch_counter) {
   const int n = (int)items.size();
-  if (n < 1) return DSLAM_OK;
   // kernel flavour: 0 = all pose, 1 = all scale, 2 = mixed (bit 1 of EvalItem::flags marks a scale item)
   int n_scale = 0;
   for (const EvalItem &it : items) n_scale += (it.flags & 2) ? 1 : 0;
   const int mode = n_scale == 0 ? 0 : (n_scale == n ? 1 : 2);
-  if (n > kResultSlots) return fail(DSLAM_EINVAL, "too many evaluation items in one round (%d > %d)", n, kResultSlots);
-  const unsigned seq = ++s->seq;
+  const unsigned seq = ++s->seq;  // atomic: group threads launch concurrently
+  *seq_out = seq;
   EvalBatch batch;
   for (int base = 0; base < n; base += kMaxItemsPerLaunch) {
     const int cnt = n - base < kMaxItemsPerLaunch ? n - base : kMaxItemsPerLaunch;
     int gx = 1;
+    long long pts = 0;
     for (int i = 0; i < cnt; i++) {
       EvalItem &it = items[base + i];
       it.nblocks = choose_blocks(it.n, cnt, s->num_sms);
       it.ppt_stride = it.nblocks * kEvalThreads;
       if (it.nblocks > gx) gx = it.nblocks;
       batch.item[i] = it;
+      pts += it.n;
     }
-    long long pts = 0;
-    for (int i = 0; i < cnt; i++) pts += batch.item[i].n;
     const bool prof = s->prof_on;
     size_t slot = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (prof) {
+      std::lock_guard<std::mutex> lock(s->prof_mutex);
       slot = s->prof_used++;
       while (s->prof_ev.size() < 2 * (slot + 1)) {
         cudaEvent_t e;
@@ -125,28 +128,35 @@ int run_items(dslam_session *s, std::vector<EvalItem> &items, std::vector<EvalOu
       if (s->prof_mode.size() <= slot) { s->prof_mode.resize(slot + 1); s->prof_points.resize(slot + 1); }
       s->prof_mode[slot] = mode;
       s->prof_points[slot] = pts;
-      DSLAM_CUDA(cudaEventRecord(s->prof_ev[2 * slot], s->stream));
+      ev0 = s->prof_ev[2 * slot];
+      ev1 = s->prof_ev[2 * slot + 1];
     }
-    DSLAM_CUDA(launch_eval(mode, batch, cnt, gx, s->scratch, s->results_dev + base, seq, s->stream));
-    if (prof) DSLAM_CUDA(cudaEventRecord(s->prof_ev[2 * slot + 1], s->stream));
+    if (prof) DSLAM_CUDA(cudaEventRecord(ev0, stream));
+    DSLAM_CUDA(launch_eval(mode, batch, cnt, gx, scratch, s->results_dev + slot0 + base, seq, stream));
+    if (prof) DSLAM_CUDA(cudaEventRecord(ev1, stream));
     s->launches++;
     if (launch_counter) (*launch_counter)++;
   }
-  // The last CTA of every item writes its record into mapped pinned memory and then the sequence number.
+  return DSLAM_OK;
+}
+
+// Wait for the result records of a launch group.  The last CTA of every item writes its record into mapped pinned
+// memory as self-validating words (payload | sequence number).
+int collect_items(dslam_session *s, const std::vector<EvalItem> &items, int slot0, cudaStream_t stream, unsigned seq, std::vector<EvalOut> &outs) {
+  const int n = (int)items.size();
   outs.resize(n);
   const auto t0 = std::chrono::steady_clock::now();
   unsigned long spins = 0;
   for (int i = 0; i < n; i++) {
     const bool is_scale = (items[i].flags & 2) != 0;
     const int nv = is_scale ? kScaleVals : kPoseVals;
-    const volatile unsigned long long *w = s->results_host[i].w;
+    const volatile unsigned long long *w = s->results_host[slot0 + i].w;
     EvalOut &o = outs[i];
-    // every word of the record carries the sequence number of the launch that wrote it
     auto wait_word = [&](int k, unsigned long long *out) -> int {
       unsigned long long v;
       while ((unsigned)((v = w[k]) & 0xffffffffull) != seq) {
         if ((++spins & 0x3fff) == 0) {
-          const cudaError_t q = cudaStreamQuery(s->stream);
+          const cudaError_t q = cudaStreamQuery(stream);
           if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "evaluation kernel");
           const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
           if (dt > s->timeout_s) return fail(DSLAM_ETIMEOUT, "evaluation kernel did not publish its result within %.1f s", s->timeout_s);
@@ -191,6 +201,16 @@ int run_items(dslam_session *s, std::vector<EvalItem> &items, std::vector<EvalOu
     o.res6[5] = o.nSat / (float)o.nE;  // :851 float division
   }
   return DSLAM_OK;
+}
+
+int run_items(dslam_session *s, std::vector<EvalItem> &items, std::vector<EvalOut> &outs, long long *launch_counter) {
+  const int n = (int)items.size();
+  if (n < 1) return DSLAM_OK;
+  if (n > kResultSlots) return fail(DSLAM_EINVAL, "too many evaluation items in one round (%d > %d)", n, kResultSlots);
+  unsigned seq = 0;
+  const int rc = launch_items(s, items, 0, s->stream, s->scratch, &seq, launch_counter);
+  if (rc != DSLAM_OK) return rc;
+  return collect_items(s, items, 0, s->stream, seq, outs);
 }
 
 void fill_common(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, int lvl, float cutoff) {
@@ -521,36 +541,135 @@ struct ScaleLM {
   }
 };
 
-// All machines (pose and scale alike) advance one evaluation per round; a round is one kernel launch.
-int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<ScaleLM> &scale, dslam_ctx *counters) {
-  std::vector<EvalItem> items;
-  std::vector<EvalOut> outs;
-  std::vector<int> who;  // >= 0: pose machine index, < 0: ~index of a scale machine
+// All machines (pose and scale alike) advance one evaluation per round.  The machines are dealt into groups that run
+// concurrently: each group has its own host thread, CUDA stream, scratch and result slots and loops
+// "prepare -> launch (one kernel for the whole group) -> wait -> consume" until its machines are done.  Every machine
+// sees exactly the evaluations it would see alone, so results do not depend on the grouping.
+void worker_main(dslam_session *s, int g) {
+  cudaSetDevice(s->device);
+  dslam_session::Worker *w = s->workers[g];
+  std::unique_lock<std::mutex> lock(w->m);
   for (;;) {
-    items.clear();
-    who.clear();
-    for (size_t i = 0; i < pose.size(); i++)
-      if (pose[i].phase != PoseLM::DONE) {
-        items.emplace_back();
-        pose[i].request(items.back());
-        who.push_back((int)i);
+    w->cv.wait(lock, [&] { return w->has_job || w->quit; });
+    if (w->quit) return;
+    lock.unlock();
+    w->job();
+    lock.lock();
+    w->has_job = false;
+    w->done = true;
+    w->cv.notify_all();
+  }
+}
+
+int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<ScaleLM> &scale, dslam_ctx *counters) {
+  constexpr int G = dslam_session::kLmGroups;
+  const int total = (int)(pose.size() + scale.size());
+  int ngroups = s->lm_groups;
+  while (ngroups > 1 && total < 4 * ngroups) ngroups--;  // a group needs a few machines to be worth a launch of its own
+  const int slots_per_group = kResultSlots / G;
+  struct Group {
+    std::vector<int> members;  // >= 0: pose machine index, < 0: ~index of a scale machine
+    int rc = DSLAM_OK;
+    std::string err;
+    long long evals = 0, launches = 0;
+  } grp[G];
+  {
+    int k = 0;
+    for (size_t i = 0; i < pose.size(); i++) grp[k++ % ngroups].members.push_back((int)i);
+    for (size_t i = 0; i < scale.size(); i++) grp[k++ % ngroups].members.push_back(~(int)i);
+  }
+  for (int g = 0; g < ngroups; g++)
+    if ((int)grp[g].members.size() > slots_per_group) return fail(DSLAM_EINVAL, "too many machines in one lock step");
+  if (ngroups > 1) {  // the side streams start after everything queued on the session stream (pyramids, template uploads)
+    DSLAM_CUDA(cudaEventRecord(s->lm_fork, s->stream));
+    for (int g = 1; g < ngroups; g++) DSLAM_CUDA(cudaStreamWaitEvent(s->lm_stream[g], s->lm_fork, 0));
+  }
+  auto now_ns = []() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  auto drive = [&](int g) {
+    Group &gr = grp[g];
+    std::vector<EvalItem> items;
+    std::vector<int> who;
+    std::vector<EvalOut> outs;
+    long long t_prep = 0, t_launch = 0, t_wait = 0, rounds = 0;
+    for (;;) {
+      const long long t0 = now_ns();
+      items.clear();
+      who.clear();
+      for (int m : gr.members) {
+        if (m >= 0) {
+          if (pose[m].phase == PoseLM::DONE) continue;
+          items.emplace_back();
+          pose[m].request(items.back());
+        } else {
+          if (scale[~m].phase == ScaleLM::DONE) continue;
+          items.emplace_back();
+          scale[~m].request(items.back());
+        }
+        who.push_back(m);
       }
-    for (size_t i = 0; i < scale.size(); i++)
-      if (scale[i].phase != ScaleLM::DONE) {
-        items.emplace_back();
-        scale[i].request(items.back());
-        who.push_back(~(int)i);
+      const long long t1 = now_ns();
+      t_prep += t1 - t0;
+      if (items.empty()) break;
+      unsigned seq = 0;
+      gr.rc = launch_items(s, items, g * slots_per_group, s->lm_stream[g], s->lm_scratch[g], &seq, &gr.launches);
+      const long long t2 = now_ns();
+      t_launch += t2 - t1;
+      rounds++;
+      if (gr.rc == DSLAM_OK) gr.rc = collect_items(s, items, g * slots_per_group, s->lm_stream[g], seq, outs);
+      if (gr.rc != DSLAM_OK) {
+        gr.err = g_err;
+        break;
       }
-    if (items.empty()) break;
-    const int rc = run_items(s, items, outs, counters ? &counters->n_launches : nullptr);
-    if (rc != DSLAM_OK) return rc;
-    if (counters) counters->n_evals += (long long)items.size();
-    for (size_t k = 0; k < who.size(); k++) {
-      if (who[k] >= 0) pose[who[k]].consume(outs[k]);
-      else scale[~who[k]].consume(outs[k]);
+      const long long t3 = now_ns();
+      t_wait += t3 - t2;
+      gr.evals += (long long)items.size();
+      for (size_t k = 0; k < who.size(); k++) {
+        if (who[k] >= 0) pose[who[k]].consume(outs[k]);
+        else scale[~who[k]].consume(outs[k]);
+      }
+      t_prep += now_ns() - t3;
+    }
+    s->t_prep_ns += t_prep;
+    s->t_launch_ns += t_launch;
+    s->t_wait_ns += t_wait;
+    s->n_rounds += rounds;
+  };
+  for (int g = 1; g < ngroups; g++) {
+    if (!s->workers[g]) {
+      s->workers[g] = new dslam_session::Worker();
+      s->workers[g]->th = std::thread(worker_main, s, g);
+    }
+    dslam_session::Worker *w = s->workers[g];
+    std::lock_guard<std::mutex> lock(w->m);
+    w->job = [&drive, g]() { drive(g); };
+    w->done = false;
+    w->has_job = true;
+    w->cv.notify_all();
+  }
+  drive(0);
+  for (int g = 1; g < ngroups; g++) {
+    dslam_session::Worker *w = s->workers[g];
+    std::unique_lock<std::mutex> lock(w->m);
+    w->cv.wait(lock, [&] { return w->done; });
+  }
+  int rc = DSLAM_OK;
+  for (int g = 0; g < ngroups; g++) {
+    if (counters) {
+      counters->n_evals += grp[g].evals;
+      counters->n_launches += grp[g].launches;
+    }
+    if (grp[g].rc != DSLAM_OK && rc == DSLAM_OK) {
+      rc = grp[g].rc;
+      set_error("%s", grp[g].err.c_str());
     }
   }
-  return DSLAM_OK;
+  if (ngroups > 1) {  // later work on the session stream (next pyramids, template changes) is ordered after the side streams
+    for (int k = 1; k < ngroups; k++) {
+      DSLAM_CUDA(cudaEventRecord(s->lm_done[k], s->lm_stream[k]));
+      DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done[k], 0));
+    }
+  }
+  return rc;
 }
 
 // trackNewestCoarse epilogue :612-637 for one finished machine
@@ -629,6 +748,21 @@ int dslam_session_create(int device, dslam_session **out) {
   DSLAM_CUDA(cudaMemsetAsync(s->scratch.counters, 0, sizeof(int) * kMaxItemsPerLaunch * 4, s->stream));
   DSLAM_CUDA(cudaEventCreate(&s->mark[0]));
   DSLAM_CUDA(cudaEventCreate(&s->mark[1]));
+  s->lm_stream[0] = s->stream;
+  s->lm_scratch[0] = s->scratch;
+  if (const char *e = getenv("DSLAM_LM_GROUPS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= dslam_session::kLmGroups) s->lm_groups = v;
+  }
+  DSLAM_CUDA(cudaEventCreateWithFlags(&s->lm_fork, cudaEventDisableTiming));
+  for (int g = 1; g < dslam_session::kLmGroups; g++) {
+    DSLAM_CUDA(cudaStreamCreateWithFlags(&s->lm_stream[g], cudaStreamNonBlocking));
+    DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch[g].partials, sizeof(double) * kMaxItemsPerLaunch * kMaxBlocksPerItem * kPoseVals));
+    DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch[g].counters, sizeof(int) * kMaxItemsPerLaunch * 4));
+    DSLAM_CUDA(cudaMemsetAsync(s->lm_scratch[g].counters, 0, sizeof(int) * kMaxItemsPerLaunch * 4, s->lm_stream[g]));
+    DSLAM_CUDA(cudaEventCreateWithFlags(&s->lm_done[g], cudaEventDisableTiming));
+    DSLAM_CUDA(cudaStreamSynchronize(s->lm_stream[g]));
+  }
   DSLAM_CUDA(cudaStreamSynchronize(s->stream));
   *out = s;
   return DSLAM_OK;
@@ -638,6 +772,25 @@ int dslam_session_destroy(dslam_session *s) {
   if (!s) return DSLAM_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
+  for (int g = 1; g < dslam_session::kLmGroups; g++) {
+    if (s->workers[g]) {
+      {
+        std::lock_guard<std::mutex> lock(s->workers[g]->m);
+        s->workers[g]->quit = true;
+        s->workers[g]->cv.notify_all();
+      }
+      s->workers[g]->th.join();
+      delete s->workers[g];
+      s->workers[g] = nullptr;
+    }
+    if (!s->lm_stream[g]) continue;
+    cudaStreamSynchronize(s->lm_stream[g]);
+    cudaFree(s->lm_scratch[g].partials);
+    cudaFree(s->lm_scratch[g].counters);
+    cudaEventDestroy(s->lm_done[g]);
+    cudaStreamDestroy(s->lm_stream[g]);
+  }
+  if (s->lm_fork) cudaEventDestroy(s->lm_fork);
   cudaFree(s->scratch.partials);
   cudaFree(s->scratch.counters);
   cudaFreeHost(s->results_host);
@@ -651,6 +804,7 @@ int dslam_session_destroy(dslam_session *s) {
 
 int dslam_session_sync(dslam_session *s) {
   if (!s) return fail(DSLAM_EINVAL, "null session");
+  for (int g = 1; g < dslam_session::kLmGroups; g++) DSLAM_CUDA(cudaStreamSynchronize(s->lm_stream[g]));
   DSLAM_CUDA(cudaStreamSynchronize(s->stream));
   return DSLAM_OK;
 }
@@ -663,7 +817,7 @@ int dslam_session_stream(dslam_session *s, void **cuda_stream_out) {
 
 int dslam_session_launch_count(dslam_session *s, long long *count) {
   if (!s || !count) return fail(DSLAM_EINVAL, "null argument");
-  *count = s->launches;
+  *count = s->launches.load();
   return DSLAM_OK;
 }
 
@@ -702,6 +856,15 @@ int dslam_session_profile_read(dslam_session *s, double out[12]) {
     if (ms > out[m + 3]) out[m + 3] = ms;
   }
   s->prof_used = 0;
+  return DSLAM_OK;
+}
+
+int dslam_session_host_times(dslam_session *s, double out[4]) {
+  if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
+  out[0] = s->t_prep_ns.exchange(0) * 1e-6;
+  out[1] = s->t_launch_ns.exchange(0) * 1e-6;
+  out[2] = s->t_wait_ns.exchange(0) * 1e-6;
+  out[3] = (double)s->n_rounds.exchange(0);
   return DSLAM_OK;
 }
 

@@ -3,7 +3,12 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -38,11 +43,33 @@ struct dslam_session {
   dslam::EvalResult *results_host = nullptr;  // cudaHostAllocMapped
   dslam::EvalResult *results_dev = nullptr;   // device alias of results_host
   dslam::EvalScratch scratch{nullptr, nullptr};
-  unsigned seq = 0;        // sequence number of the last evaluation launch group
-  long long launches = 0;  // kernels of this library launched on the stream
+  std::atomic<unsigned> seq{0};        // sequence number of the last evaluation launch group
+  std::atomic<long long> launches{0};  // kernels of this library launched on the session's streams
   cudaEvent_t mark[2] = {nullptr, nullptr};
   int num_sms = 148;
   double timeout_s = 20.0;
+  // Lock-step LM rounds: the machines of a call are dealt into `lm_groups` groups; every group has its own CUDA stream,
+  // reduction scratch, slice of the result ring and HOST THREAD, and runs "prepare -> launch -> wait -> consume" on its
+  // own.  The kernels of different groups overlap on the GPU (each is latency-bound and fills a fraction of the SMs) and
+  // the host-side LM algebra + launch overhead (which bounds a single thread at ~15 us per round) runs in parallel.
+  // Group 0 uses `stream` / `scratch` and the calling thread.
+  static constexpr int kLmGroups = 4;
+  int lm_groups = 4;  // DSLAM_LM_GROUPS (1..kLmGroups)
+  cudaStream_t lm_stream[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};
+  dslam::EvalScratch lm_scratch[kLmGroups] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t lm_done[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lm_fork = nullptr;
+  struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+  };
+  Worker *workers[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused (the caller's thread)
+  std::mutex prof_mutex;
+  // host-side time split of the lock-step driver (ns, summed over the group threads)
+  std::atomic<long long> t_prep_ns{0}, t_launch_ns{0}, t_wait_ns{0}, n_rounds{0};
   // optional per-launch profiling of the evaluation kernels (CUDA events on this stream around every launch)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;     // pairs

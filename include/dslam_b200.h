@@ -63,6 +63,9 @@ int dslam_session_elapsed_ms(dslam_session *s, float *ms);
  * launches, out[8..11] mixed pose+scale launches; reading resets the counters. */
 int dslam_session_profile(dslam_session *s, int enable);
 int dslam_session_profile_read(dslam_session *s, double out[12]);
+/* host-side time split of the lock-step LM driver since the last call, in ms: out[0] LM algebra + item preparation,
+ * out[1] kernel launches, out[2] waiting for results, out[3] number of launches */
+int dslam_session_host_times(dslam_session *s, double out[4]);
 /* pinned host memory helpers (cudaHostAlloc) so callers can make H2D/D2H truly asynchronous */
 int dslam_host_alloc(unsigned long long bytes, void **out);
 int dslam_host_free(void *p);
