@@ -702,6 +702,9 @@ int check_ctx_frame(const dslam_ctx *c, const dslam_frame *f, int coarsestLvl) {
 }  // namespace
 }  // namespace dslam
 
+#ifdef DSLAM_KERNEL_TIMING
+namespace dslam { cudaError_t debug_times(unsigned long long *out8, int reset); }
+#endif
 using namespace dslam;
 
 // ===================================================================================================
@@ -867,6 +870,14 @@ int dslam_session_host_times(dslam_session *s, double out[4]) {
   out[3] = (double)s->n_rounds.exchange(0);
   return DSLAM_OK;
 }
+
+#ifdef DSLAM_KERNEL_TIMING
+int dslam_debug_kernel_times(dslam_session *s, unsigned long long *out8, int reset) {
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  DSLAM_CUDA(dslam::debug_times(out8, reset));
+  return DSLAM_OK;
+}
+#endif
 
 int dslam_host_alloc(unsigned long long bytes, void **out) {
   if (!out) return fail(DSLAM_EINVAL, "null argument");

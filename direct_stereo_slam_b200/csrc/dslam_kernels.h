@@ -12,7 +12,7 @@ constexpr int kMaxLevels = 6;
 // residual / Jacobian / normal-equation kernels (kernels_residual.cu)
 // ---------------------------------------------------------------------------------------------------
 constexpr int kEvalThreads = 128;        // threads per CTA of the evaluation kernels
-constexpr int kMaxBlocksPerItem = 64;    // partial-sum slots per work item
+constexpr int kMaxBlocksPerItem = 96;    // partial-sum slots per work item
 constexpr int kMaxItemsPerLaunch = 128;  // work items carried in kernel-parameter space per launch
 constexpr int kPoseVals = 48;            // 45 upper-triangle sums + E + shiftT + shiftRT
 constexpr int kScaleVals = 8;            // JwJ, Jwr, rwr, E, shiftT, shiftRT, 0, 0

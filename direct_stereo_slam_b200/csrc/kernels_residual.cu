@@ -103,6 +103,18 @@ __device__ __forceinline__ float3 interp33(const float4 *__restrict__ tex, float
   return r;
 }
 
+#ifdef DSLAM_KERNEL_TIMING
+// diagnostic build only: phase timestamps (globaltimer, ns) of the last launch: [0] first CTA entry, [1] last CTA leaves
+// the point loop, [2] last ticket taken, [3] last result record written, [4] first CTA leaves the loop
+__device__ unsigned long long g_dbg_times[8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DBG_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_dbg_times[i], gtime()); } while (0)
+#define DBG_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_dbg_times[i], gtime()); } while (0)
+#else
+#define DBG_MIN(i)
+#define DBG_MAX(i)
+#endif
+
 constexpr float kHuberTH = 9.0f;  // setting_huberTH  deps:dso/src/util/settings.cpp:127
 
 template <int CAP>
@@ -262,6 +274,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   if ((int)blockIdx.x >= it.nblocks) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  DBG_MIN(0);
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) acc[i] = 0.0;
@@ -275,6 +288,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
     else eval_points<0, NV>(it, acc, nE, nSat, nInl);
   }
 
+  DBG_MAX(1);
+  DBG_MIN(4);
   // ---- CTA reduction ---------------------------------------------------------------------------------
   __shared__ double sred[NW][NV];
   __shared__ int scnt[3];
@@ -311,11 +326,13 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
     atomicAdd(cnt + 0, scnt[0]);
     atomicAdd(cnt + 1, scnt[1]);
     atomicAdd(cnt + 2, scnt[2]);
-    __threadfence();
-    const int ticket = atomicAdd(cnt + 3, 1);
+    // one acq_rel RMW instead of fence + relaxed atomic + fence: releases this CTA's partial record and counters
+    // (ordered before it through the barrier) and acquires those of the CTAs that took earlier tickets
+    int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(cnt + 3) : "memory");
     s_last = (ticket == it.nblocks - 1);
-    if (s_last) __threadfence();  // acquire side: the other CTAs' partials and counters
   }
+  DBG_MAX(2);
   __syncthreads();
   if (!s_last) return;
 
@@ -356,6 +373,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
     w[kResultCountBase + k] = ((unsigned long long)(unsigned)v << 32) | seq;
     __stcg(cnt + k, 0);
   }
+  DBG_MAX(3);
   if (tid == 67) __stcg(cnt + 3, 0);  // ticket: the next launch on this stream starts after this grid has drained
 }
 
@@ -373,11 +391,21 @@ cudaError_t launch_mode(const EvalBatch &batch, int nitems, int grid_x, EvalScra
                         cudaStream_t stream) {
   if (nitems <= 1) return launch_cap<MODE, 1>(batch, nitems, grid_x, scratch, results, seq, stream);
   if (nitems <= 8) return launch_cap<MODE, 8>(batch, nitems, grid_x, scratch, results, seq, stream);
+  if (nitems <= 16) return launch_cap<MODE, 16>(batch, nitems, grid_x, scratch, results, seq, stream);
   if (nitems <= 32) return launch_cap<MODE, 32>(batch, nitems, grid_x, scratch, results, seq, stream);
   return launch_cap<MODE, kMaxItemsPerLaunch>(batch, nitems, grid_x, scratch, results, seq, stream);
 }
 
 }  // namespace
+
+#ifdef DSLAM_KERNEL_TIMING
+cudaError_t debug_times(unsigned long long *out8, int reset) {
+  unsigned long long init[8] = {~0ull, 0, 0, 0, ~0ull, 0, 0, 0};
+  cudaError_t e = cudaMemcpyFromSymbol(out8, g_dbg_times, sizeof(init));
+  if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(g_dbg_times, init, sizeof(init));
+  return e;
+}
+#endif
 
 cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream) {

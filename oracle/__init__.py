@@ -17,11 +17,32 @@ c_d = C.POINTER(C.c_double)
 c_i = C.POINTER(C.c_int)
 
 
+def _native_dir():
+    """-march=native objects are machine specific and must never travel: they live under the temp dir, keyed by the
+    oracle sources and the CPU flags of this machine."""
+    import hashlib
+    import tempfile
+
+    h = hashlib.sha1()
+    for f in ("dslam_oracle.cpp", "sc_generate.cpp", "Makefile"):
+        h.update(open(os.path.join(_HERE, f), "rb").read())
+    try:
+        flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0]
+    except Exception:
+        flags = ""
+    h.update(flags.encode())
+    return os.path.join(tempfile.gettempdir(), "dslam_oracle_native_" + h.hexdigest()[:16])
+
+
 def build(native=False, quiet=True):
     """Compile the oracle with the committed Makefile; returns the path of the shared library."""
-    target = "native" if native else "all"
-    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL if quiet else None)
-    return os.path.join(_BUILD, "libdslam_oracle_native.so" if native else "libdslam_oracle.so")
+    out = subprocess.DEVNULL if quiet else None
+    if native:
+        d = _native_dir()
+        subprocess.run(["make", "-C", _HERE, "native", "B=" + d], check=True, stdout=out)
+        return os.path.join(d, "libdslam_oracle_native.so")
+    subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=out)
+    return os.path.join(_BUILD, "libdslam_oracle.so")
 
 
 def _fp(a):
@@ -60,9 +81,7 @@ def pyr_levels_used(w, h, max_levels=6):
 class Oracle:
     def __init__(self, native=False, path=None):
         if path is None:
-            path = os.path.join(_BUILD, "libdslam_oracle_native.so" if native else "libdslam_oracle.so")
-            if not os.path.exists(path):
-                path = build(native=native)
+            path = build(native=native)  # make decides whether anything is out of date
         self.path = path
         L = self.lib = C.CDLL(path)
         L.orc_make_images.argtypes = [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]
