@@ -424,3 +424,156 @@ class ReferencePieces:
         ncand = np.zeros(n, np.int32)
         self.lib.ref_search_ringkey_sequence(_fp(keys), n, dim, _ip(cand), _ip(ncand))
         return cand, ncand
+
+
+class ReferenceTracker:
+    """oracle/_ref/libdslam_ref_tracker.so: the reference's OWN TrackerAndScaler.cpp hot path (constructor, makeK,
+    makeCoarseDepthL0, trackNewestCoarse, calcResPose, calcGSSSEPose, optimizeScale, calcResScale, calcGSSSEScale) compiled
+    in place against the Eigen / Sophus / DSO stand-ins of oracle/shim (oracle/ref_build.py)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so"))
+
+    def __init__(self, w, h, levels, K0, K1, T_stereo, path=None):
+        path = path or os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = self.L = C.CDLL(path)
+        L.reft_create.restype = C.c_void_p
+        L.reft_create.argtypes = [C.c_int, C.c_int, C.c_int, c_f, c_f, c_d]
+        L.reft_destroy.argtypes = [C.c_void_p]
+        L.reft_set_aff_mode.argtypes = [C.c_float, C.c_float]
+        L.reft_set_ref.argtypes = [C.c_void_p, c_f, C.c_int, c_i, c_i, c_f, c_f, C.c_float, C.c_double, C.c_double]
+        L.reft_get_ref_level.restype = C.c_int
+        L.reft_get_ref_level.argtypes = [C.c_void_p, C.c_int, c_f, c_f, c_f, c_f]
+        L.reft_scale_idepth.argtypes = [C.c_void_p, C.c_float]
+        L.reft_set_new_frame.argtypes = [C.c_void_p, c_f, C.c_float]
+        L.reft_set_right_frame.argtypes = [C.c_void_p, c_f]
+        L.reft_calc_res_pose.restype = C.c_int
+        L.reft_calc_res_pose.argtypes = [C.c_void_p, C.c_int, c_d, C.c_double, C.c_double, C.c_float, c_d]
+        L.reft_calc_gs_pose.argtypes = [C.c_void_p, C.c_int, c_d, C.c_double, C.c_double, c_d, c_d]
+        L.reft_get_warped.restype = C.c_int
+        L.reft_get_warped.argtypes = [C.c_void_p, C.c_int, c_f]
+        L.reft_track.restype = C.c_int
+        L.reft_track.argtypes = [C.c_void_p, c_d, c_d, C.c_int, c_d, c_d, c_d]
+        L.reft_calc_res_scale.restype = C.c_int
+        L.reft_calc_res_scale.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, c_d]
+        L.reft_calc_gs_scale.argtypes = [C.c_void_p, C.c_int, C.c_float, c_f, c_f]
+        L.reft_optimize_scale.restype = C.c_float
+        L.reft_optimize_scale.argtypes = [C.c_void_p, c_f, C.c_int]
+        L.reft_get_K.argtypes = [C.c_void_p, C.c_int, c_f]
+        L.refimg_make_images.argtypes = [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]
+        K0 = np.ascontiguousarray(K0, np.float32)
+        K1 = np.ascontiguousarray(K1, np.float32)
+        T = np.ascontiguousarray(T_stereo, np.float64).reshape(16)
+        self.levels = levels
+        self.p = C.c_void_p(L.reft_create(w, h, levels, _fp(K0), _fp(K1), _dp(T)))
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.L.reft_destroy(self.p)
+        except Exception:
+            pass
+
+    def set_aff_mode(self, a, b):
+        self.L.reft_set_aff_mode(a, b)
+
+    @staticmethod
+    def weight_from_hdif(hdif):
+        """weight = sqrtf(1e-3 / (HdiF + 1e-12))  (TrackerAndScaler.cpp:160) in the C types of that expression."""
+        hdif = np.asarray(hdif, np.float32)
+        return np.sqrt((1e-3 / (hdif.astype(np.float64) + 1e-12)).astype(np.float32)).astype(np.float32)
+
+    def set_ref(self, dIp_ref_all, pu, pv, pid, hdif, exposure=1.0, a=0.0, b=0.0):
+        pu = np.ascontiguousarray(pu, np.int32)
+        pv = np.ascontiguousarray(pv, np.int32)
+        pid = np.ascontiguousarray(pid, np.float32)
+        hdif = np.ascontiguousarray(hdif, np.float32)
+        self._keep["ref"] = (dIp_ref_all, pu, pv, pid, hdif)
+        self.L.reft_set_ref(self.p, _fp(dIp_ref_all), len(pu), _ip(pu), _ip(pv), _fp(pid), _fp(hdif), exposure, a, b)
+
+    def get_ref_level(self, lvl):
+        n = self.L.reft_get_ref_level(self.p, lvl, None, None, None, None)
+        arrs = [np.empty(n, np.float32) for _ in range(4)]
+        self.L.reft_get_ref_level(self.p, lvl, *[_fp(x) for x in arrs])
+        return arrs
+
+    def scale_idepth(self, s):
+        self.L.reft_scale_idepth(self.p, s)
+
+    def set_new_frame(self, dIp_all, exposure=1.0):
+        self._keep["new"] = dIp_all
+        self.L.reft_set_new_frame(self.p, _fp(dIp_all), exposure)
+
+    def set_right_frame(self, dIp_all):
+        self._keep["right"] = dIp_all
+        self.L.reft_set_right_frame(self.p, _fp(dIp_all))
+
+    def calc_res_pose(self, lvl, pose7, aff, cutoff=20.0):
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        res = np.empty(6, np.float64)
+        n = self.L.reft_calc_res_pose(self.p, lvl, _dp(pose7), aff[0], aff[1], cutoff, _dp(res))
+        return res, n
+
+    def calc_gs_pose(self, lvl, pose7, aff):
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        H = np.empty(64, np.float64)
+        b = np.empty(8, np.float64)
+        self.L.reft_calc_gs_pose(self.p, lvl, _dp(pose7), aff[0], aff[1], _dp(H), _dp(b))
+        return H.reshape(8, 8), b
+
+    def get_warped(self, which=0):
+        n = self.L.reft_get_warped(self.p, which, None)
+        out = np.empty((8, n), np.float32)
+        self.L.reft_get_warped(self.p, which, _fp(out))
+        return out
+
+    def track_newest_coarse(self, pose7, aff, coarsest, min_res=None):
+        pose7 = np.array(pose7, np.float64)
+        aff = np.array(aff, np.float64)
+        min_res = np.full(5, np.nan) if min_res is None else np.ascontiguousarray(min_res, np.float64)
+        last = np.empty(5, np.float64)
+        flow = np.empty(3, np.float64)
+        ok = self.L.reft_track(self.p, _dp(pose7), _dp(aff), coarsest, _dp(min_res), _dp(last), _dp(flow))
+        return bool(ok), pose7, aff, last, flow
+
+    def calc_res_scale(self, lvl, scale, cutoff=20.0):
+        res = np.empty(6, np.float64)
+        n = self.L.reft_calc_res_scale(self.p, lvl, scale, cutoff, _dp(res))
+        return res, n
+
+    def calc_gs_scale(self, lvl, scale):
+        H = C.c_float(0)
+        b = C.c_float(0)
+        self.L.reft_calc_gs_scale(self.p, lvl, scale, C.byref(H), C.byref(b))
+        return H.value, b.value
+
+    def optimize_scale(self, scale, coarsest):
+        s = C.c_float(scale)
+        rmse = self.L.reft_optimize_scale(self.p, C.byref(s), coarsest)
+        return rmse, s.value
+
+    def get_K(self, lvl):
+        out = np.empty(17, np.float32)
+        self.L.reft_get_K(self.p, lvl, _fp(out))
+        return out
+
+
+def reference_make_images(img, levels, B256=None):
+    """The reference's own FrameHessian::makeImages (deps:dso HessianBlocks.cpp:128-191 compiled in place); same output layout
+    as Oracle.make_images (first / last row of dx, dy, absSquaredGrad zeroed: the reference leaves them uninitialised)."""
+    L = C.CDLL(os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so"))
+    L.refimg_make_images.argtypes = [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    tot = level_offsets(w, h, levels)[-1]
+    dIp = np.empty((tot, 3), np.float32)
+    ag = np.empty(tot, np.float32)
+    Bp = None
+    if B256 is not None:
+        B256 = np.ascontiguousarray(B256, np.float32)
+        Bp = _fp(B256)
+    L.refimg_make_images(_fp(img), w, h, levels, Bp, _fp(dIp), _fp(ag))
+    return dIp, ag

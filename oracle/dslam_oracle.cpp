@@ -4,17 +4,24 @@
 // file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // load the shared library built from it (oracle/_build/libdslam_oracle.so).
 //
-// PARITY STATUS: **parity unpinned** for the pose / scale / pyramid functions.  The reference
-// (IRVLab/direct_stereo_slam @ fd12853c, DSO @ aca17755 inside dependencies.zip) ships no tests,
-// golden vectors or fixtures for this path and cannot be compiled in this image
-// (every translation unit includes Eigen, which is absent).  Each function below restates the
-// arithmetic of the cited reference lines in the same operation order, with floating-point
-// contraction OFF (-ffp-contract=off).  Where the reference delegates to Eigen 3.3 / Sophus
-// expression templates the evaluation order of those libraries' published algorithms is restated
-// (Eigen 3.3.7 coefficient-based small products reduce 3 terms as e0 + (e1 + e2); Eigen 3x3 inverse
-// by cofactors; Sophus quaternion SE3).  The Scan-Context search functions (search_sc /
-// search_ringkey) ARE pinned: oracle/ref_build.py compiles the reference's own search_place.h (and
-// ScaleAccumulator.h) in place against tiny shims and tests/test_oracle_ref.py compares.
+// PARITY STATUS.  The reference (IRVLab/direct_stereo_slam @ fd12853c, DSO @ aca17755 inside dependencies.zip) ships no
+// tests, golden vectors or fixtures for this path and cannot be built as a whole in this image (no Eigen,
+// Sophus' dependencies, OpenCV, ROS).  The restatement below is pinned as follows:
+//   * BIT-EXACT against the reference's OWN SOURCE TEXT compiled in place (oracle/ref_build.py -> oracle/_ref/, g++ on the
+//     reference's files, nothing copied): TrackerAndScaler.cpp hot path (:1-336, :451-1172 — constructor, makeK,
+//     makeCoarseDepthL0, trackNewestCoarse, calcResPose, calcGSSSEPose, optimizeScale, calcResScale, calcGSSSEScale),
+//     FrameHessian::makeImages (deps:dso HessianBlocks.cpp:128-191), Accumulator9 (deps:dso MatrixAccumulators.h),
+//     ScaleAccumulator.h, getInterpolatedElement33 (deps:dso util/globalFuncs.h), search_place.h (search_ringkey,
+//     search_sc).  tests/test_oracle_ref.py, tests/test_oracle_ref_tracker.py.
+//   * Those sources are compiled against stand-ins (oracle/shim) for Eigen, Sophus::SE3d, OpenCV and the DSO structs, so
+//     what remains UNPINNED is only what the stand-ins restate: the evaluation order Eigen 3.3 gives the small fixed-size
+//     expressions (3-term coefficient products reduce as e0 + (e1 + e2); 3x3 inverse by cofactors; `scale * M * v`
+//     keeps the scalar in the lhs coefficients), Eigen's LDLT (any backward-stable 8x8 double solve agrees to ~1e-15)
+//     and Sophus' quaternion SE3 exp / product.  FLANN (un-vendored, unpinned; Ubuntu 20.04 libflann-dev 1.9.1) is
+//     replaced by exact brute force in flann::L2's summation order.  ScanContext::generate (sc_generate.cpp) is unpinned
+//     (it depends on Eigen's SelfAdjointEigenSolver sign conventions).
+// Every function restates the arithmetic of the cited reference lines in the same operation order, with floating-point
+// contraction OFF (-ffp-contract=off).
 //
 // "src/..."  = /root/reference/src/...          "deps:dso/..." = dso/ inside dependencies.zip
 //

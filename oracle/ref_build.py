@@ -37,7 +37,23 @@ def main():
                "-I", os.path.join(REF, "src"),             # scale_optimization/..., loop_closure/...
                os.path.join(HERE, "ref_driver.cpp"), "-o", os.path.join(OUT, "libdslam_ref.so")]
         subprocess.run(cmd, check=True)
-    print("built", os.path.join(OUT, "libdslam_ref.so"))
+        print("built", os.path.join(OUT, "libdslam_ref.so"))
+        # ---- the tracker itself: the reference's TrackerAndScaler.cpp (hot-path line ranges) against the shims ----------
+        with zipfile.ZipFile(os.path.join(REF, "dependencies.zip")) as z:
+            z.extract("dso/src/util/globalFuncs.h", tmp)  # getInterpolatedElement33
+            hb = z.read("dso/src/FullSystem/HessianBlocks.cpp").decode().split("\n")
+        with open(os.path.join(tmp, "makeimages_extract.inc"), "w") as f:
+            f.write("\n".join(hb[127:191]))  # FrameHessian::makeImages, :128-191
+        src = open(os.path.join(REF, "src", "scale_optimization", "TrackerAndScaler.cpp")).read().split("\n")
+        keep = src[0:336] + src[450:1172] + ["", "}  // namespace dso", ""]  # :1-336 and :451-1172 (1-based, inclusive)
+        with open(os.path.join(tmp, "tracker_extract.inc"), "w") as f:
+            f.write("\n".join(keep))
+        cmd = ["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-w",
+               "-I", os.path.join(HERE, "shim"), "-I", tmp, "-I", os.path.join(tmp, "dso", "src"),
+               "-I", os.path.join(REF, "src"), "-I", os.path.join(REF, "src", "scale_optimization"),
+               os.path.join(HERE, "ref_driver_tracker.cpp"), "-o", os.path.join(OUT, "libdslam_ref_tracker.so")]
+        subprocess.run(cmd, check=True)
+        print("built", os.path.join(OUT, "libdslam_ref_tracker.so"))
     return 0
 
 

@@ -1,0 +1,3 @@
+#pragma once
+#include "FullSystem/HessianBlocks.h"
+#include "util/globalFuncs.h"
