@@ -431,6 +431,8 @@ class ReferenceTracker:
     makeCoarseDepthL0, trackNewestCoarse, calcResPose, calcGSSSEPose, optimizeScale, calcResScale, calcGSSSEScale) compiled
     in place against the Eigen / Sophus / DSO stand-ins of oracle/shim (oracle/ref_build.py)."""
 
+    OPT_PATH = os.path.join(_HERE, "_ref", "libdslam_ref_tracker_opt.so")  # -O3 build for timing
+
     @staticmethod
     def available():
         return os.path.exists(os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so"))
@@ -561,10 +563,16 @@ class ReferenceTracker:
         return out
 
 
-def reference_make_images(img, levels, B256=None):
+_REF_LIBS = {}
+
+
+def reference_make_images(img, levels, B256=None, path=None):
     """The reference's own FrameHessian::makeImages (deps:dso HessianBlocks.cpp:128-191 compiled in place); same output layout
     as Oracle.make_images (first / last row of dx, dy, absSquaredGrad zeroed: the reference leaves them uninitialised)."""
-    L = C.CDLL(os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so"))
+    path = path or os.path.join(_HERE, "_ref", "libdslam_ref_tracker.so")
+    if path not in _REF_LIBS:
+        _REF_LIBS[path] = C.CDLL(path)
+    L = _REF_LIBS[path]
     L.refimg_make_images.argtypes = [c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape

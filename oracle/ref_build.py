@@ -54,6 +54,13 @@ def main():
                os.path.join(HERE, "ref_driver_tracker.cpp"), "-o", os.path.join(OUT, "libdslam_ref_tracker.so")]
         subprocess.run(cmd, check=True)
         print("built", os.path.join(OUT, "libdslam_ref_tracker.so"))
+        # the same translation unit with the reference's own optimisation level (CMakeLists.txt:4-11: Release, -march=native;
+        # x86-64-v3 instead of native because the library travels to the GPU box) for the timed CPU baseline of bench.py
+        cmd_opt = [c for c in cmd if c not in ("-O2", "-ffp-contract=off", "-msse2")]
+        cmd_opt[1:1] = ["-O3", "-march=x86-64-v3"]
+        cmd_opt[-1] = os.path.join(OUT, "libdslam_ref_tracker_opt.so")
+        subprocess.run(cmd_opt, check=True)
+        print("built", cmd_opt[-1])
     return 0
 
 
