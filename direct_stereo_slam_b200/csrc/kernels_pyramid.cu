@@ -122,73 +122,97 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                : "memory");
 }
 
-__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ FrameBatch B) {
-  __shared__ __align__(128) float box[kGradBoxH * kGradBoxW];
-  __shared__ __align__(8) uint64_t bar;
+// Persistent CTAs with a two-stage TMA pipeline: while the threads turn the halo box of tile i into texels, the box of
+// tile i+1 (possibly of another level / frame) is already in flight.  A tile that lives alone in its CTA pays the
+// descriptor fetch, the TMA round trip and the pointer loads serially (~2 us for 16 KB of output) — that, not
+// bandwidth, bounded the one-tile-per-CTA version at 2.8 TB/s.
+struct TileInfo {
+  float4 *tex;
+  float *hd, *ha;
+  const float *plane, *Bt;
+  int x0, y0, w, h, pitch;
+};
+
+__global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ FrameBatch B, int nframes) {
+  constexpr int kBoxStride = (kGradBoxH * kGradBoxW + 31) / 32 * 32;  // every stage 128-B aligned (TMA destination)
+  __shared__ __align__(128) float box[2][kBoxStride];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ TileInfo info[2];
   const int tid = threadIdx.x;
   const PyramidGeom &G = B.G;
-  const FrameDev *__restrict__ F = B.f[blockIdx.y];
-  // which level / tile
-  int lvl = 0;
-#pragma unroll
-  for (int l = 1; l < kMaxLevels; l++)
-    if (l < G.levels && (int)blockIdx.x >= G.tile_begin[l]) lvl = l;
-  const int t = blockIdx.x - G.tile_begin[lvl];
-  const int tx = t % G.tiles_x[lvl], ty = t / G.tiles_x[lvl];
-  const int x0 = tx * kGradTileW, y0 = ty * kGradTileH;
-  const int w = G.w[lvl], h = G.h[lvl], pitch = G.pitch[lvl];
+  const int tiles_per_frame = G.tile_begin[G.levels];
+  const int total = tiles_per_frame * nframes;
 
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
+  auto issue = [&](int g, int stage) {  // thread 0 only
+    const int frame = g / tiles_per_frame, tix = g - frame * tiles_per_frame;
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; l++)
+      if (l < G.levels && tix >= G.tile_begin[l]) lvl = l;
+    const int t = tix - G.tile_begin[lvl];
+    const int tx = t % G.tiles_x[lvl], ty = t / G.tiles_x[lvl];
+    const FrameDev *F = B.f[frame];
+    TileInfo ti;
+    ti.x0 = tx * kGradTileW; ti.y0 = ty * kGradTileH;
+    ti.w = G.w[lvl]; ti.h = G.h[lvl]; ti.pitch = G.pitch[lvl];
+    ti.tex = F->tex[lvl]; ti.hd = F->host_dIp[lvl]; ti.ha = F->host_abs[lvl]; ti.plane = F->plane[lvl]; ti.Bt = F->B256;
+    info[stage] = ti;
     const CUtensorMap *map = &F->map[lvl];
     tensormap_acquire(map);
-    mbar_expect_tx(&bar, kGradBoxH * kGradBoxW * sizeof(float));
-    tma_load_2d(box, map, x0 - 4, y0 - 1, &bar);
-  }
-  const float *__restrict__ plane = F->plane[lvl];
-  float4 *__restrict__ tex = F->tex[lvl];
-  float *__restrict__ hd = F->host_dIp[lvl];
-  float *__restrict__ ha = F->host_abs[lvl];
-  const float *__restrict__ Bt = F->B256;
-  mbar_wait(&bar, 0);
+    mbar_expect_tx(&bar[stage], kGradBoxH * kGradBoxW * sizeof(float));
+    tma_load_2d(box[stage], map, ti.x0 - 4, ti.y0 - 1, &bar[stage]);
+  };
 
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int g = blockIdx.x; g < total; g += gridDim.x, it++) {
+    const int stage = it & 1;
+    if (tid == 0 && g + (int)gridDim.x < total) issue(g + gridDim.x, stage ^ 1);  // stage^1 was released by the barrier below
+    mbar_wait(&bar[stage], (it >> 1) & 1);
+    const TileInfo ti = info[stage];
+    const float *__restrict__ bx = box[stage];
 #pragma unroll
-  for (int k = 0; k < kGradTileH / 4; k++) {
-    const int lx = tid % kGradTileW, ly = tid / kGradTileW + 4 * k;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= w || y >= h) continue;
-    const float *s = box + (ly + 1) * kGradBoxW + (lx + 4);
-    const float c = s[0];
-    float dx = 0.f, dy = 0.f, ag = 0.f;
-    if (y >= 1 && y <= h - 2) {
-      // linear-index neighbours: wrap at the row ends exactly like dI_l[idx-1] / dI_l[idx+1]
-      const float left = (x == 0) ? __ldg(plane + (size_t)(y - 1) * pitch + (w - 1)) : s[-1];
-      const float right = (x == w - 1) ? __ldg(plane + (size_t)(y + 1) * pitch) : s[1];
-      dx = 0.5f * (right - left);
-      dy = 0.5f * (s[kGradBoxW] - s[-kGradBoxW]);
-      if (!isfinite(dx)) dx = 0.f;
-      if (!isfinite(dy)) dy = 0.f;
-      ag = dx * dx + dy * dy;
-      if (Bt != nullptr) {
-        int ci = (int)(c + 0.5f);
-        if (ci < 5) ci = 5;
-        if (ci > 250) ci = 250;
-        const float gw = __ldg(Bt + ci + 1) - __ldg(Bt + ci);
-        ag *= gw * gw;
+    for (int k = 0; k < kGradTileH / 4; k++) {
+      const int lx = tid % kGradTileW, ly = tid / kGradTileW + 4 * k;
+      const int x = ti.x0 + lx, y = ti.y0 + ly;
+      if (x >= ti.w || y >= ti.h) continue;
+      const float *s = bx + (ly + 1) * kGradBoxW + (lx + 4);
+      const float c = s[0];
+      float dx = 0.f, dy = 0.f, ag = 0.f;
+      if (y >= 1 && y <= ti.h - 2) {
+        // linear-index neighbours: wrap at the row ends exactly like dI_l[idx-1] / dI_l[idx+1]
+        const float left = (x == 0) ? __ldg(ti.plane + (size_t)(y - 1) * ti.pitch + (ti.w - 1)) : s[-1];
+        const float right = (x == ti.w - 1) ? __ldg(ti.plane + (size_t)(y + 1) * ti.pitch) : s[1];
+        dx = 0.5f * (right - left);
+        dy = 0.5f * (s[kGradBoxW] - s[-kGradBoxW]);
+        if (!isfinite(dx)) dx = 0.f;
+        if (!isfinite(dy)) dy = 0.f;
+        ag = dx * dx + dy * dy;
+        if (ti.Bt != nullptr) {
+          int ci = (int)(c + 0.5f);
+          if (ci < 5) ci = 5;
+          if (ci > 250) ci = 250;
+          const float gw = __ldg(ti.Bt + ci + 1) - __ldg(ti.Bt + ci);
+          ag *= gw * gw;
+        }
       }
+      const size_t idx = (size_t)y * ti.w + x;
+      __stcs(ti.tex + idx, make_float4(c, dx, dy, ag));
+      if (ti.hd != nullptr) {
+        ti.hd[3 * idx + 0] = c;
+        ti.hd[3 * idx + 1] = dx;
+        ti.hd[3 * idx + 2] = dy;
+      }
+      if (ti.ha != nullptr) ti.ha[idx] = ag;
     }
-    const size_t idx = (size_t)y * w + x;
-    tex[idx] = make_float4(c, dx, dy, ag);
-    if (hd != nullptr) {
-      hd[3 * idx + 0] = c;
-      hd[3 * idx + 1] = dx;
-      hd[3 * idx + 2] = dy;
-    }
-    if (ha != nullptr) ha[idx] = ag;
+    __syncthreads();  // everyone is done with box[stage] / info[stage]: thread 0 may refill them in the next iteration
   }
 }
 
@@ -235,7 +259,10 @@ cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t str
 
 cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream) {
   if (nframes < 1) return cudaSuccess;
-  gradient_kernel<<<dim3(B.G.tile_begin[B.G.levels], nframes), 256, 0, stream>>>(B);
+  const int total = B.G.tile_begin[B.G.levels] * nframes;
+  int grid = 148 * 6;  // persistent: 6 CTAs (6 x 2 boxes of 5 KB) per SM
+  if (grid > total) grid = total;
+  gradient_kernel<<<grid, 256, 0, stream>>>(B, nframes);
   return cudaGetLastError();
 }
 
