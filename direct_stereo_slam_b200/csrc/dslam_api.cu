@@ -82,7 +82,7 @@ struct EvalOut {           // one calcRes* + calcGSSSE* evaluation, host view
 int choose_blocks(int n, int nitems, int num_sms) {
   int per = (n + kEvalThreads - 1) / kEvalThreads;  // one template point per thread: shortest critical path
   if (per < 1) per = 1;
-  const long budget = (long)num_sms * 6;            // resident CTAs worth ~2 waves when many items share a launch
+  const long budget = (long)num_sms * 5;            // one resident wave (96 registers x 128 threads -> 5 CTAs per SM) when many items share a launch
   if ((long)per * nitems > budget) {
     per = (int)(budget / nitems);
     if (per < 1) per = 1;
@@ -753,6 +753,13 @@ int dslam_session_create(int device, dslam_session **out) {
   DSLAM_CUDA(cudaEventCreate(&s->mark[1]));
   s->lm_stream[0] = s->stream;
   s->lm_scratch[0] = s->scratch;
+  {  // one host thread per group: as many as the cores this process can count on (torchrun exports LOCAL_WORLD_SIZE)
+    int ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    int g = (int)(std::thread::hardware_concurrency() / (unsigned)ranks);
+    g = g > dslam_session::kLmGroups ? dslam_session::kLmGroups : (g < 1 ? 1 : g);
+    s->lm_groups = g;
+  }
   if (const char *e = getenv("DSLAM_LM_GROUPS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= dslam_session::kLmGroups) s->lm_groups = v;

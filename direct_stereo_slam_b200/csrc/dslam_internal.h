@@ -53,11 +53,11 @@ struct dslam_session {
   // own.  The kernels of different groups overlap on the GPU (each is latency-bound and fills a fraction of the SMs) and
   // the host-side LM algebra + launch overhead (which bounds a single thread at ~15 us per round) runs in parallel.
   // Group 0 uses `stream` / `scratch` and the calling thread.
-  static constexpr int kLmGroups = 4;
+  static constexpr int kLmGroups = 8;
   int lm_groups = 4;  // DSLAM_LM_GROUPS (1..kLmGroups)
-  cudaStream_t lm_stream[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};
-  dslam::EvalScratch lm_scratch[kLmGroups] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  cudaEvent_t lm_done[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t lm_stream[kLmGroups] = {};
+  dslam::EvalScratch lm_scratch[kLmGroups] = {};
+  cudaEvent_t lm_done[kLmGroups] = {};
   cudaEvent_t lm_fork = nullptr;
   struct Worker {
     std::thread th;
@@ -66,7 +66,7 @@ struct dslam_session {
     std::function<void()> job;
     bool has_job = false, done = false, quit = false;
   };
-  Worker *workers[kLmGroups] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused (the caller's thread)
+  Worker *workers[kLmGroups] = {};  // [0] unused (the caller's thread)
   std::mutex prof_mutex;
   // host-side time split of the lock-step driver (ns, summed over the group threads)
   std::atomic<long long> t_prep_ns{0}, t_launch_ns{0}, t_wait_ns{0}, n_rounds{0};

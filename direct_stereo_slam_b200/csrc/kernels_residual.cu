@@ -83,6 +83,22 @@ struct WarpRS<8> {
   __device__ static __forceinline__ int base(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 };
 
+template <>
+struct WarpRS<16> {
+  static constexpr int KEEP = 1;
+  __device__ static __forceinline__ void run(double (&a)[16], int lane) {
+    rs_halve<16>(a, 16, lane & 16);
+    rs_halve<8>(a, 8, lane & 8);
+    rs_halve<4>(a, 4, lane & 4);
+    rs_halve<2>(a, 2, lane & 2);
+    a[0] = a[0] + shfl_xor_d(a[0], 1);
+  }
+  __device__ static __forceinline__ bool writer(int lane) { return (lane & 1) == 0; }
+  __device__ static __forceinline__ int base(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  }
+};
+
 // Eigen 3.3 coefficient product of three terms: e0 + (e1 + e2), third factor is the literal 1.
 __device__ __forceinline__ float dot3_xy1(float m0, float m1, float m2, float x, float y) { return m0 * x + (m1 * y + m2); }
 
@@ -122,7 +138,9 @@ struct BatchT {
   EvalItem item[CAP];
 };
 
-// Per-point work of one item.  MODE 0 = pose (calcResPose + calcGSSSEPose), 1 = scale (calcResScale + calcGSSSEScale).
+// Per-point work of one item with per-thread fp64 accumulators.  Used for SCALE items (MODE 1: calcResScale +
+// calcGSSSEScale); pose items take the DMMA path of eval_pose_mma below (the MODE 0 branches here are the same arithmetic
+// in per-thread FMA form and are kept as the readable statement of what the MMA path computes).
 // acc layout: pose  [0..44] upper triangle of [J0..J7 r]^T w [J0..J7 r], [45] E, [46] shiftT, [47] shiftRT
 //             scale [0] JwJ, [1] Jwr, [2] rwr, [3] E, [4] shiftT, [5] shiftRT
 template <int MODE, int NV>
@@ -263,6 +281,150 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, double (&acc)[NV
   }
 }
 
+// D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor cores (DMMA).  Fragments: A[row = lane/4][col = lane%4],
+// B[row = lane%4][col = lane/4], C/D[row = lane/4][col = 2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// index of H(g, n), g <= n, in the 45-entry upper triangle of the 9x9 [J0..J7 r] system
+__device__ __forceinline__ int tri9(int g, int n) { return 9 * g - (g * (g - 1)) / 2 + (n - g); }
+
+// Pose items: calcResPose + calcGSSSEPose with the 8x8 block H = sum_p (J_p w_p) J_p^T accumulated by DMMA.
+// A warp takes 32 template points per iteration; every lane warps / samples its point and forms its Jacobian row in the
+// reference's fp32 arithmetic, the rows go through shared memory (the transposition the MMA fragments need: lane (g, k)
+// of MMA m reads element g of point 4m + k) and eight m8n8k4 DMMAs add the 32 outer products to the warp's 8x8
+// accumulator — 2 registers per lane instead of 72 per thread, no warp reduction for H at all.  Products of fp32 values
+// are exact in fp64, so the result differs from the per-thread FMA form only in the order of the fp64 additions.
+// b = sum J w r, sum w r^2, E and the flow sums stay per lane (12 doubles) and are folded by a 16-wide reduce-scatter.
+// Results land in sred_w[48] (this warp's slot, pre-zeroed) in the oracle's acc layout.
+__device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w, float *sJ, float *sJw, int &nE, int &nSat, int &nInl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 *__restrict__ tex = it.tex;
+  const float4 *__restrict__ pts = it.pts;
+  const int wl = it.w, hl = it.h, n = it.n, stride = it.ppt_stride;
+  const float fxl = it.fx, fyl = it.fy, cxl = it.cx, cyl = it.cy;
+  const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
+  const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
+  const int g = lane >> 2, k = lane & 3;
+
+  double c0 = 0.0, c1 = 0.0;  // H(g, 2k), H(g, 2k+1)
+  double ext[16];             // [0..7] b, [8] sum w r^2, [9] E, [10] shiftT, [11] shiftRT
+#pragma unroll
+  for (int i = 0; i < 16; i++) ext[i] = 0.0;
+
+  int base = (blockIdx.x * (kEvalThreads / 32) + warp) * 32;
+  float4 p_next = base + lane < n ? __ldg(pts + base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; base < n; base += stride) {  // warp-uniform trip count: mma.sync needs all 32 lanes
+    const int i = base + lane;
+    const float4 p = p_next;
+    if (base + stride + lane < n) p_next = __ldg(pts + base + stride + lane);
+    float J[8], Jw[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) J[c] = Jw[c] = 0.f;
+    if (i < n) {
+      const float x = p.x, y = p.y, id = p.z, refColor = p.w;
+      // :747  pt = RKi * (x,y,1) + t*id
+      const float pt0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) + it.t[0] * id;
+      const float pt1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) + it.t[1] * id;
+      const float pt2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) + it.t[2] * id;
+      const float u = pt0 / pt2;
+      const float v = pt1 / pt2;
+      const float Ku = fxl * u + cxl;
+      const float Kv = fyl * v + cyl;
+      const float new_idepth = id / pt2;
+      if (Ku > 2 && Kv > 2 && Ku < wlm3 && Kv < hlm3 && new_idepth > 0) {
+        const float3 hit = interp33(tex, Ku, Kv, wl);
+        if (isfinite(hit.x)) {
+          const float residual = hit.x - (it.p0 * refColor + it.p1);
+          const float absr = fabsf(residual);
+          const float hw = absr < kHuberTH ? 1.0f : kHuberTH / absr;
+          nE++;
+          if (absr > cutoff) {
+            ext[9] += (double)maxEnergy;
+            nSat++;
+          } else {
+            ext[9] += (double)(hw * residual * residual * (2 - hw));
+            nInl++;
+            // calcGSSSEPose :658-678, lane arithmetic of the SSE code
+            const float dx = hit.y * fxl, dy = hit.z * fyl;
+            J[0] = new_idepth * dx;
+            J[1] = new_idepth * dy;
+            J[2] = 0.0f - (new_idepth * ((u * dx) + (v * dy)));
+            J[3] = 0.0f - (((u * v) * dx) + (dy * (1.0f + (v * v))));
+            J[4] = ((u * v) * dy) + (dx * (1.0f + (u * u)));
+            J[5] = (u * dy) - (v * dx);
+            J[6] = it.p0 * (it.p2 - refColor);
+            J[7] = -1.0f;
+            const double rd = (double)residual;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              Jw[c] = J[c] * hw;
+              ext[c] = fma((double)Jw[c], rd, ext[c]);
+            }
+            ext[8] = fma((double)(residual * hw), rd, ext[8]);
+          }
+        }
+      }
+    }
+    // rows -> shared memory (conflict-free: 32 B per lane, contiguous), then the fragment gathers (bank = 8k + g)
+    float4 *dJ = reinterpret_cast<float4 *>(sJ + lane * 8), *dW = reinterpret_cast<float4 *>(sJw + lane * 8);
+    dJ[0] = make_float4(J[0], J[1], J[2], J[3]);
+    dJ[1] = make_float4(J[4], J[5], J[6], J[7]);
+    dW[0] = make_float4(Jw[0], Jw[1], Jw[2], Jw[3]);
+    dW[1] = make_float4(Jw[4], Jw[5], Jw[6], Jw[7]);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const double a = (double)sJw[(4 * m + k) * 8 + g];
+      const double b = (double)sJ[(4 * m + k) * 8 + g];
+      dmma_8x8x4(c0, c1, a, b);
+    }
+    __syncwarp();
+  }
+
+  // Flow indicators (:754-784): every 32nd template point of level 0, whether or not it projects into the image.
+  if (it.flags & 1) {
+    const int nflow = (n + 31) >> 5;
+    for (int kf = blockIdx.x * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
+      const float4 p = __ldg(pts + 32 * kf);
+      const float x = p.x, y = p.y, id = p.z;
+      const float kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
+      const float kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
+      const float kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
+      const float mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
+      const float mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
+      const float mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
+      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
+      const float ptz = mx2 + tT2;
+      const float Ku = fxl * ((mx0 + tT0) / ptz) + cxl, Kv = fyl * ((mx1 + tT1) / ptz) + cyl;
+      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
+      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
+      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
+      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
+      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      ext[10] += (double)sT1;
+      ext[10] += (double)sT2;
+      ext[11] += (double)sRT1;
+      ext[11] += (double)sRT2;
+    }
+  }
+
+  // warp results -> this warp's slot of the CTA reduction buffer (oracle layout: upper triangle, E, shiftT, shiftRT)
+  if (g <= 2 * k) sred_w[tri9(g, 2 * k)] = c0;
+  if (g <= 2 * k + 1) sred_w[tri9(g, 2 * k + 1)] = c1;
+  WarpRS<16>::run(ext, lane);
+  if (WarpRS<16>::writer(lane)) {
+    const int j = WarpRS<16>::base(lane);
+    if (j < 8) sred_w[tri9(j, 8)] = ext[0];
+    else if (j == 8) sred_w[44] = ext[0];
+    else if (j < 12) sred_w[45 + (j - 9)] = ext[0];
+  }
+}
+
 // MODE 0 = pose items only, 1 = scale items only, 2 = mixed (bit 1 of EvalItem::flags selects scale; used when the pose
 // tracker and the scale optimiser of a stereo frame advance in the same launch).  grid = (max nblocks, nitems).
 template <int MODE, int CAP>
@@ -275,32 +437,29 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   DBG_MIN(0);
-  double acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; i++) acc[i] = 0.0;
+  __shared__ double sred[NW][NV];
+  __shared__ __align__(16) float sJ[MODE == 1 ? 1 : NW][MODE == 1 ? 4 : 256], sJw[MODE == 1 ? 1 : NW][MODE == 1 ? 4 : 256];
+  __shared__ int scnt[3];
+  __shared__ int s_last;
+  if (tid < 3) scnt[tid] = 0;
+  for (int i = lane; i < NV; i += 32) sred[warp][i] = 0.0;
+  __syncwarp();
   int nE = 0, nSat = 0, nInl = 0;
-  if (MODE == 0) {
-    eval_points<0, NV>(it, acc, nE, nSat, nInl);
-  } else if (MODE == 1) {
-    eval_points<1, NV>(it, acc, nE, nSat, nInl);
+  const bool scale_item = MODE == 1 || (MODE == 2 && (it.flags & 2));
+  if (!scale_item) {
+    if (MODE != 1) eval_pose_mma(it, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
   } else {
-    if (it.flags & 2) eval_points<1, NV>(it, acc, nE, nSat, nInl);
-    else eval_points<0, NV>(it, acc, nE, nSat, nInl);
+    double acc[kScaleVals];
+#pragma unroll
+    for (int i = 0; i < kScaleVals; i++) acc[i] = 0.0;
+    eval_points<1, kScaleVals>(it, acc, nE, nSat, nInl);
+    WarpRS<kScaleVals>::run(acc, lane);
+    if (WarpRS<kScaleVals>::writer(lane)) sred[warp][WarpRS<kScaleVals>::base(lane)] = acc[0];
   }
 
   DBG_MAX(1);
   DBG_MIN(4);
   // ---- CTA reduction ---------------------------------------------------------------------------------
-  __shared__ double sred[NW][NV];
-  __shared__ int scnt[3];
-  __shared__ int s_last;
-  if (tid < 3) scnt[tid] = 0;
-  WarpRS<NV>::run(acc, lane);
-  if (WarpRS<NV>::writer(lane)) {
-    const int b = WarpRS<NV>::base(lane);
-#pragma unroll
-    for (int k = 0; k < WarpRS<NV>::KEEP; k++) sred[warp][b + k] = acc[k];
-  }
   nE = __reduce_add_sync(0xffffffffu, nE);
   nSat = __reduce_add_sync(0xffffffffu, nSat);
   nInl = __reduce_add_sync(0xffffffffu, nInl);
@@ -343,19 +502,21 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   // latency in total instead of one per partial) and then adds them in CTA order — the order is fixed, so the result
   // is bit-reproducible for a given launch geometry.
   constexpr int PARTS = kEvalThreads / NV >= 2 ? 2 : 1;
-  constexpr int MAXLD = (kMaxBlocksPerItem + PARTS - 1) / PARTS;
+  constexpr int CHUNK = 12;  // independent loads in flight per thread (one L2 latency per chunk instead of one per partial)
   __shared__ double sfin[PARTS][NV];
   if (tid < NV * PARTS) {
     const int vi = tid % NV, part_i = tid / NV;
-    double v[MAXLD];
-#pragma unroll
-    for (int k = 0; k < MAXLD; k++) {
-      const int b = part_i + k * PARTS;
-      v[k] = b < it.nblocks ? __ldcg(pbase + (size_t)b * kPoseVals + vi) : 0.0;
-    }
     double s = 0.0;
+    for (int b0 = part_i; b0 < it.nblocks; b0 += CHUNK * PARTS) {
+      double v[CHUNK];
 #pragma unroll
-    for (int k = 0; k < MAXLD; k++) s += v[k];
+      for (int k = 0; k < CHUNK; k++) {
+        const int b = b0 + k * PARTS;
+        v[k] = b < it.nblocks ? __ldcg(pbase + (size_t)b * kPoseVals + vi) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < CHUNK; k++) s += v[k];
+    }
     sfin[part_i][vi] = s;
   }
   __syncthreads();
