@@ -73,17 +73,21 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     p = os.path.join(ROOT, "profiles")
     os.makedirs(p, exist_ok=True)
-    launch_list(os.path.join(g, "launches_r01b.csv"), "r01 launch list: bench.py --streams 32 --steps 2 --warmup 3 (KITTI 1232x368, 4 LM groups)", os.path.join(p, "r01_launches.md"))
-    ev = full_report(os.path.join(g, "prof_eval_r01b.ncu-rep"), "r01 eval_kernel (fused residual/Jacobian) inside bench.py, 32 streams / 4 groups", os.path.join(p, "r01_eval_kernel.md"))
-    full_report(os.path.join(g, "prof_eval128_r01.ncu-rep"), "r01 eval_kernel, 128 pose items of 9.9k points in one launch (tools/one_eval.py kitti 128) — before the flow-pass split", os.path.join(p, "r01_eval_kernel_128items_early.md"))
-    py = full_report(os.path.join(g, "prof_pyr_r01.ncu-rep"), "r01 pyramid + Scan-Context kernels inside bench.py", os.path.join(p, "r01_pyramid_sc_kernels.md"))
+    launch_list(os.path.join(g, "launches_r01c.csv"), "r01 launch list: bench.py --streams 32 --steps 2 --warmup 3 (KITTI 1232x368, 8 LM groups, DMMA eval kernel)",
+                os.path.join(p, "r01_launches.md"))
+    ev = full_report(os.path.join(g, "prof_eval_r01c.ncu-rep"), "r01 eval_kernel (fused residual / Jacobian / DMMA normal equations) inside bench.py, 32 streams / 8 groups",
+                     os.path.join(p, "r01_eval_kernel.md"))
+    full_report(os.path.join(g, "prof_eval128_dmma.ncu-rep"), "r01 eval_kernel, 128 pose items of 9.9k points in one launch (tools/one_eval.py kitti 128)",
+                os.path.join(p, "r01_eval_kernel_128items.md"))
+    py = full_report(os.path.join(g, "prof_pyr_r01c.ncu-rep"), "r01 pyramid kernels inside bench.py (32 frames per launch)", os.path.join(p, "r01_pyramid_kernels.md"))
+    sc = full_report(os.path.join(g, "prof_sc_r01c.ncu-rep"), "r01 Scan-Context kernels, 100k descriptors (tools/sc_sweep.py; first launches: Q=1)", os.path.join(p, "r01_scan_context_kernels.md"))
     traffic = {}
     tr = [to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]) for d in ev if "dram__bytes_read.sum" in d]
     if tr:
         traffic["pose_eval_dram_bytes_per_launch"] = sum(tr) / len(tr)
-        traffic["source"] = "profiles/r01_eval_kernel.md (mean over %d captured launches of the mixed eval kernel, ~40k template points each)" % len(tr)
-    for d in py:
+        traffic["source"] = "profiles/r01_eval_kernel.md (mean over %d captured launches of the eval kernel inside bench.py --streams 32)" % len(tr)
+    for d in py + sc:
         if "dram__bytes_read.sum" in d:
-            traffic.setdefault("other", {})[d["kernel"]] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+            traffic.setdefault("other", {}).setdefault(d["kernel"], []).append(to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]))
     json.dump(traffic, open(os.path.join(p, "traffic.json"), "w"), indent=1)
     print(json.dumps(traffic, indent=1))
