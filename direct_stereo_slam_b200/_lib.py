@@ -71,6 +71,7 @@ SIGNATURES = {
     "dslam_track_newest_coarse_multi": [vp, vp, C.c_float, C.c_int, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i],
     "dslam_track_newest_coarse_batch": [C.c_int, c_pp, c_pp, c_f, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i],
     "dslam_optimize_scale_batch": [C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
+    "dslam_track_new_coarse": [vp, vp, C.c_float, C.c_int, c_d, c_d, C.c_int, c_d, C.c_double, c_d, c_d, c_d, c_d, c_i, c_i],
     "dslam_lm_batch": [C.c_int, c_pp, c_pp, c_f, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i, C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
     "dslam_get_trace": [vp, c_d, C.c_int, c_i],
     "dslam_ctx_counters": [vp, C.POINTER(C.c_longlong)],
@@ -78,6 +79,7 @@ SIGNATURES = {
     "dslam_sc_destroy": [vp],
     "dslam_sc_add": [vp, C.c_int, c_f, c_f, c_i],
     "dslam_sc_add_sparse": [vp, c_f, c_i, c_d, C.c_int, C.c_int],
+    "dslam_sc_generate": [vp, c_d, C.c_int, C.c_double, c_f, c_f, c_d, c_d, C.c_int, C.c_int],
     "dslam_sc_size": [vp, c_i],
     "dslam_sc_search_ringkey": [vp, C.c_int, c_f, C.c_int, C.c_float, C.c_int, c_i, c_f],
     "dslam_sc_search_sc": [vp, C.c_int, c_f, c_i, C.c_int, c_i, c_f],

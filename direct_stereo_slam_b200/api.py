@@ -362,6 +362,22 @@ class TrackerAndScaler:
                                                        coarsestLvl, _dp(mr), _dp(last), _dp(flow), _ip(ok)))
         return ok.astype(bool), poses, affs, last, flow
 
+    def trackNewCoarse(self, newFrameHessian, pose_tries, aff_init, coarsestLvl, last_coarse_rmse, reTrackThreshold=1.5):
+        """The hypothesis loop of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:192-247), speculative lock-step evaluation.
+        -> dict(pose, aff, achievedRes, flow, haveOneGood, tryIterations)"""
+        tries = np.ascontiguousarray(np.atleast_2d(pose_tries), np.float64)
+        aff0 = np.ascontiguousarray(aff_init, np.float64)
+        last = np.ascontiguousarray(last_coarse_rmse, np.float64)
+        pose = np.empty(7)
+        aff = np.empty(2)
+        ach = np.empty(5)
+        flow = np.empty(3)
+        good = C.c_int(0)
+        ntry = C.c_int(0)
+        check(self.lib.dslam_track_new_coarse(self.p, newFrameHessian.p, newFrameHessian.ab_exposure, len(tries), _dp(tries), _dp(aff0), coarsestLvl,
+                                              _dp(last), reTrackThreshold, _dp(pose), _dp(aff), _dp(ach), _dp(flow), C.byref(good), C.byref(ntry)))
+        return dict(pose=pose, aff=aff, achievedRes=ach, flow=flow, haveOneGood=bool(good.value), tryIterations=ntry.value)
+
     def optimizeScale(self, fh1, scale, coarsestLvl):
         """-> (level-0 RMSE, optimised scale)   (TrackerAndScaler.cpp:854-964)"""
         s = C.c_float(scale)
@@ -433,6 +449,16 @@ class ScanContextDB:
         idx = np.ascontiguousarray(idx, np.int32)
         val = np.ascontiguousarray(val, np.float64)
         check(self.lib.dslam_sc_add_sparse(self.p, _fp(ringkey), _ip(idx), _dp(val), len(idx), global_id))
+
+    def generate(self, pts_spherical, lidar_range=40.0, append=False, global_id=-1):
+        """ScanContext::generate (ScanContext.cpp:78-142) on the device -> (ringkey [r], dense signature fp32 [s*r], fp64 values, tfm_pca_rig 4x4)."""
+        pts = np.ascontiguousarray(pts_spherical, np.float64).reshape(-1, 3)
+        rk = np.empty(self.n_rings, np.float32)
+        sig = np.empty(self.n_cells, np.float32)
+        sig64 = np.empty(self.n_cells, np.float64)
+        tfm = np.empty(16, np.float64)
+        check(self.lib.dslam_sc_generate(self.p, _dp(pts), len(pts), lidar_range, _fp(rk), _fp(sig), _dp(sig64), _dp(tfm), 1 if append else 0, global_id))
+        return rk, sig, sig64, tfm.reshape(4, 4)
 
     def search_ringkey(self, ringkeys, k=3, thres=0.1, max_id=2**31 - 1):
         ringkeys = np.ascontiguousarray(np.atleast_2d(ringkeys), np.float32)

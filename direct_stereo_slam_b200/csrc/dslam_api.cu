@@ -318,6 +318,12 @@ struct PoseLM {
   double lastResiduals[5]{};
   double flow[3]{};
   long long iters = 0;
+  struct LevelEvent {  // what the reference's level epilogue (:595-599) saw, in order (a level may appear twice: :601-604)
+    int lvl;
+    double residual;
+    double flow[3];
+  };
+  std::vector<LevelEvent> events;
 
   void begin(const dslam_ctx *c_, const dslam_frame *f_, float exposure, const double pose7[7], const double aff[2], int coarsestLvl,
              const double minRes[5], std::vector<double> *tr) {
@@ -328,6 +334,7 @@ struct PoseLM {
     flow[0] = flow[1] = flow[2] = 1000;  // lastFlowIndicators.setConstant(1000)  :460
     lvl = coarsestLvl;
     haveRepeated = false;
+    events.clear();
     start_level();
   }
   void start_level() {
@@ -430,6 +437,7 @@ struct PoseLM {
   void finish_level() {
     lastResiduals[lvl] = sqrtf((float)(resOld.res6[0] / resOld.res6[1]));  // :595
     flow[0] = resOld.res6[2]; flow[1] = resOld.res6[3]; flow[2] = resOld.res6[4];
+    events.push_back(LevelEvent{lvl, lastResiduals[lvl], {flow[0], flow[1], flow[2]}});
     if (lastResiduals[lvl] > 1.5 * minResForAbort[lvl]) {  // :597-598
       ok = false;
       phase = DONE;
@@ -1520,6 +1528,101 @@ int dslam_optimize_scale_multi(dslam_ctx *c, dslam_frame *f_right, int nseeds, f
 
 int dslam_optimize_scale(dslam_ctx *c, dslam_frame *f_right, float *scale_io, int coarsestLvl, float *rmse_out) {
   return dslam_optimize_scale_multi(c, f_right, 1, scale_io, coarsestLvl, rmse_out);
+}
+
+// The hypothesis loop of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:192-247) with the retries evaluated speculatively in
+// lock-step batches.  A trial does not depend on `achievedRes` except for the abort test at the end of every level
+// (TrackerAndScaler.cpp:597-598), so each trial is run without that test, its per-level (residual, flow) events are
+// recorded, and the sequential loop is then REPLAYED on the recorded events with the evolving achievedRes: an aborted
+// trial is cut at the level where the reference would have returned false.  The outputs are exactly those of the
+// sequential loop.  Trials are evaluated in stages (1, then 4, then all the rest) and a stage only runs if the replay
+// reaches it — in the common case the first hypothesis ends the loop and nothing else is evaluated.
+int dslam_track_new_coarse(dslam_ctx *c, dslam_frame *f, float new_exposure, int ntries, const double *pose7_tries, const double aff_init[2],
+                           int coarsestLvl, const double last_coarse_rmse[5], double reTrackThreshold, double pose7_out[7], double aff_out[2],
+                           double achievedRes_out[5], double flow3_out[3], int *haveOneGood_out, int *tryIterations_out) {
+  int rc = check_ctx_frame(c, f, coarsestLvl);
+  if (rc != DSLAM_OK) return rc;
+  if (ntries < 1 || ntries > kResultSlots || !pose7_tries || !aff_init || !last_coarse_rmse || !pose7_out || !aff_out || !achievedRes_out)
+    return fail(DSLAM_EINVAL, "bad argument");
+  c->trace.clear();
+  const double never[5] = {NAN, NAN, NAN, NAN, NAN};  // "x > 1.5 * NaN" is false: no abort while speculating
+  std::vector<PoseLM> lms((size_t)ntries);
+  std::vector<ScaleLM> none;
+  std::vector<double> p0((size_t)ntries * 7), a0((size_t)ntries * 2);
+  int computed = 0;
+  auto compute_until = [&](int upto) -> int {  // evaluate trials [computed, upto) in one lock step
+    if (upto > ntries) upto = ntries;
+    if (upto <= computed) return DSLAM_OK;
+    std::vector<PoseLM> batch((size_t)(upto - computed));
+    for (int i = computed; i < upto; i++) {
+      std::memcpy(&p0[7 * (size_t)i], pose7_tries + 7 * (size_t)i, sizeof(double) * 7);
+      a0[2 * (size_t)i] = aff_init[0];
+      a0[2 * (size_t)i + 1] = aff_init[1];
+      batch[i - computed].begin(c, f, new_exposure, &p0[7 * (size_t)i], &a0[2 * (size_t)i], coarsestLvl, never, i == 0 ? &c->trace : nullptr);
+    }
+    const int r = run_lock_step(c->s, batch, none, c);
+    if (r != DSLAM_OK) return r;
+    for (int i = computed; i < upto; i++) {
+      lms[i] = std::move(batch[i - computed]);
+      c->n_iters += lms[i].iters;
+    }
+    computed = upto;
+    return DSLAM_OK;
+  };
+  double achieved[5] = {NAN, NAN, NAN, NAN, NAN};
+  double flow[3] = {100, 100, 100};
+  double pose[7] = {0, 0, 0, 1, 0, 0, 0}, aff[2] = {0, 0};
+  bool haveOneGood = false;
+  int tries = 0;
+  const int stage_end[3] = {1, 5, ntries};
+  for (int i = 0; i < ntries; i++) {
+    if (i >= computed) {
+      int upto = ntries;
+      for (int st = 0; st < 3; st++)
+        if (i < stage_end[st]) { upto = stage_end[st]; break; }
+      rc = compute_until(upto);
+      if (rc != DSLAM_OK) return rc;
+    }
+    PoseLM &m = lms[i];
+    // replay trackNewestCoarse(..., achievedRes, currentRes) on the recorded level events
+    double cur[5] = {NAN, NAN, NAN, NAN, NAN}, fl[3] = {1000, 1000, 1000};
+    bool aborted = false;
+    for (const PoseLM::LevelEvent &e : m.events) {
+      cur[e.lvl] = e.residual;
+      fl[0] = e.flow[0]; fl[1] = e.flow[1]; fl[2] = e.flow[2];
+      if (e.residual > 1.5 * achieved[e.lvl]) {  // TrackerAndScaler.cpp:597-598
+        aborted = true;
+        break;
+      }
+    }
+    double pose_i[7], aff_i[2] = {aff_init[0], aff_init[1]};
+    std::memcpy(pose_i, pose7_tries + 7 * (size_t)i, sizeof(pose_i));
+    bool good = false;
+    if (!aborted) good = finish_pose(c, m, new_exposure, pose_i, aff_i);
+    tries++;
+    if (good && std::isfinite((float)cur[0]) && !(cur[0] >= achieved[0])) {  // FrontEnd.cpp:222-229
+      flow[0] = fl[0]; flow[1] = fl[1]; flow[2] = fl[2];
+      aff[0] = aff_i[0]; aff[1] = aff_i[1];
+      std::memcpy(pose, pose_i, sizeof(pose));
+      haveOneGood = true;
+    }
+    if (haveOneGood)  // :232-239
+      for (int k = 0; k < 5; k++)
+        if (!std::isfinite((float)achieved[k]) || achieved[k] > cur[k]) achieved[k] = cur[k];
+    if (haveOneGood && achieved[0] < last_coarse_rmse[0] * reTrackThreshold) break;  // :241-243
+  }
+  if (!haveOneGood) {  // :246-252
+    flow[0] = flow[1] = flow[2] = 0;
+    aff[0] = aff_init[0]; aff[1] = aff_init[1];
+    std::memcpy(pose, pose7_tries, sizeof(pose));
+  }
+  std::memcpy(pose7_out, pose, sizeof(pose));
+  aff_out[0] = aff[0]; aff_out[1] = aff[1];
+  std::memcpy(achievedRes_out, achieved, sizeof(achieved));
+  if (flow3_out) std::memcpy(flow3_out, flow, sizeof(flow));
+  if (haveOneGood_out) *haveOneGood_out = haveOneGood ? 1 : 0;
+  if (tryIterations_out) *tryIterations_out = tries;
+  return DSLAM_OK;
 }
 
 int dslam_get_trace(dslam_ctx *c, double *rows, int max_rows, int *rows_out) {

@@ -142,6 +142,11 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
                            const float *q_sigs, const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width,
                            unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
 size_t sc_scratch_bytes(int nq);
+// ScanContext::generate on the device: moments (mean[3], cov[6]) of an n x 3 fp64 cloud; then binning + normalisation
+// with the PCA axes the host derived from them.  sig = dense fp32 [num_s * num_r], sig64 (optional) the fp64 values.
+cudaError_t launch_sc_moments(const double *pts, int n, double *out9, cudaStream_t stream);
+cudaError_t launch_sc_bin_finalize(const double *pts, int n, const double mean[3], const double v9[9], double lidar_range, int num_s, int num_r,
+                                   unsigned long long *cells, float *ringkey, float *sig, double *sig64, cudaStream_t stream);
 // exact re-score of the scan's survivors in search_sc's arithmetic -> per-query best packed (dist, GLOBAL id) key
 cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const float *sigs, const int *ids, const float *q_sigs, int nq, int n_cells,
                                    int sc_width, unsigned long long *exact_keys, unsigned long long *best, cudaStream_t stream);

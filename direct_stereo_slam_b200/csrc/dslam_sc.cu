@@ -92,6 +92,11 @@ struct dslam_scdb {
   int paircap = 0;
   int *d_pair_q = nullptr, *d_pair_row = nullptr;
   float *d_pair_diff = nullptr;
+  // descriptor generation scratch
+  double *d_pts = nullptr, *d_mom = nullptr, *d_gen_sig64 = nullptr;
+  int pts_cap = 0;
+  u64 *d_cells = nullptr;
+  float *d_gen_sig = nullptr, *d_gen_key = nullptr;
   // staging for appends
   float *h_stage = nullptr;  // pinned
   size_t h_stage_floats = 0;
@@ -218,6 +223,7 @@ int dslam_sc_destroy(dslam_scdb *db) {
   }
   cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids);
   cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best); cudaFree(db->d_gather);
+  cudaFree(db->d_pts); cudaFree(db->d_mom); cudaFree(db->d_gen_sig64); cudaFree(db->d_cells); cudaFree(db->d_gen_sig); cudaFree(db->d_gen_key);
   cudaFree(db->d_scratch); cudaFree(db->d_pair_q); cudaFree(db->d_pair_row); cudaFree(db->d_pair_diff);
   if (db->h_keys) cudaFreeHost(db->h_keys);
   if (db->h_stage) cudaFreeHost(db->h_stage);
@@ -268,6 +274,68 @@ int dslam_sc_add_sparse(dslam_scdb *db, const float *ringkey, const int *idx, co
   }
   const int id = global_id < 0 ? (db->ids.empty() ? 0 : db->ids.back() + 1) : global_id;
   return dslam_sc_add(db, 1, ringkey, db->h_stage, &id);
+}
+
+// ScanContext::generate (src/loop_closure/loop_detection/ScanContext.cpp:78-142 with align_points_PCA :19-66).
+int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar_range, float *ringkey_out, float *sig_dense_out,
+                      double *sig_dense64_out, double tfm_pca_rig[16], int append, int global_id) {
+  if (!db || !pts_xyz || n < 1 || !(lidar_range > 0)) return fail(DSLAM_EINVAL, "bad argument");
+  if (append && db->n + 1 > db->capacity) return fail(DSLAM_ENOMEM, "database capacity %d exceeded", db->capacity);
+  const int last = db->ids.empty() ? -1 : db->ids.back();
+  const int id = global_id < 0 ? last + 1 : global_id;
+  if (append && id <= last) return fail(DSLAM_EINVAL, "global ids must be strictly ascending within a shard (%d after %d)", id, last);
+  dslam_session *s = db->s;
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  if (n > db->pts_cap) {
+    cudaFree(db->d_pts);
+    db->d_pts = nullptr;
+    const int cap = n + n / 2 + 1024;
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_pts, (size_t)cap * 3 * sizeof(double)));
+    db->pts_cap = cap;
+  }
+  if (!db->d_mom) {
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_mom, 16 * sizeof(double)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_cells, (size_t)db->n_cells * sizeof(u64)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_gen_sig, (size_t)db->n_cells * sizeof(float)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_gen_sig64, (size_t)db->n_cells * sizeof(double)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_gen_key, (size_t)db->n_rings * sizeof(float)));
+  }
+  DSLAM_CUDA(cudaMemcpyAsync(db->d_pts, pts_xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  DSLAM_CUDA(launch_sc_moments(db->d_pts, n, db->d_mom, s->stream));
+  s->launches++;
+  double mom[9];
+  DSLAM_CUDA(cudaMemcpyAsync(mom, db->d_mom, sizeof(mom), cudaMemcpyDeviceToHost, s->stream));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  // the 3x3 eigen-decomposition stays on the host (like the 8x8 solve of the trackers)
+  const double cov[9] = {mom[3], mom[4], mom[5], mom[4], mom[6], mom[7], mom[5], mom[7], mom[8]};
+  double evals[3], ev[9], v9[9];
+  hm::sym_eig3(cov, evals, ev);
+  for (int j = 0; j < 3; j++)
+    for (int c = 0; c < 3; c++) v9[3 * j + c] = ev[c * 3 + j];
+  if (tfm_pca_rig) {  // :54-65
+    for (int i = 0; i < 16; i++) tfm_pca_rig[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) tfm_pca_rig[r * 4 + c] = v9[3 * r + c];
+    for (int r = 0; r < 3; r++) tfm_pca_rig[r * 4 + 3] = -(tfm_pca_rig[r * 4] * mom[0] + tfm_pca_rig[r * 4 + 1] * mom[1] + tfm_pca_rig[r * 4 + 2] * mom[2]);
+  }
+  DSLAM_CUDA(launch_sc_bin_finalize(db->d_pts, n, mom, v9, lidar_range, db->n_sectors, db->n_rings, db->d_cells, db->d_gen_key, db->d_gen_sig,
+                                    db->d_gen_sig64, s->stream));
+  s->launches += 3;
+  if (append) {  // the new descriptor goes into the database without touching the host
+    DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs + (size_t)db->n * db->n_cells, db->d_gen_sig, (size_t)db->n_cells * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    DSLAM_CUDA(cudaMemcpyAsync(db->d_keys + (size_t)db->n * db->n_rings, db->d_gen_key, (size_t)db->n_rings * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    DSLAM_CUDA(cudaMemcpyAsync(db->d_ids + db->n, &id, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  }
+  if (ringkey_out) DSLAM_CUDA(cudaMemcpyAsync(ringkey_out, db->d_gen_key, (size_t)db->n_rings * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  if (sig_dense_out) DSLAM_CUDA(cudaMemcpyAsync(sig_dense_out, db->d_gen_sig, (size_t)db->n_cells * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  if (sig_dense64_out) DSLAM_CUDA(cudaMemcpyAsync(sig_dense64_out, db->d_gen_sig64, (size_t)db->n_cells * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  if (append) {
+    db->row_of[id] = db->n;
+    db->ids.push_back(id);
+    db->n += 1;
+  }
+  return DSLAM_OK;
 }
 
 int dslam_sc_size(dslam_scdb *db, int *n_local) {

@@ -203,6 +203,54 @@ inline void aff_from_to(float exposureF, float exposureT, double aF, double bF, 
   out[1] = bT - a * bF;
 }
 
+// Symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations: eigenvalues ascending (the order Eigen's
+// SelfAdjointEigenSolver returns them in, ScanContext.cpp:42-46), eigenvectors as the COLUMNS of evecs (row-major 3x3),
+// each normalised and sign-fixed so that its largest-magnitude component is positive (Eigen's signs are an artefact of
+// its QR iteration; this library documents its own convention instead).
+inline void sym_eig3(const double Ain[9], double evals[3], double evecs[9]) {
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; i++) A[i] = Ain[i];
+  for (int sweep = 0; sweep < 64; sweep++) {
+    const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        const double apq = A[p * 3 + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) {
+          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
+          A[k * 3 + p] = c * akp - sn * akq; A[k * 3 + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+          A[p * 3 + k] = c * apk - sn * aqk; A[q * 3 + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - sn * vkq; V[k * 3 + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2 - i; j++)
+      if (A[order[j + 1] * 4] < A[order[j] * 4]) { const int tmp = order[j]; order[j] = order[j + 1]; order[j + 1] = tmp; }
+  for (int j = 0; j < 3; j++) {
+    const int src = order[j];
+    evals[j] = A[src * 3 + src];
+    const double v[3] = {V[src], V[3 + src], V[6 + src]};
+    const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    int big = 0;
+    for (int k = 1; k < 3; k++)
+      if (std::fabs(v[k]) > std::fabs(v[big])) big = k;
+    const double sgn = (v[big] < 0 ? -1.0 : 1.0) / nrm;
+    for (int k = 0; k < 3; k++) evecs[k * 3 + j] = v[k] * sgn;
+  }
+}
+
 struct CamPyramid {
   float fx[8], fy[8], cx[8], cy[8];
   void set(int levels, float fx0, float fy0, float cx0, float cy0) {

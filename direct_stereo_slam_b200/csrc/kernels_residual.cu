@@ -53,25 +53,7 @@ __device__ __forceinline__ void rs_halve(double *a, int mask, bool upper) {
 }
 
 template <>
-struct WarpRS<48> {
-  static constexpr int KEEP = 3;
-  __device__ static __forceinline__ void run(double (&a)[48], int lane) {
-    rs_halve<48>(a, 16, lane & 16);
-    rs_halve<24>(a, 8, lane & 8);
-    rs_halve<12>(a, 4, lane & 4);
-    rs_halve<6>(a, 2, lane & 2);
-#pragma unroll
-    for (int i = 0; i < 3; i++) a[i] = a[i] + shfl_xor_d(a[i], 1);
-  }
-  __device__ static __forceinline__ bool writer(int lane) { return (lane & 1) == 0; }
-  __device__ static __forceinline__ int base(int lane) {
-    return ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
-  }
-};
-
-template <>
 struct WarpRS<8> {
-  static constexpr int KEEP = 1;
   __device__ static __forceinline__ void run(double (&a)[8], int lane) {
     rs_halve<8>(a, 16, lane & 16);
     rs_halve<4>(a, 8, lane & 8);
@@ -85,7 +67,6 @@ struct WarpRS<8> {
 
 template <>
 struct WarpRS<16> {
-  static constexpr int KEEP = 1;
   __device__ static __forceinline__ void run(double (&a)[16], int lane) {
     rs_halve<16>(a, 16, lane & 16);
     rs_halve<8>(a, 8, lane & 8);

@@ -312,6 +312,115 @@ __global__ void __launch_bounds__(256) sc_rescore_pairs_kernel(const int *__rest
   if (lane == 0) diff_out[p] = diff;
 }
 
+// ---- descriptor generation (ScanContext::generate, src/loop_closure/loop_detection/ScanContext.cpp:19-142) ------
+// Stage 1 (one CTA): mean of the cloud, then the 3x3 scatter matrix of the centred points (align_points_PCA :22-41), fp64.
+// The sums are block reductions in a fixed order (deterministic; they differ from the reference's sequential sums only
+// by the order of the fp64 additions).  out[0..2] = mean, out[3..8] = cov (xx, xy, xz, yy, yz, zz).
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) sc_moments_kernel(const double *__restrict__ pts, int n, double *__restrict__ out) {
+  __shared__ double sh[32];
+  double sx = 0, sy = 0, sz = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sx += pts[3 * i];
+    sy += pts[3 * i + 1];
+    sz += pts[3 * i + 2];
+  }
+  const double mx = block_sum(sx, sh) / n, my = block_sum(sy, sh) / n, mz = block_sum(sz, sh) / n;
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = pts[3 * i] - mx, y = pts[3 * i + 1] - my, z = pts[3 * i + 2] - mz;
+    c[0] += x * x; c[1] += x * y; c[2] += x * z; c[3] += y * y; c[4] += y * z; c[5] += z * z;
+  }
+  double r[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) r[k] = block_sum(c[k], sh);
+  if (threadIdx.x == 0) {
+    out[0] = mx; out[1] = my; out[2] = mz;
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[3 + k] = r[k];
+  }
+}
+
+__device__ __forceinline__ u64 order_double(double d) {
+  const u64 b = (u64)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unorder_double(u64 k) {
+  const u64 b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct ScGenParams {
+  double mean[3];
+  double v[9];  // v[3*j + c]: component c of eigenvector j (ascending eigenvalues): x' = pm . v0 (up), y' = pm . v1, z' = pm . v2
+  double lidar_range;
+  int num_s, num_r;
+};
+
+// Stage 2: rotate into the PCA frame and take the per-cell maximum height (:98-117); cells hold order-preserving keys.
+__global__ void __launch_bounds__(256) sc_bin_kernel(const double *__restrict__ pts, int n, const __grid_constant__ ScGenParams P, u64 *__restrict__ cells) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = pts[3 * i] - P.mean[0], y = pts[3 * i + 1] - P.mean[1], z = pts[3 * i + 2] - P.mean[2];
+  const double hx = __dadd_rn(__dadd_rn(__dmul_rn(x, P.v[0]), __dmul_rn(y, P.v[1])), __dmul_rn(z, P.v[2]));
+  const double yp = __dadd_rn(__dadd_rn(__dmul_rn(x, P.v[3]), __dmul_rn(y, P.v[4])), __dmul_rn(z, P.v[5]));
+  const double zp = __dadd_rn(__dadd_rn(__dmul_rn(x, P.v[6]), __dmul_rn(y, P.v[7])), __dmul_rn(z, P.v[8]));
+  const double rho = sqrt(__dadd_rn(__dmul_rn(yp, yp), __dmul_rn(zp, zp)));
+  double theta = atan2(zp, yp);
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  while (theta < 0) theta += two_pi;
+  while (theta >= two_pi) theta -= two_pi;
+  const int si = (int)(theta / two_pi * P.num_s);
+  const int ri = (int)(rho / P.lidar_range * P.num_r);
+  if (ri >= P.num_r || si >= P.num_s) return;
+  atomicMax(cells + si * P.num_r + ri, order_double(hx));
+}
+
+// Stage 3 (one CTA): ring key = occupied sectors per ring / num_s, per-sector L2 normalisation (:119-141); dense fp32 out.
+__global__ void __launch_bounds__(256) sc_finalize_kernel(const u64 *__restrict__ cells, const __grid_constant__ ScGenParams P, float *__restrict__ ringkey,
+                                                         float *__restrict__ sig, double *__restrict__ sig64) {
+  __shared__ double norm[256];
+  const int tid = threadIdx.x, ns = P.num_s, nr = P.num_r;
+  const double empty_below = -P.lidar_range;
+  for (int sct = tid; sct < ns; sct += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < nr; r++) {  // ascending cell index inside the sector, like the reference's loop over i
+      const double h = unorder_double(cells[sct * nr + r]);
+      if (h >= empty_below) acc += h * h;
+    }
+    norm[sct] = sqrt(acc);
+  }
+  for (int r = tid; r < nr; r += blockDim.x) {
+    float cnt = 0.f;
+    for (int sct = 0; sct < ns; sct++)
+      if (unorder_double(cells[sct * nr + r]) >= empty_below) cnt++;
+    ringkey[r] = cnt / ns;
+  }
+  __syncthreads();
+  for (int i = tid; i < ns * nr; i += blockDim.x) {
+    const double h = unorder_double(cells[i]);
+    const double v = h >= empty_below ? h / norm[i / nr] : 0.0;
+    sig[i] = (float)v;
+    if (sig64) sig64[i] = v;
+  }
+}
+
+__global__ void sc_fill_cells_kernel(u64 *cells, int n, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cells[i] = order_double(v);
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -364,6 +473,27 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
                                                          q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch);
     sc_merge_kernel<<<nqc, 32, 0, stream>>>(scratch, grid, out + (size_t)q0 * kScTopK);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sc_moments(const double *pts, int n, double *out9, cudaStream_t stream) {
+  sc_moments_kernel<<<1, 1024, 0, stream>>>(pts, n, out9);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sc_bin_finalize(const double *pts, int n, const double mean[3], const double v9[9], double lidar_range, int num_s, int num_r,
+                                   unsigned long long *cells, float *ringkey, float *sig, double *sig64, cudaStream_t stream) {
+  if (num_s > 256) return cudaErrorInvalidValue;
+  ScGenParams P;
+  for (int i = 0; i < 3; i++) P.mean[i] = mean[i];
+  for (int i = 0; i < 9; i++) P.v[i] = v9[i];
+  P.lidar_range = lidar_range;
+  P.num_s = num_s;
+  P.num_r = num_r;
+  const int nc = num_s * num_r;
+  sc_fill_cells_kernel<<<(nc + 255) / 256, 256, 0, stream>>>(cells, nc, -lidar_range - 1.0);
+  if (n > 0) sc_bin_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, P, cells);
+  sc_finalize_kernel<<<1, 256, 0, stream>>>(cells, P, ringkey, sig, sig64);
   return cudaGetLastError();
 }
 

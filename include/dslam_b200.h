@@ -162,6 +162,15 @@ int dslam_lm_batch(int n_pose, dslam_ctx *const *pose_ctxs, dslam_frame *const *
                    double *aff_io, int coarsestLvl, const double minResForAbort[5], double *lastResiduals, double *flow3, int *ok,
                    int n_scale, dslam_ctx *const *scale_ctxs, dslam_frame *const *scale_frames, float *scales_io, int scale_coarsestLvl,
                    float *rmse_out);
+/* The retry loop of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:192-247): ntries pose hypotheses (the 5 motion models +
+ * 78 small rotations of :147-180), all starting from aff_init, tried in order with the evolving achievedRes as
+ * minResForAbort until achievedRes[0] < last_coarse_rmse[0] * reTrackThreshold (setting_reTrackThreshold = 1.5).
+ * Results are exactly those of the sequential loop; hypotheses are evaluated speculatively in lock-step batches
+ * (1, then 4, then the rest) and the loop is replayed on their recorded per-level residuals.  When nothing was good
+ * the outputs are (tries[0], aff_init, flow = 0) like :246-252. */
+int dslam_track_new_coarse(dslam_ctx *c, dslam_frame *f, float new_exposure, int ntries, const double *pose7_tries, const double aff_init[2],
+                           int coarsestLvl, const double last_coarse_rmse[5], double reTrackThreshold, double pose7_out[7], double aff_out[2],
+                           double achievedRes_out[5], double flow3_out[3], int *haveOneGood_out, int *tryIterations_out);
 /* per-iteration trace of the last track / optimizeScale call on this ctx (first start only for *_multi):
  * rows of 15 doubles (lvl, iteration (-1 = level start), accept, n_padded, lambda, E/n old, E/n new, inc[8]).
  * Returns the number of rows through *rows_out. */
@@ -181,6 +190,13 @@ int dslam_sc_add(dslam_scdb *db, int n, const float *ringkeys, const float *sigs
 /* append one descriptor in the reference's sparse form (SigType = vector<pair<int,double>>, ScanContext.h:24);
  * values are rounded to the database's fp32 storage format; global_id < 0 = previous id + 1 */
 int dslam_sc_add_sparse(dslam_scdb *db, const float *ringkey, const int *idx, const double *val, int nnz, int global_id);
+/* ScanContext::generate on the device (src/loop_closure/loop_detection/ScanContext.cpp:19-142): PCA alignment of the
+ * n x 3 fp64 cloud (the 3x3 eigen-decomposition runs on the host; eigenvectors are sign-normalised so that their largest
+ * component is positive), polar max-height binning, ring key, per-sector L2 normalisation.  Outputs (any may be NULL):
+ * ringkey[n_rings], dense signature as fp32 / fp64 [n_sectors*n_rings] (0 = empty cell), tfm_pca_rig row-major 4x4.
+ * append != 0 also appends the descriptor to the database (device to device) under global_id (< 0: previous + 1). */
+int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar_range, float *ringkey_out, float *sig_dense_out,
+                      double *sig_dense64_out, double tfm_pca_rig[16], int append, int global_id);
 int dslam_sc_size(dslam_scdb *db, int *n_local);
 /* brute-force exact replacement of search_ringkey's kNN: for each of nq queries the k nearest ring keys
  * (squared L2, flann::L2 arithmetic) among ids < max_id with dist < thres; ties -> lowest id.

@@ -116,6 +116,8 @@ class Oracle:
         L.orc_scale_accumulator.argtypes = [c_f, c_f, c_f, C.c_int, c_f]
         L.orc_track_newest_coarse.restype = C.c_int
         L.orc_track_newest_coarse.argtypes = [C.c_void_p, C.c_int, c_d, c_d, C.c_int, c_d, c_d, c_d]
+        L.orc_track_new_coarse.restype = C.c_int
+        L.orc_track_new_coarse.argtypes = [C.c_void_p, C.c_int, C.c_int, c_d, c_d, C.c_int, c_d, C.c_double, c_d, c_d, c_d, c_d, c_i]
         L.orc_calc_res_scale.restype = C.c_int
         L.orc_calc_res_scale.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, c_d]
         L.orc_calc_gs_scale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, c_f, c_f, c_d]
@@ -341,6 +343,17 @@ class OracleTracker:
         flow = np.empty(3, np.float64)
         ok = self.L.orc_track_newest_coarse(self.p, mode, _dp(pose7), _dp(aff), coarsest, _dp(min_res), _dp(last), _dp(flow))
         return bool(ok), pose7, aff, last, flow
+
+    def track_new_coarse(self, mode, tries7, aff_init, coarsest, last_coarse_rmse, re_track_threshold=1.5):
+        """The retry loop of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:192-252), sequential like the reference."""
+        tries7 = np.ascontiguousarray(np.atleast_2d(tries7), np.float64)
+        aff0 = np.ascontiguousarray(aff_init, np.float64)
+        last = np.ascontiguousarray(last_coarse_rmse, np.float64)
+        pose, aff, ach, flow = np.empty(7), np.empty(2), np.empty(5), np.empty(3)
+        ntry = C.c_int(0)
+        good = self.L.orc_track_new_coarse(self.p, mode, len(tries7), _dp(tries7), _dp(aff0), coarsest, _dp(last), re_track_threshold, _dp(pose),
+                                           _dp(aff), _dp(ach), _dp(flow), C.byref(ntry))
+        return dict(pose=pose, aff=aff, achievedRes=ach, flow=flow, haveOneGood=bool(good), tryIterations=ntry.value)
 
     def calc_res_scale(self, lvl, scale, cutoff=20.0):
         res = np.empty(6, np.float64)

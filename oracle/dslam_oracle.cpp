@@ -1048,6 +1048,46 @@ int orc_track_newest_coarse(void *p, int mode, double pose7_io[7], double aff_io
   for (int i = 0; i < 3; i++) flow3[i] = T.lastFlow[i];
   return ok;
 }
+// The hypothesis loop of FrontEnd::trackNewCoarse  src/FrontEnd.cpp:192-252 (restated; FrontEnd.cpp itself needs the whole
+// DSO system and cannot be compiled in place).  tries7 = ntries poses, every trial starts from aff_init.
+// Returns haveOneGood; *tries_out = tryIterations.
+int orc_track_new_coarse(void *p, int mode, int ntries, const double *tries7, const double aff_init[2], int coarsestLvl, const double last_coarse_rmse[5],
+                         double reTrackThreshold, double pose7_out[7], double aff_out[2], double achievedRes[5], double flow3[3], int *tries_out) {
+  Tracker &T = *(Tracker *)p;
+  double flowVecs[3] = {100, 100, 100};
+  SE3 lastF_2_fh = se3_identity();
+  double aff_g2l[2] = {0, 0};
+  for (int i = 0; i < 5; i++) achievedRes[i] = NAN;
+  bool haveOneGood = false;
+  int tryIterations = 0;
+  for (int i = 0; i < ntries; i++) {
+    double aff_this[2] = {aff_init[0], aff_init[1]};
+    SE3 lastF_2_fh_this = se3_from7(tries7 + 7 * i);
+    double currentRes[5];
+    const bool trackingIsGood = track_newest_coarse(T, mode, lastF_2_fh_this, aff_this, coarsestLvl, achievedRes, currentRes) != 0;
+    tryIterations++;
+    if (trackingIsGood && std::isfinite((float)currentRes[0]) && !(currentRes[0] >= achievedRes[0])) {
+      for (int k = 0; k < 3; k++) flowVecs[k] = T.lastFlow[k];
+      aff_g2l[0] = aff_this[0]; aff_g2l[1] = aff_this[1];
+      lastF_2_fh = lastF_2_fh_this;
+      haveOneGood = true;
+    }
+    if (haveOneGood)
+      for (int k = 0; k < 5; k++)
+        if (!std::isfinite((float)achievedRes[k]) || achievedRes[k] > currentRes[k]) achievedRes[k] = currentRes[k];
+    if (haveOneGood && achievedRes[0] < last_coarse_rmse[0] * reTrackThreshold) break;
+  }
+  if (!haveOneGood) {
+    flowVecs[0] = flowVecs[1] = flowVecs[2] = 0;
+    aff_g2l[0] = aff_init[0]; aff_g2l[1] = aff_init[1];
+    lastF_2_fh = se3_from7(tries7);
+  }
+  se3_to7(lastF_2_fh, pose7_out);
+  aff_out[0] = aff_g2l[0]; aff_out[1] = aff_g2l[1];
+  for (int k = 0; k < 3; k++) flow3[k] = flowVecs[k];
+  *tries_out = tryIterations;
+  return haveOneGood ? 1 : 0;
+}
 int orc_calc_res_scale(void *p, int lvl, float scale, float cutoffTH, double res6[6]) {
   Tracker &T = *(Tracker *)p;
   calc_res_scale(T, lvl, scale, cutoffTH, res6);

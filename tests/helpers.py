@@ -68,3 +68,18 @@ class GpuCase:
 def perturbed_pose(o, pose7, rng, trans=0.01, rot=0.002):
     xi = np.concatenate([rng.normal(0, trans, 3), rng.normal(0, rot, 3)])
     return o.se3_mul(o.se3_exp(xi), pose7)
+
+
+def rotation_hypotheses(o, base7, deltas=(0.02, 0.03, 0.04)):
+    """The rotation retries of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:164-180): base * SE3(Quaterniond(1, sx*d, sy*d, sz*d), 0)
+    for 26 sign patterns and a few rotation steps (the quaternion is normalised by the SE3 constructor)."""
+    signs = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (-1, 1, 0), (0, -1, 1), (-1, 0, 1),
+             (1, -1, 0), (0, 1, -1), (1, 0, -1), (-1, -1, 0), (0, -1, -1), (-1, 0, -1), (-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1),
+             (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+    out = []
+    for d in deltas:
+        for s in signs:
+            q = np.array([s[0] * d, s[1] * d, s[2] * d, 1.0])
+            q /= np.linalg.norm(q)
+            out.append(o.se3_mul(base7, np.concatenate([q, [0, 0, 0]])))
+    return np.stack(out)

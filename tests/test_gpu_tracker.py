@@ -267,3 +267,42 @@ def test_errors(session, oracle):
     assert e.value.code == EINVAL  # coarsestLvl out of range
     trk.close()
     fr.close()
+
+
+@pytest.mark.parametrize("scenario", ["first_try_wins", "needs_retries", "nothing_good", "improves_later"])
+def test_track_new_coarse_speculative_equals_sequential(session, oracle, scenario):
+    """dslam_track_new_coarse (the hypothesis loop of FrontEnd::trackNewCoarse, src/FrontEnd.cpp:192-252, evaluated
+    speculatively in lock-step batches) returns what the sequential loop returns."""
+    from helpers import rotation_hypotheses
+
+    oc = OracleCase(oracle, "tiny", 3)
+    gc = GpuCase(session, oc)
+    true = oc.case["pose7_true"]
+    off = oracle.se3_mul(oracle.se3_exp([0.0, 0, 0, 0.0, 0.09, 0.0]), true)  # 5 degrees off: fails on the fine levels
+    if scenario == "first_try_wins":
+        tries = np.concatenate([[true, IDENT7], rotation_hypotheses(oracle, true)])
+        last = np.full(5, 20.0)
+    elif scenario == "needs_retries":
+        tries = np.concatenate([[off, oracle.se3_mul(off, off)], rotation_hypotheses(oracle, off, (0.02, 0.03, 0.045)), [true]])
+        last = np.full(5, 7.0)
+    elif scenario == "nothing_good":
+        far = oracle.se3_exp([1.0e5, 0, 0, 0, 0, 0])
+        tries = np.stack([far, oracle.se3_mul(far, far), far])
+        last = np.full(5, 1.0)
+    else:
+        tries = np.concatenate([[IDENT7, off], rotation_hypotheses(oracle, off, (0.045,)), [true, true]])
+        last = np.full(5, 0.5)  # never good enough: every hypothesis is tried
+    ref = oc.trk.track_new_coarse(1, tries, (0.0, 0.0), oc.levels - 1, last)
+    l0 = session.launch_count()
+    got = gc.trk.trackNewCoarse(gc.f_new, tries, (0.0, 0.0), oc.levels - 1, last)
+    launches = session.launch_count() - l0
+    assert got["haveOneGood"] == ref["haveOneGood"] and got["tryIterations"] == ref["tryIterations"], (got, ref)
+    assert rel_err(got["pose"], ref["pose"]) < 1e-8 and np.allclose(got["aff"], ref["aff"], rtol=1e-7, atol=1e-9)
+    assert np.allclose(got["achievedRes"], ref["achievedRes"], rtol=1e-6, equal_nan=True)
+    assert np.allclose(got["flow"], ref["flow"], rtol=1e-8)
+    if scenario == "first_try_wins":
+        assert got["tryIterations"] == 1 and launches < 80  # only the first hypothesis was evaluated
+    if scenario == "improves_later":
+        assert got["tryIterations"] == len(tries)
+    print(scenario, "tries", got["tryIterations"], "of", len(tries), "launches", launches)
+    gc.close()
