@@ -126,6 +126,18 @@ class Oracle:
         L.orc_get_trace.restype = C.c_int
         L.orc_get_trace.argtypes = [C.c_void_p, c_d, C.c_int]
         L.orc_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.orc_pe_create.restype = C.c_void_p
+        L.orc_pe_create.argtypes = [C.c_int, C.c_int, C.c_int, c_f]
+        L.orc_pe_destroy.argtypes = [C.c_void_p]
+        L.orc_pe_set_points.argtypes = [C.c_void_p, C.c_int, c_d, c_f, C.c_float]
+        L.orc_pe_set_new_frame.argtypes = [C.c_void_p, c_f, C.c_float]
+        L.orc_pe_set_aff_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_pe_calc_res.restype = C.c_int
+        L.orc_pe_calc_res.argtypes = [C.c_void_p, C.c_int, C.c_int, c_d, C.c_double, C.c_double, C.c_float, c_d, c_d, c_d, c_d]
+        L.orc_pe_estimate.restype = C.c_int
+        L.orc_pe_estimate.argtypes = [C.c_void_p, C.c_int, c_d, C.c_int, c_f, c_i]
+        L.orc_pe_get_trace.restype = C.c_int
+        L.orc_pe_get_trace.argtypes = [C.c_void_p, c_d, C.c_int]
         L.orc_search_sc.argtypes = [c_i, c_d, C.c_int, c_i, c_i, c_d, c_i, C.c_int, C.c_int, c_i, c_f]
         L.orc_search_sc_dense.argtypes = [c_f, c_f, C.c_int, c_i, C.c_int, C.c_int, c_i, c_f]
         L.orc_search_ringkey.restype = C.c_int
@@ -150,6 +162,9 @@ class Oracle:
 
     def tracker(self, w, h, levels, K0, K1, T_stereo):
         return OracleTracker(self, w, h, levels, K0, K1, T_stereo)
+
+    def pose_estimator(self, w, h, levels, cam):
+        return OraclePoseEstimator(self, w, h, levels, cam)
 
     # ---- SE3 helpers ----------------------------------------------------------------------------------
     def se3_exp(self, a6):
@@ -598,3 +613,107 @@ def reference_make_images(img, levels, B256=None, path=None):
         Bp = _fp(B256)
     L.refimg_make_images(_fp(img), w, h, levels, Bp, _fp(dIp), _fp(ag))
     return dIp, ag
+
+
+class OraclePoseEstimator:
+    """dso::PoseEstimator restated (src/loop_closure/pose_estimation/PoseEstimator.cpp)."""
+
+    def __init__(self, orc, w, h, levels, cam):
+        self.L = orc.lib
+        cam = np.ascontiguousarray(cam, np.float32)
+        self.levels = levels
+        self.p = C.c_void_p(self.L.orc_pe_create(w, h, levels, _fp(cam)))
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.L.orc_pe_destroy(self.p)
+        except Exception:
+            pass
+
+    def set_points(self, pts, colors, ref_exposure=1.0):
+        """pts [n,3] float64; colors [levels, n] float32 (pair.second[lvl])."""
+        pts = np.ascontiguousarray(pts, np.float64)
+        colors = np.ascontiguousarray(colors, np.float32)
+        self.L.orc_pe_set_points(self.p, len(pts), _dp(pts), _fp(colors), ref_exposure)
+
+    def set_new_frame(self, dIp_all, exposure=1.0):
+        self._keep["new"] = dIp_all
+        self.L.orc_pe_set_new_frame(self.p, _fp(dIp_all), exposure)
+
+    def set_aff_mode(self, a, b):
+        self.L.orc_pe_set_aff_mode(self.p, a, b)
+
+    def calc_res(self, lvl, mode, T, aff=(0.0, 0.0), cutoff=20.0):
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        res, H, b, acc = np.empty(6), np.empty(64), np.empty(8), np.empty(45)
+        n = self.L.orc_pe_calc_res(self.p, lvl, mode, _dp(T), aff[0], aff[1], cutoff, _dp(res), _dp(H), _dp(b), _dp(acc))
+        return res, n, H.reshape(8, 8), b, acc
+
+    def estimate(self, mode, T, coarsest):
+        T = np.array(T, np.float64).reshape(16)
+        err = C.c_float(0)
+        inl = C.c_int(0)
+        ok = self.L.orc_pe_estimate(self.p, mode, _dp(T), coarsest, C.byref(err), C.byref(inl))
+        return bool(ok), T.reshape(4, 4), err.value, inl.value
+
+    def trace(self):
+        n = self.L.orc_pe_get_trace(self.p, None, 0)
+        out = np.zeros((n, 15), np.float64)
+        if n:
+            self.L.orc_pe_get_trace(self.p, _dp(out), n)
+        return out
+
+
+class ReferencePoseEstimator:
+    """oracle/_ref/libdslam_ref_pe.so: the reference's own PoseEstimator.cpp compiled in place (oracle/ref_build.py)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libdslam_ref_pe.so"))
+
+    def __init__(self, w, h, levels, cam):
+        L = self.L = C.CDLL(os.path.join(_HERE, "_ref", "libdslam_ref_pe.so"))
+        L.refpe_create.restype = C.c_void_p
+        L.refpe_create.argtypes = [C.c_int, C.c_int, C.c_int, c_f]
+        L.refpe_destroy.argtypes = [C.c_void_p]
+        L.refpe_set_aff_mode.argtypes = [C.c_float, C.c_float]
+        L.refpe_set_points.argtypes = [C.c_void_p, C.c_int, c_d, c_f, C.c_float]
+        L.refpe_set_new_frame.argtypes = [C.c_void_p, c_f, C.c_float]
+        L.refpe_estimate.restype = C.c_int
+        L.refpe_estimate.argtypes = [C.c_void_p, c_d, C.c_int, c_f]
+        L.refpe_calc_res.restype = C.c_int
+        L.refpe_calc_res.argtypes = [C.c_void_p, C.c_int, c_d, C.c_double, C.c_double, C.c_float, c_d, c_d, c_d]
+        cam = np.ascontiguousarray(cam, np.float32)
+        self.p = C.c_void_p(L.refpe_create(w, h, levels, _fp(cam)))
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.L.refpe_destroy(self.p)
+        except Exception:
+            pass
+
+    def set_aff_mode(self, a, b):
+        self.L.refpe_set_aff_mode(a, b)
+
+    def set_points(self, pts, colors, ref_exposure=1.0):
+        pts = np.ascontiguousarray(pts, np.float64)
+        colors = np.ascontiguousarray(colors, np.float32)
+        self.L.refpe_set_points(self.p, len(pts), _dp(pts), _fp(colors), ref_exposure)
+
+    def set_new_frame(self, dIp_all, exposure=1.0):
+        self._keep["new"] = dIp_all
+        self.L.refpe_set_new_frame(self.p, _fp(dIp_all), exposure)
+
+    def calc_res(self, lvl, T, aff=(0.0, 0.0), cutoff=20.0):
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        res, H, b = np.empty(6), np.empty(64), np.empty(8)
+        n = self.L.refpe_calc_res(self.p, lvl, _dp(T), aff[0], aff[1], cutoff, _dp(res), _dp(H), _dp(b))
+        return res, n, H.reshape(8, 8), b
+
+    def estimate(self, T, coarsest):
+        T = np.array(T, np.float64).reshape(16)
+        err = C.c_float(0)
+        ok = self.L.refpe_estimate(self.p, _dp(T), coarsest, C.byref(err))
+        return bool(ok), T.reshape(4, 4), err.value

@@ -775,6 +775,269 @@ float optimize_scale(Tracker &T, int mode, float &scale, int coarsestLvl) {
   return last_residuals[0];
 }
 
+// ------------------------------------------------------------------------------------------------
+// PoseEstimator (loop-closure photometric alignment)  src/loop_closure/pose_estimation/PoseEstimator.cpp
+// The third copy of the 8-DoF Gauss-Newton: 3-D reference points with one colour per pyramid level.
+// ------------------------------------------------------------------------------------------------
+struct PoseEst {
+  int levels = 0;
+  int w[kMaxLevels], h[kMaxLevels];
+  float fx[kMaxLevels], fy[kMaxLevels], cx[kMaxLevels], cy[kMaxLevels];
+  std::vector<double> pts;                  // n x 3 (Eigen::Vector3d first of each pair)
+  std::vector<float> colors[kMaxLevels];    // pair.second[lvl]
+  int n = 0;
+  std::vector<float> buf[8];
+  int buf_n = 0;
+  const float *dIp_new[kMaxLevels];
+  float new_exposure = 1.f, ref_exposure = 1.f;
+  double ref_a = 0, ref_b = 0;  // ref_aff_g2l_ = AffLight()  (:316)
+  int affModeA = 0, affModeB = 0;
+  int res_acc_mode = 0;
+  std::vector<TraceRec> trace;
+};
+
+// PoseEstimator::makeK  :66-83
+void pe_make_K(PoseEst &P, int w0, int h0, const float cam[4]) {
+  P.w[0] = w0; P.h[0] = h0; P.fx[0] = cam[0]; P.fy[0] = cam[1]; P.cx[0] = cam[2]; P.cy[0] = cam[3];
+  for (int l = 1; l < P.levels; l++) {
+    P.w[l] = P.w[0] >> l; P.h[l] = P.h[0] >> l;
+    P.fx[l] = P.fx[l - 1] * 0.5; P.fy[l] = P.fy[l - 1] * 0.5;
+    P.cx[l] = (P.cx[0] + 0.5) / ((int)1 << l) - 0.5;
+    P.cy[l] = (P.cy[0] + 0.5) / ((int)1 << l) - 0.5;
+  }
+}
+
+// PoseEstimator::calcRes  :141-296
+void pe_calc_res(PoseEst &P, int lvl, const SE3 &refToNew, double aff_a, double aff_b, float cutoffTH, double rs[6]) {
+  float E = 0;
+  double Ed = 0, sTd = 0, sRTd = 0;
+  int numTermsInE = 0, numTermsInWarped = 0, numSaturated = 0;
+  const int wl = P.w[lvl], hl = P.h[lvl];
+  const float *dINewl = P.dIp_new[lvl];
+  const float fxl = P.fx[lvl], fyl = P.fy[lvl], cxl = P.cx[lvl], cyl = P.cy[lvl];
+  double Rd[9]; quat_to_R(refToNew.q, Rd);
+  float R[9]; for (int i = 0; i < 9; i++) R[i] = (float)Rd[i];
+  const float t[3] = {(float)refToNew.t[0], (float)refToNew.t[1], (float)refToNew.t[2]};
+  double affd[2]; aff_from_to(P.ref_exposure, P.new_exposure, P.ref_a, P.ref_b, aff_a, aff_b, affd);
+  const float affLL[2] = {(float)affd[0], (float)affd[1]};
+  float sumSquaredShiftT = 0, sumSquaredShiftRT = 0, sumSquaredShiftNum = 0;
+  const float maxEnergy = 2 * kHuberTH * cutoffTH - kHuberTH * kHuberTH;
+  for (int b = 0; b < 8; b++) if ((int)P.buf[b].size() < P.n + 4) P.buf[b].resize(P.n + 4);
+  for (int i = 0; i < P.n; i++) {
+    const float x = (float)P.pts[3 * i], y = (float)P.pts[3 * i + 1], z = (float)P.pts[3 * i + 2];
+    const float u0 = x / z, v0 = y / z;
+    const float Ku0 = fxl * u0 + cxl, Kv0 = fyl * v0 + cyl;
+    float pt[3];
+    for (int r = 0; r < 3; r++) pt[r] = dot3f(R[r * 3], x, R[r * 3 + 1], y, R[r * 3 + 2], z) + t[r];
+    const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+    const float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+    const float new_idepth = 1 / pt[2];
+    if (lvl == 0 && i % 32 == 0) {  // :191-226
+      const float ptT[3] = {x + t[0], y + t[1], 1 + t[2]}, ptT2[3] = {x - t[0], y - t[1], 1 - t[2]};
+      float pt3[3];
+      for (int r = 0; r < 3; r++) pt3[r] = dot3f(R[r * 3], x, R[r * 3 + 1], y, R[r * 3 + 2], 1.0f) - t[r];
+      const float KuT = fxl * (ptT[0] / ptT[2]) + cxl, KvT = fyl * (ptT[1] / ptT[2]) + cyl;
+      const float KuT2 = fxl * (ptT2[0] / ptT2[2]) + cxl, KvT2 = fyl * (ptT2[1] / ptT2[2]) + cyl;
+      const float Ku3 = fxl * (pt3[0] / pt3[2]) + cxl, Kv3 = fyl * (pt3[1] / pt3[2]) + cyl;
+      const float sT1 = (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0), sT2 = (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
+      const float sRT1 = (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0), sRT2 = (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
+      sumSquaredShiftT += sT1; sumSquaredShiftT += sT2; sumSquaredShiftRT += sRT1; sumSquaredShiftRT += sRT2;
+      sTd += (double)sT1; sTd += (double)sT2; sRTd += (double)sRT1; sRTd += (double)sRT2;
+      sumSquaredShiftNum += 2;
+    }
+    if (!(Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0)) continue;
+    const float refColor = P.colors[lvl][i];
+    float hit[3]; interp33(dINewl, Ku, Kv, wl, hit);
+    if (!std::isfinite(hit[0])) continue;
+    const float residual = hit[0] - (float)(affLL[0] * refColor + affLL[1]);
+    const float hw = std::fabs(residual) < kHuberTH ? 1 : kHuberTH / std::fabs(residual);
+    if (std::fabs(residual) > cutoffTH) {
+      E += maxEnergy; Ed += (double)maxEnergy; numTermsInE++; numSaturated++;
+    } else {
+      E += hw * residual * residual * (2 - hw);
+      Ed += (double)(hw * residual * residual * (2 - hw));
+      numTermsInE++;
+      P.buf[0][numTermsInWarped] = new_idepth; P.buf[1][numTermsInWarped] = u; P.buf[2][numTermsInWarped] = v;
+      P.buf[3][numTermsInWarped] = hit[1]; P.buf[4][numTermsInWarped] = hit[2];
+      P.buf[5][numTermsInWarped] = residual; P.buf[6][numTermsInWarped] = hw; P.buf[7][numTermsInWarped] = refColor;
+      numTermsInWarped++;
+    }
+  }
+  while (numTermsInWarped % 4 != 0) {
+    for (int b = 0; b < 8; b++) P.buf[b][numTermsInWarped] = 0;
+    numTermsInWarped++;
+  }
+  P.buf_n = numTermsInWarped;
+  rs[0] = E; rs[1] = numTermsInE; rs[2] = sumSquaredShiftT / (sumSquaredShiftNum + 0.1); rs[3] = 0;
+  rs[4] = sumSquaredShiftRT / (sumSquaredShiftNum + 0.1); rs[5] = numSaturated / (float)numTermsInE;
+  if (P.res_acc_mode == 1) { rs[0] = Ed; rs[2] = sTd / (sumSquaredShiftNum + 0.1); rs[4] = sRTd / (sumSquaredShiftNum + 0.1); }
+}
+
+// PoseEstimator::calcGSSSE  :84-139  (identical to calcGSSSEPose with b0 = ref_aff_g2l_.b)
+void pe_calc_gs(PoseEst &P, int lvl, int mode, double aff_a, double aff_b, double H[64], double b[8], double *acc45_out) {
+  const float fxl = P.fx[lvl], fyl = P.fy[lvl];
+  const float b0 = (float)P.ref_b;
+  double affd[2]; aff_from_to(P.ref_exposure, P.new_exposure, P.ref_a, P.ref_b, aff_a, aff_b, affd);
+  const float a = (float)affd[0];
+  const int n = P.buf_n;
+  double acc[45];
+  if (mode == 0) {
+    static thread_local TieredAcc<9> A;
+    A.initialize();
+    for (int i = 0; i < n; i += 4) {
+      float J[9][4], w[4];
+      for (int l = 0; l < 4; l++) {
+        float Jl[8];
+        pose_jacobian(P.buf[0][i + l], P.buf[1][i + l], P.buf[2][i + l], P.buf[3][i + l], P.buf[4][i + l], P.buf[7][i + l], fxl, fyl, a, b0, Jl);
+        for (int j = 0; j < 8; j++) J[j][l] = Jl[j];
+        J[8][l] = P.buf[5][i + l];
+        w[l] = P.buf[6][i + l];
+      }
+      A.update(J, w);
+    }
+    float o[45]; A.finish(o);
+    for (int e = 0; e < 45; e++) acc[e] = o[e];
+  } else {
+    for (int e = 0; e < 45; e++) acc[e] = 0;
+    for (int i = 0; i < n; i++) {
+      float J[9];
+      pose_jacobian(P.buf[0][i], P.buf[1][i], P.buf[2][i], P.buf[3][i], P.buf[4][i], P.buf[7][i], fxl, fyl, a, b0, J);
+      J[8] = P.buf[5][i];
+      const float w = P.buf[6][i];
+      int e = 0;
+      for (int r = 0; r < 9; r++) {
+        const float Jw = J[r] * w;
+        for (int c = r; c < 9; c++, e++) acc[e] += (double)Jw * (double)J[c];
+      }
+    }
+  }
+  if (acc45_out) for (int e = 0; e < 45; e++) acc45_out[e] = acc[e];
+  const float invn = 1.0f / n;
+  double Hf[81];
+  { int e = 0; for (int r = 0; r < 9; r++) for (int c = r; c < 9; c++, e++) Hf[r * 9 + c] = Hf[c * 9 + r] = acc[e]; }
+  for (int r = 0; r < 8; r++) {
+    for (int c = 0; c < 8; c++) H[r * 8 + c] = Hf[r * 9 + c] * invn;
+    b[r] = Hf[r * 9 + 8] * invn;
+  }
+  const double sc[8] = {kScaleXiRot, kScaleXiRot, kScaleXiRot, kScaleXiTrans, kScaleXiTrans, kScaleXiTrans, kScaleA, kScaleB};
+  for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) H[r * 8 + c] *= sc[c];
+  for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) H[r * 8 + c] *= sc[r];
+  for (int r = 0; r < 8; r++) b[r] *= sc[r];
+}
+
+// SE3(Matrix3d, Vector3d) as used at :321-322 (quaternion from the rotation block) and SE3::matrix() (:463)
+SE3 se3_from_matrix4(const double *m) {
+  SE3 s;
+  double q[4];
+  const double tr = m[0] + m[5] + m[10];
+  if (tr > 0) {
+    double t = std::sqrt(tr + 1.0); q[3] = 0.5 * t; t = 0.5 / t;
+    q[0] = (m[9] - m[6]) * t; q[1] = (m[2] - m[8]) * t; q[2] = (m[4] - m[1]) * t;
+  } else {
+    int i = 0; if (m[5] > m[0]) i = 1; if (m[10] > m[i * 4 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(m[i * 4 + i] - m[j * 4 + j] - m[k * 4 + k] + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (m[k * 4 + j] - m[j * 4 + k]) * t; q[j] = (m[j * 4 + i] + m[i * 4 + j]) * t; q[k] = (m[k * 4 + i] + m[i * 4 + k]) * t;
+  }
+  std::memcpy(s.q, q, sizeof(q));
+  quat_normalize(s.q);
+  s.t[0] = m[3]; s.t[1] = m[7]; s.t[2] = m[11];
+  return s;
+}
+void se3_to_matrix4(const SE3 &s, double *m) {
+  double R[9]; quat_to_R(s.q, R);
+  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) m[r * 4 + c] = R[r * 3 + c]; m[r * 4 + 3] = s.t[r]; }
+  m[12] = m[13] = m[14] = 0; m[15] = 1;
+}
+
+// PoseEstimator::estimate  :298-506.  Returns aff_good && low_res && enough_inlier; outputs pose_error, inlier_percent.
+int pe_estimate(PoseEst &P, int mode, double T_io[16], int coarsest_lvl, float *pose_error, int *inlier_percent_out) {
+  const int maxIterations[] = {10, 20, 50, 50, 50};
+  const float lambdaExtrapolationLimit = 0.001;
+  P.res_acc_mode = mode;
+  P.trace.clear();
+  int lastInners[kMaxLevels] = {0};
+  double lastResiduals[5]; for (int i = 0; i < 5; i++) lastResiduals[i] = NAN;
+  double aff_cur[2] = {0, 0};
+  SE3 refToNew_current = se3_from_matrix4(T_io);
+  bool haveRepeated = false;
+  for (int lvl = coarsest_lvl; lvl >= 0; lvl--) {
+    double H[64], b[8];
+    float levelCutoffRepeat = 1;
+    double resOld[6];
+    pe_calc_res(P, lvl, refToNew_current, aff_cur[0], aff_cur[1], kCoarseCutoffTH * levelCutoffRepeat, resOld);
+    while (resOld[5] > 0.6 && levelCutoffRepeat < 50) {
+      levelCutoffRepeat *= 2;
+      pe_calc_res(P, lvl, refToNew_current, aff_cur[0], aff_cur[1], kCoarseCutoffTH * levelCutoffRepeat, resOld);
+    }
+    pe_calc_gs(P, lvl, mode, aff_cur[0], aff_cur[1], H, b, nullptr);
+    float lambda = 0.01;
+    { TraceRec tr{}; tr.lvl = lvl; tr.iteration = -1; tr.accept = 1; tr.n = P.buf_n; tr.lambda = lambda; tr.e_new = resOld[0] / resOld[1]; P.trace.push_back(tr); }
+    for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
+      double Hl[64]; std::memcpy(Hl, H, sizeof(Hl));
+      for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + lambda);
+      double nb[8]; for (int i = 0; i < 8; i++) nb[i] = -b[i];
+      double inc[8];
+      ldlt_solve(8, Hl, 8, nb, inc);
+      if (P.affModeA < 0 && P.affModeB < 0) { ldlt_solve(6, Hl, 8, nb, inc); inc[6] = inc[7] = 0; }
+      if (!(P.affModeA < 0) && P.affModeB < 0) { ldlt_solve(7, Hl, 8, nb, inc); inc[7] = 0; }
+      if (P.affModeA < 0 && !(P.affModeB < 0)) {
+        double Hs[64]; std::memcpy(Hs, Hl, sizeof(Hs));
+        double bs[8]; std::memcpy(bs, nb, sizeof(bs));
+        for (int i = 0; i < 8; i++) Hs[i * 8 + 6] = Hs[i * 8 + 7];
+        for (int j = 0; j < 8; j++) Hs[6 * 8 + j] = Hs[7 * 8 + j];
+        bs[6] = bs[7];
+        double is[8]; ldlt_solve(7, Hs, 8, bs, is);
+        for (int i = 0; i < 6; i++) inc[i] = is[i];
+        inc[6] = 0; inc[7] = is[6];
+      }
+      float extrapFac = 1;
+      if (lambda < lambdaExtrapolationLimit) extrapFac = std::sqrt(std::sqrt(lambdaExtrapolationLimit / lambda));
+      for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+      double incScaled[8];
+      for (int i = 0; i < 3; i++) incScaled[i] = inc[i] * kScaleXiRot;
+      for (int i = 3; i < 6; i++) incScaled[i] = inc[i] * kScaleXiTrans;
+      incScaled[6] = inc[6] * kScaleA; incScaled[7] = inc[7] * kScaleB;
+      { double s = 0; for (int i = 0; i < 8; i++) s += incScaled[i]; if (!std::isfinite(s)) for (int i = 0; i < 8; i++) incScaled[i] = 0; }
+      SE3 refToNew_new = se3_mul(se3_exp(incScaled), refToNew_current);
+      double aff_new[2] = {aff_cur[0] + incScaled[6], aff_cur[1] + incScaled[7]};
+      double resNew[6];
+      pe_calc_res(P, lvl, refToNew_new, aff_new[0], aff_new[1], kCoarseCutoffTH * levelCutoffRepeat, resNew);
+      const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
+      { TraceRec tr{}; tr.lvl = lvl; tr.iteration = iteration; tr.accept = accept; tr.n = P.buf_n; tr.lambda = lambda;
+        tr.e_old = resOld[0] / resOld[1]; tr.e_new = resNew[0] / resNew[1]; for (int i = 0; i < 8; i++) tr.inc[i] = inc[i]; P.trace.push_back(tr); }
+      if (accept) {
+        pe_calc_gs(P, lvl, mode, aff_new[0], aff_new[1], H, b, nullptr);
+        std::memcpy(resOld, resNew, sizeof(resOld));
+        aff_cur[0] = aff_new[0]; aff_cur[1] = aff_new[1];
+        refToNew_current = refToNew_new;
+        lambda *= 0.5;
+      } else {
+        lambda *= 4;
+        if (lambda < lambdaExtrapolationLimit) lambda = lambdaExtrapolationLimit;
+      }
+      double nrm = 0; for (int i = 0; i < 8; i++) nrm += inc[i] * inc[i];
+      if (!(std::sqrt(nrm) > 1e-3)) break;
+    }
+    lastResiduals[lvl] = sqrtf((float)(resOld[0] / resOld[1]));
+    lastInners[lvl] = (int)resOld[1];
+    if (levelCutoffRepeat > 1 && !haveRepeated) { lvl++; haveRepeated = true; }
+  }
+  se3_to_matrix4(refToNew_current, T_io);
+  *pose_error = (float)lastResiduals[0];
+  bool aff_good = true;
+  if ((P.affModeA != 0 && (fabsf((float)aff_cur[0]) > 1.2)) || (P.affModeB != 0 && (fabsf((float)aff_cur[1]) > 200))) aff_good = false;
+  double rel[2]; aff_from_to(P.ref_exposure, P.new_exposure, P.ref_a, P.ref_b, aff_cur[0], aff_cur[1], rel);
+  const float relA = (float)rel[0], relB = (float)rel[1];
+  if ((P.affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (P.affModeB == 0 && (fabsf(relB) > 200))) aff_good = false;
+  const bool low_res = *pose_error < 10.0;                                     // RES_THRES  PoseEstimator.h:25
+  const int inlier_percent = 100 * float(lastInners[0]) / P.n;                  // :480
+  const bool enough_inlier = inlier_percent > 90;                              // INNER_PERCENT  :26
+  *inlier_percent_out = inlier_percent;
+  return (aff_good && low_res && enough_inlier) ? 1 : 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1112,6 +1375,52 @@ int orc_get_trace(void *p, double *out, int max_rows) {
   return n;
 }
 void orc_get_counters(void *p, long out[2]) { Tracker &T = *(Tracker *)p; out[0] = T.n_res_evals; out[1] = T.n_gs_evals; }
+
+// ---- PoseEstimator -------------------------------------------------------------------------------
+void *orc_pe_create(int w, int h, int levels, const float cam[4]) {
+  PoseEst *P = new PoseEst();
+  P->levels = levels;
+  pe_make_K(*P, w, h, cam);
+  for (int l = 0; l < kMaxLevels; l++) P->dIp_new[l] = nullptr;
+  return P;
+}
+void orc_pe_destroy(void *p) { delete (PoseEst *)p; }
+// pts: n x 3 doubles; colors: levels arrays of n floats, level-major
+void orc_pe_set_points(void *p, int n, const double *pts, const float *colors, float ref_exposure) {
+  PoseEst &P = *(PoseEst *)p;
+  P.n = n;
+  P.pts.assign(pts, pts + 3 * (size_t)n);
+  for (int l = 0; l < P.levels; l++) P.colors[l].assign(colors + (size_t)l * n, colors + (size_t)(l + 1) * n);
+  P.ref_exposure = ref_exposure;
+}
+void orc_pe_set_new_frame(void *p, const float *dIp_all, float exposure) {
+  PoseEst &P = *(PoseEst *)p; int off = 0;
+  for (int l = 0; l < P.levels; l++) { P.dIp_new[l] = dIp_all + 3 * off; off += P.w[l] * P.h[l]; }
+  P.new_exposure = exposure;
+}
+void orc_pe_set_aff_mode(void *p, int a, int b) { ((PoseEst *)p)->affModeA = a; ((PoseEst *)p)->affModeB = b; }
+int orc_pe_calc_res(void *p, int lvl, int mode, const double T16[16], double aff_a, double aff_b, float cutoff, double res6[6], double H64[64], double b8[8],
+                    double acc45[45]) {
+  PoseEst &P = *(PoseEst *)p;
+  P.res_acc_mode = mode;
+  pe_calc_res(P, lvl, se3_from_matrix4(T16), aff_a, aff_b, cutoff, res6);
+  if (H64) pe_calc_gs(P, lvl, mode, aff_a, aff_b, H64, b8, acc45);
+  return P.buf_n;
+}
+int orc_pe_estimate(void *p, int mode, double T_io[16], int coarsest_lvl, float *pose_error, int *inlier_percent) {
+  return pe_estimate(*(PoseEst *)p, mode, T_io, coarsest_lvl, pose_error, inlier_percent);
+}
+int orc_pe_get_trace(void *p, double *out, int max_rows) {
+  PoseEst &P = *(PoseEst *)p;
+  const int n = (int)P.trace.size();
+  if (out)
+    for (int i = 0; i < n && i < max_rows; i++) {
+      const TraceRec &r = P.trace[i]; double *o = out + 15 * i;
+      o[0] = r.lvl; o[1] = r.iteration; o[2] = r.accept; o[3] = r.n; o[4] = r.lambda; o[5] = r.e_old; o[6] = r.e_new;
+      for (int k = 0; k < 8; k++) o[7 + k] = r.inc[k];
+    }
+  return n;
+}
 
 // ---- Scan Context --------------------------------------------------------------------------------
 // search_sc  src/loop_closure/loop_detection/search_place.h:59-85 on sparse index-sorted signatures.

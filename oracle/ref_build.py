@@ -61,6 +61,13 @@ def main():
         cmd_opt[-1] = os.path.join(OUT, "libdslam_ref_tracker_opt.so")
         subprocess.run(cmd_opt, check=True)
         print("built", cmd_opt[-1])
+        # ---- PoseEstimator.cpp as a whole (loop-closure alignment) -------------------------------------
+        cmd = ["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-w",
+               "-I", os.path.join(HERE, "shim"), "-I", tmp, "-I", os.path.join(tmp, "dso", "src"), "-I", os.path.join(REF, "src"),
+               "-I", os.path.join(REF, "src", "loop_closure", "pose_estimation"),
+               os.path.join(HERE, "ref_driver_pe.cpp"), "-o", os.path.join(OUT, "libdslam_ref_pe.so")]
+        subprocess.run(cmd, check=True)
+        print("built", os.path.join(OUT, "libdslam_ref_pe.so"))
     return 0
 
 

@@ -59,6 +59,29 @@ class SE3 {
     normalize();
     t_[0] = T(0, 3); t_[1] = T(1, 3); t_[2] = T(2, 3);
   }
+  // SE3(rotation matrix, translation) — both may be matrices or block views
+  template <class RotT, class TransT>
+  SE3(const RotT &R, const TransT &t) {
+    Eigen::Matrix4d T;
+    T.setZero();
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) T(r, c) = R(r, c);
+      T(r, 3) = t[r];
+    }
+    T(3, 3) = 1;
+    *this = SE3(T);
+  }
+  Eigen::Matrix4d matrix() const {
+    Eigen::Matrix4d T;
+    T.setZero();
+    const Mat33 R = rotationMatrix();
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) T(r, c) = R(r, c);
+      T(r, 3) = t_[r];
+    }
+    T(3, 3) = 1;
+    return T;
+  }
   static SE3 from7(const double *p) {
     SE3 s;
     std::memcpy(s.q_, p, 32);

@@ -83,3 +83,31 @@ def rotation_hypotheses(o, base7, deltas=(0.02, 0.03, 0.04)):
             q /= np.linalg.norm(q)
             out.append(o.se3_mul(base7, np.concatenate([q, [0, 0, 0]])))
     return np.stack(out)
+
+
+def loop_closure_points(oc, n=1500, seed=0):
+    """Reference points of a loop-closure alignment (LoopHandler::publishKeyframes, src/loop_closure/LoopHandler.cpp:166-178):
+    3-D points of the keyframe in its camera frame + their colour on every pyramid level."""
+    c = oc.case
+    cfg = oc.cfg
+    rng = np.random.default_rng(seed)
+    sel = rng.choice(len(c["pu"]), min(n, len(c["pu"])), replace=False)
+    u, v = c["pu"][sel].astype(np.float64), c["pv"][sel].astype(np.float64)
+    z = 1.0 / c["pid"][sel].astype(np.float64) * c["scale_error"]
+    pts = np.stack([(u - cfg["cx"]) / cfg["fx"] * z, (v - cfg["cy"]) / cfg["fy"] * z, z], 1)
+    off = orc.level_offsets(oc.w, oc.h, oc.levels)
+    colors = np.zeros((oc.levels, len(sel)), np.float32)
+    for l in range(oc.levels):
+        wl, hl = oc.w >> l, oc.h >> l
+        I = oc.dIp_ref[off[l]:off[l + 1], 0].reshape(hl, wl)
+        ul = np.clip(((u + 0.5) / (1 << l) - 0.5).round().astype(int), 0, wl - 1)
+        vl = np.clip(((v + 0.5) / (1 << l) - 0.5).round().astype(int), 0, hl - 1)
+        colors[l] = I[vl, ul]
+    return pts, colors
+
+
+def mat4_from_pose7(o, p7):
+    T = np.eye(4)
+    T[:3, :3] = o.se3_R(p7)
+    T[:3, 3] = p7[4:]
+    return T
