@@ -73,6 +73,13 @@ SIGNATURES = {
     "dslam_optimize_scale_batch": [C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
     "dslam_track_new_coarse": [vp, vp, C.c_float, C.c_int, c_d, c_d, C.c_int, c_d, C.c_double, c_d, c_d, c_d, c_d, c_i, c_i],
     "dslam_lm_batch": [C.c_int, c_pp, c_pp, c_f, c_d, c_d, C.c_int, c_d, c_d, c_d, c_i, C.c_int, c_pp, c_pp, c_f, C.c_int, c_f],
+    "dslam_pe_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],
+    "dslam_pe_destroy": [vp],
+    "dslam_pe_set_affine_mode": [vp, C.c_int, C.c_int],
+    "dslam_pe_set_points": [vp, C.c_int, c_d, c_f, C.c_float],
+    "dslam_pe_eval": [vp, vp, C.c_float, c_f, C.c_int, c_d, c_d, C.c_float, c_d, c_d, c_d, c_i, c_d],
+    "dslam_pe_estimate": [vp, vp, C.c_float, c_f, C.c_int, c_d, c_f, c_i, c_i],
+    "dslam_pe_get_trace": [vp, c_d, C.c_int, c_i],
     "dslam_get_trace": [vp, c_d, C.c_int, c_i],
     "dslam_ctx_counters": [vp, C.POINTER(C.c_longlong)],
     "dslam_sc_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],

@@ -406,6 +406,76 @@ class TrackerAndScaler:
         return dict(evals=out[0], launches=out[1], iterations=out[2])
 
 
+class PoseEstimator:
+    """dso::PoseEstimator (src/loop_closure/pose_estimation/PoseEstimator.h:34-49) on the GPU: direct alignment of a
+    loop-closure candidate (LoopHandler.cpp:274-277)."""
+
+    def __init__(self, session, w, h, levels=None):
+        self.s = session
+        self.lib = session.lib
+        self.w, self.h = w, h
+        self.levels = pyr_levels_used(w, h) if levels is None else levels
+        p = C.c_void_p()
+        check(self.lib.dslam_pe_create(session.p, w, h, self.levels, C.byref(p)))
+        self.p = p
+        self.inlier_percent = 0
+
+    def close(self):
+        if self.p:
+            self.lib.dslam_pe_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setAffineOptMode(self, modeA, modeB):
+        check(self.lib.dslam_pe_set_affine_mode(self.p, modeA, modeB))
+
+    def setPoints(self, pts, colors, ref_ab_exposure):
+        """pts [n,3] float64 (pair.first), colors [n, levels] float32 (pair.second[lvl])."""
+        pts = np.ascontiguousarray(pts, np.float64)
+        colors = np.ascontiguousarray(colors, np.float32)
+        if pts.ndim != 2 or pts.shape[1] != 3 or colors.shape != (len(pts), self.levels):
+            raise ValueError("pts must be [n,3] and colors [n,levels]")
+        check(self.lib.dslam_pe_set_points(self.p, len(pts), _dp(pts), _fp(colors), ref_ab_exposure))
+
+    def calcResAndGS(self, new_fh, new_cam, lvl, ref_to_new, aff=(0.0, 0.0), cutoffTH=20.0):
+        cam = np.ascontiguousarray(new_cam, np.float32)
+        T = np.ascontiguousarray(np.asarray(ref_to_new, np.float64).reshape(16))
+        aff = np.ascontiguousarray(aff, np.float64)
+        H, b, res, acc = np.empty((8, 8)), np.empty(8), np.empty(6), np.empty(48)
+        n = np.empty(1, np.int32)
+        check(self.lib.dslam_pe_eval(self.p, new_fh.p, new_fh.ab_exposure, _fp(cam), lvl, _dp(T), _dp(aff), cutoffTH, _dp(H), _dp(b), _dp(res),
+                                     _ip(n), _dp(acc)))
+        return dict(H=H, b=b, res6=res, n=int(n[0]), acc48=acc)
+
+    def estimate(self, pts, ref_ab_exposure, new_fh, new_cam, coarsest_lvl, ref_to_new):
+        """bool estimate(pts, ref_ab_exposure, new_fh, new_cam, coarsest_lvl, ref_to_new&, pose_error&) (:298-304).
+        pts = (xyz [n,3], colors [n,levels]) or None to reuse the last setPoints.  Returns (ok, ref_to_new 4x4, pose_error)."""
+        if pts is not None:
+            self.setPoints(pts[0], pts[1], ref_ab_exposure)
+        cam = np.ascontiguousarray(new_cam, np.float32)
+        T = np.array(ref_to_new, np.float64).reshape(16)
+        err = C.c_float(0)
+        inl = C.c_int(0)
+        ok = C.c_int(0)
+        check(self.lib.dslam_pe_estimate(self.p, new_fh.p, new_fh.ab_exposure, _fp(cam), coarsest_lvl, _dp(T), C.byref(err), C.byref(inl),
+                                         C.byref(ok)))
+        self.inlier_percent = inl.value
+        return bool(ok.value), T.reshape(4, 4), err.value
+
+    def trace(self):
+        n = C.c_int(0)
+        check(self.lib.dslam_pe_get_trace(self.p, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 15))
+        if n.value:
+            check(self.lib.dslam_pe_get_trace(self.p, _dp(out), n.value, C.byref(n)))
+        return out
+
+
 class ScanContextDB:
     """Scan-Context descriptor database; replaces search_ringkey / search_sc (search_place.h:25-85)."""
 

@@ -15,6 +15,7 @@
 #include <new>
 
 #include "dslam_internal.h"
+#include <limits>
 
 namespace dslam {
 
@@ -237,7 +238,12 @@ void fill_pose_item(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, floa
   hm::qmatrix(refToNew.q, Rd);
   float Rf[9];
   for (int k = 0; k < 9; k++) Rf[k] = (float)Rd[k];
-  hm::mat33f_mul(Rf, c->Ki[lvl], it.M);
+  if (c->point3d) {  // PoseEstimator::calcRes :160-161: R and t as floats, no K^-1 (the records are 3-D points)
+    for (int k = 0; k < 9; k++) it.M[k] = Rf[k];
+    it.flags |= 4;
+  } else {
+    hm::mat33f_mul(Rf, c->Ki[lvl], it.M);
+  }
   for (int k = 0; k < 3; k++) it.t[k] = (float)refToNew.t[k];
   double affd[2];
   hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], affd);
@@ -322,6 +328,7 @@ struct PoseLM {
     int lvl;
     double residual;
     double flow[3];
+    int numTermsInE;  // (int)resOld[1]: lastInners[lvl] of PoseEstimator::estimate :455
   };
   std::vector<LevelEvent> events;
 
@@ -437,7 +444,7 @@ struct PoseLM {
   void finish_level() {
     lastResiduals[lvl] = sqrtf((float)(resOld.res6[0] / resOld.res6[1]));  // :595
     flow[0] = resOld.res6[2]; flow[1] = resOld.res6[3]; flow[2] = resOld.res6[4];
-    events.push_back(LevelEvent{lvl, lastResiduals[lvl], {flow[0], flow[1], flow[2]}});
+    events.push_back(LevelEvent{lvl, lastResiduals[lvl], {flow[0], flow[1], flow[2]}, (int)resOld.res6[1]});
     if (lastResiduals[lvl] > 1.5 * minResForAbort[lvl]) {  // :597-598
       ok = false;
       phase = DONE;
@@ -1623,6 +1630,157 @@ int dslam_track_new_coarse(dslam_ctx *c, dslam_frame *f, float new_exposure, int
   if (haveOneGood_out) *haveOneGood_out = haveOneGood ? 1 : 0;
   if (tryIterations_out) *tryIterations_out = tries;
   return DSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dso::PoseEstimator  src/loop_closure/pose_estimation/PoseEstimator.cpp  (loop-closure direct alignment)
+// ---------------------------------------------------------------------------------------------------
+int dslam_pe_create(dslam_session *s, int w, int h, int levels, dslam_pe **out) {
+  if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
+  *out = nullptr;
+  if (w < 8 || h < 8 || levels < 1 || levels > DSLAM_MAX_LEVELS) return fail(DSLAM_EINVAL, "bad geometry");
+  dslam_pe *p = new (std::nothrow) dslam_pe();
+  if (!p) return fail(DSLAM_ENOMEM, "out of host memory");
+  dslam_ctx &c = p->ctx;
+  c.s = s;
+  c.levels = levels;
+  c.point3d = true;
+  for (int l = 0; l < levels; l++) {  // PoseEstimator::PoseEstimator :36-52
+    c.w[l] = w >> l;
+    c.h[l] = h >> l;
+  }
+  *out = p;
+  return DSLAM_OK;
+}
+
+int dslam_pe_destroy(dslam_pe *p) {
+  if (!p) return DSLAM_OK;
+  cudaSetDevice(p->ctx.s->device);
+  cudaStreamSynchronize(p->ctx.s->stream);
+  cudaFree(p->block);
+  cudaFreeHost(p->stage);
+  delete p;
+  return DSLAM_OK;
+}
+
+int dslam_pe_set_affine_mode(dslam_pe *p, int modeA, int modeB) {
+  if (!p) return fail(DSLAM_EINVAL, "null estimator");
+  p->ctx.affModeA = modeA;
+  p->ctx.affModeB = modeB;
+  return DSLAM_OK;
+}
+
+// pts_ = pts; ref_ab_exposure_ = ref_ab_exposure; ref_aff_g2l_ = AffLight()  :307-317
+int dslam_pe_set_points(dslam_pe *p, int n, const double *pts_xyz, const float *colors, float ref_ab_exposure) {
+  if (!p || !pts_xyz || !colors) return fail(DSLAM_EINVAL, "null argument");
+  if (n < 1) return fail(DSLAM_EINVAL, "no points");
+  dslam_ctx &c = p->ctx;
+  dslam_session *s = c.s;
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  const int levels = c.levels;
+  if (n > p->cap) {
+    DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(p->block);
+    cudaFreeHost(p->stage);
+    p->block = nullptr;
+    p->stage = nullptr;
+    p->cap = 0;
+    const int cap = (n + 1023) & ~1023;
+    DSLAM_CUDA(cudaMalloc((void **)&p->block, (size_t)levels * cap * sizeof(float4)));
+    DSLAM_CUDA(cudaHostAlloc((void **)&p->stage, (size_t)levels * cap * sizeof(float4), cudaHostAllocDefault));
+    p->cap = cap;
+  } else {
+    DSLAM_CUDA(cudaStreamSynchronize(s->stream));  // the staging buffer may still feed the previous upload
+  }
+  for (int l = 0; l < levels; l++) {
+    float4 *dst = p->stage + (size_t)l * n;
+    for (int i = 0; i < n; i++)  // :168-171  the point as floats, pts_[i].second[lvl]
+      dst[i] = make_float4((float)pts_xyz[3 * (size_t)i], (float)pts_xyz[3 * (size_t)i + 1], (float)pts_xyz[3 * (size_t)i + 2],
+                           colors[(size_t)i * levels + l]);
+    c.pts[l] = p->block + (size_t)l * n;
+    c.pc_n[l] = n;
+  }
+  DSLAM_CUDA(cudaMemcpyAsync(p->block, p->stage, (size_t)levels * n * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+  c.ref_exposure = ref_ab_exposure;
+  c.ref_a = c.ref_b = 0;
+  c.have_ref = true;
+  return DSLAM_OK;
+}
+
+static int pe_prepare(dslam_pe *p, dslam_frame *f, const float new_cam[4], int lvl) {
+  if (!p || !new_cam) return fail(DSLAM_EINVAL, "null argument");
+  p->ctx.cam0.set(p->ctx.levels, new_cam[0], new_cam[1], new_cam[2], new_cam[3]);  // makeK(new_cam) :66-83
+  return check_ctx_frame(&p->ctx, f, lvl);
+}
+
+int dslam_pe_eval(dslam_pe *p, dslam_frame *new_fh, float new_exposure, const float new_cam[4], int lvl, const double T_ref_to_new[16],
+                  const double aff_ab[2], float cutoffTH, double *H64, double *b8, double *res6, int *n_padded, double *acc48) {
+  int rc = pe_prepare(p, new_fh, new_cam, 0);
+  if (rc != DSLAM_OK) return rc;
+  if (!T_ref_to_new || !aff_ab) return fail(DSLAM_EINVAL, "null argument");
+  hm::Se3 T;
+  T.q = hm::qfrom_matrix(T_ref_to_new, 4);
+  T.t[0] = T_ref_to_new[3]; T.t[1] = T_ref_to_new[7]; T.t[2] = T_ref_to_new[11];
+  double p7[7];
+  T.to7(p7);
+  return dslam_pose_eval(&p->ctx, new_fh, new_exposure, lvl, 1, p7, aff_ab, cutoffTH, H64, b8, res6, n_padded, acc48);
+}
+
+int dslam_pe_estimate(dslam_pe *p, dslam_frame *new_fh, float new_exposure, const float new_cam[4], int coarsest_lvl, double ref_to_new_io[16],
+                      float *pose_error, int *inlier_percent, int *ok) {
+  int rc = pe_prepare(p, new_fh, new_cam, coarsest_lvl);
+  if (rc != DSLAM_OK) return rc;
+  if (!ref_to_new_io || !pose_error || !ok) return fail(DSLAM_EINVAL, "null argument");
+  dslam_ctx *c = &p->ctx;
+  c->trace.clear();
+  // SE3(ref_to_new.block<3,3>(0,0), ref_to_new.block<3,1>(0,3))  :321-322
+  hm::Se3 T;
+  T.q = hm::qfrom_matrix(ref_to_new_io, 4);
+  T.t[0] = ref_to_new_io[3]; T.t[1] = ref_to_new_io[7]; T.t[2] = ref_to_new_io[11];
+  double p7[7];
+  T.to7(p7);
+  const double aff0[2] = {0, 0};  // aff_g2l_current = AffLight()  :319
+  const double inf = std::numeric_limits<double>::infinity();
+  const double no_abort[5] = {inf, inf, inf, inf, inf};  // estimate() has no minResForAbort test
+  std::vector<PoseLM> lms(1);
+  std::vector<ScaleLM> none;
+  lms[0].begin(c, new_fh, new_exposure, p7, aff0, coarsest_lvl, no_abort, &c->trace);
+  rc = run_lock_step(c->s, lms, none, c);
+  if (rc != DSLAM_OK) return rc;
+  PoseLM &m = lms[0];
+  c->n_iters += m.iters;
+  // ref_to_new = refToNew_current.matrix()  :463
+  double R[9];
+  hm::qmatrix(m.cur.q, R);
+  for (int r = 0; r < 3; r++) {
+    for (int k = 0; k < 3; k++) ref_to_new_io[r * 4 + k] = R[r * 3 + k];
+    ref_to_new_io[r * 4 + 3] = m.cur.t[r];
+  }
+  ref_to_new_io[12] = ref_to_new_io[13] = ref_to_new_io[14] = 0;
+  ref_to_new_io[15] = 1;
+  *pose_error = (float)m.lastResiduals[0];  // :464
+  // :466-478 affine sanity, the same test as the tracker's epilogue
+  bool aff_good = true;
+  const double *aff = m.aff_cur;
+  if ((c->affModeA != 0 && (fabsf((float)aff[0]) > 1.2)) || (c->affModeB != 0 && (fabsf((float)aff[1]) > 200))) aff_good = false;
+  double rel[2];
+  hm::aff_from_to(c->ref_exposure, new_exposure, c->ref_a, c->ref_b, aff[0], aff[1], rel);
+  const float relA = (float)rel[0], relB = (float)rel[1];
+  if ((c->affModeA == 0 && (fabsf(logf(relA)) > 1.5)) || (c->affModeB == 0 && (fabsf(relB) > 200))) aff_good = false;
+  int lastInners0 = 0;
+  for (const PoseLM::LevelEvent &e : m.events)
+    if (e.lvl == 0) lastInners0 = e.numTermsInE;
+  const bool low_res = *pose_error < 10.0;                                  // RES_THRES  PoseEstimator.h:25
+  const int percent = 100 * float(lastInners0) / c->pc_n[0];                // :480
+  const bool enough_inlier = percent > 90;                                  // INNER_PERCENT  PoseEstimator.h:26
+  if (inlier_percent) *inlier_percent = percent;
+  *ok = (aff_good && low_res && enough_inlier) ? 1 : 0;
+  return DSLAM_OK;
+}
+
+int dslam_pe_get_trace(dslam_pe *p, double *rows, int max_rows, int *rows_out) {
+  if (!p) return fail(DSLAM_EINVAL, "null estimator");
+  return dslam_get_trace(&p->ctx, rows, max_rows, rows_out);
 }
 
 int dslam_get_trace(dslam_ctx *c, double *rows, int max_rows, int *rows_out) {

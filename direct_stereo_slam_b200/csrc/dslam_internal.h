@@ -111,6 +111,7 @@ struct dslam_ctx {
   float4 *pts_stage = nullptr;  // pinned host staging for uploads, level l at px_off[l]
   size_t px_off[dslam::kMaxLevels + 1]{};
   bool have_ref = false;
+  bool point3d = false;  // PoseEstimator flavour: pts[lvl] hold (x, y, z, color[lvl]) of the matched keyframe's points
   float ref_exposure = 1.f;
   double ref_a = 0, ref_b = 0;
   int affModeA = 0, affModeB = 0;
@@ -121,4 +122,12 @@ struct dslam_ctx {
   int pt_stage_cap = 0;
   std::vector<double> trace;  // rows of 15 doubles
   long long n_evals = 0, n_launches = 0, n_iters = 0;
+};
+
+// dso::PoseEstimator (src/loop_closure/pose_estimation/PoseEstimator.h): the 8-DoF machinery of dslam_ctx over 3-D points
+struct dslam_pe {
+  dslam_ctx ctx;
+  int cap = 0;              // points per level the device / staging buffers hold
+  float4 *block = nullptr;  // levels * cap records
+  float4 *stage = nullptr;  // pinned
 };

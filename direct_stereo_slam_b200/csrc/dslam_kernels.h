@@ -20,12 +20,12 @@ constexpr int kScaleVals = 8;            // JwJ, Jwr, rwr, E, shiftT, shiftRT, 0
 // One evaluation of calcRes*+calcGSSSE* = one work item. Lives in kernel-parameter (constant) space.
 struct alignas(16) EvalItem {
   const float4 *tex;  // level texels (I, dx, dy, absgrad) of the frame sampled
-  const float4 *pts;  // template records (u, v, idepth, color)
+  const float4 *pts;  // template records (u, v, idepth, color); 3-D point records (x, y, z, color[lvl]) when flags bit2
   int n;              // pc_n[lvl]
   int w, h;           // level size
-  int flags;          // bit0: accumulate flow indicators (lvl == 0)
+  int flags;          // bit0: accumulate flow indicators (lvl == 0); bit1: scale item; bit2: PoseEstimator 3-D point item
   float fx, fy, cx, cy;  // intrinsics of the camera sampled (cam0 for pose, cam1 for scale)
-  float M[9];         // pose: R*Ki ; scale: R_f1_f0*Ki
+  float M[9];         // pose: R*Ki ; scale: R_f1_f0*Ki ; 3-D point item: R
   float t[3];         // pose: translation ; scale: t_f1_f0
   float Ki[9];        // K^-1 of the level (flow indicators)
   float p0, p1, p2;   // pose: affLL a, affLL b, b0 ; scale: scale, unused, unused

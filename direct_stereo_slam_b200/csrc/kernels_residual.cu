@@ -82,6 +82,7 @@ struct WarpRS<16> {
 
 // Eigen 3.3 coefficient product of three terms: e0 + (e1 + e2), third factor is the literal 1.
 __device__ __forceinline__ float dot3_xy1(float m0, float m1, float m2, float x, float y) { return m0 * x + (m1 * y + m2); }
+__device__ __forceinline__ float dot3_xyz(float m0, float m1, float m2, float x, float y, float z) { return m0 * x + (m1 * y + m2 * z); }
 
 // getInterpolatedElement33 on float4 texels; .w of the texel (absSquaredGrad) is ignored.
 __device__ __forceinline__ float3 interp33(const float4 *__restrict__ tex, float x, float y, int width) {
@@ -288,6 +289,7 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
   const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
   const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
   const int g = lane >> 2, k = lane & 3;
+  const bool point3d = (it.flags & 4) != 0;  // PoseEstimator flavour: records are 3-D points of the matched keyframe
 
   double c0 = 0.0, c1 = 0.0;  // H(g, 2k), H(g, 2k+1)
   double ext[16];             // [0..7] b, [8] sum w r^2, [9] E, [10] shiftT, [11] shiftRT
@@ -304,16 +306,19 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
 #pragma unroll
     for (int c = 0; c < 8; c++) J[c] = Jw[c] = 0.f;
     if (i < n) {
-      const float x = p.x, y = p.y, id = p.z, refColor = p.w;
-      // :747  pt = RKi * (x,y,1) + t*id
-      const float pt0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) + it.t[0] * id;
-      const float pt1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) + it.t[1] * id;
-      const float pt2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) + it.t[2] * id;
+      const float x = p.x, y = p.y, refColor = p.w;
+      // template point : record (u, v, idepth, color)  :747  pt = RKi * (x,y,1) + t*id ; new_idepth = id / pt[2]
+      // 3-D point      : record (x, y, z, color)       PoseEstimator.cpp:172-181  pt = R * (x,y,z) + t ; new_idepth = 1 / pt[2]
+      // One expression serves both: multiplying by the literal 1 is exact, so zz = 1 / idm = 1 reproduce either form bit for bit.
+      const float zz = point3d ? p.z : 1.0f, idm = point3d ? 1.0f : p.z;
+      const float pt0 = dot3_xyz(it.M[0], it.M[1], it.M[2], x, y, zz) + it.t[0] * idm;
+      const float pt1 = dot3_xyz(it.M[3], it.M[4], it.M[5], x, y, zz) + it.t[1] * idm;
+      const float pt2 = dot3_xyz(it.M[6], it.M[7], it.M[8], x, y, zz) + it.t[2] * idm;
       const float u = pt0 / pt2;
       const float v = pt1 / pt2;
       const float Ku = fxl * u + cxl;
       const float Kv = fyl * v + cyl;
-      const float new_idepth = id / pt2;
+      const float new_idepth = idm / pt2;
       if (Ku > 2 && Kv > 2 && Ku < wlm3 && Kv < hlm3 && new_idepth > 0) {
         const float3 hit = interp33(tex, Ku, Kv, wl);
         if (isfinite(hit.x)) {
@@ -365,7 +370,34 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
   }
 
   // Flow indicators (:754-784): every 32nd template point of level 0, whether or not it projects into the image.
-  if (it.flags & 1) {
+  if ((it.flags & 1) && point3d) {
+    // PoseEstimator.cpp:191-226: same four probes, but on the raw (x, y) of the 3-D point with z replaced by 1 and
+    // measured against the projection (Ku0, Kv0) of the untransformed point.
+    const int nflow = (n + 31) >> 5;
+    for (int kf = blockIdx.x * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
+      const float4 p = __ldg(pts + 32 * kf);
+      const float x = p.x, y = p.y, z = p.z;
+      const float Ku0 = fxl * (x / z) + cxl, Kv0 = fyl * (y / z) + cyl;
+      const float pt0 = dot3_xyz(it.M[0], it.M[1], it.M[2], x, y, z) + it.t[0];
+      const float pt1 = dot3_xyz(it.M[3], it.M[4], it.M[5], x, y, z) + it.t[1];
+      const float pt2 = dot3_xyz(it.M[6], it.M[7], it.M[8], x, y, z) + it.t[2];
+      const float Ku = fxl * (pt0 / pt2) + cxl, Kv = fyl * (pt1 / pt2) + cyl;
+      const float ptTz = 1.0f + it.t[2], ptT2z = 1.0f - it.t[2];
+      const float pt3z = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) - it.t[2];
+      const float KuT = fxl * ((x + it.t[0]) / ptTz) + cxl, KvT = fyl * ((y + it.t[1]) / ptTz) + cyl;
+      const float KuT2 = fxl * ((x - it.t[0]) / ptT2z) + cxl, KvT2 = fyl * ((y - it.t[1]) / ptT2z) + cyl;
+      const float Ku3 = fxl * ((dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) - it.t[0]) / pt3z) + cxl;
+      const float Kv3 = fyl * ((dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) - it.t[1]) / pt3z) + cyl;
+      const float sT1 = (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0);
+      const float sT2 = (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
+      const float sRT1 = (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0);
+      const float sRT2 = (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
+      ext[10] += (double)sT1;
+      ext[10] += (double)sT2;
+      ext[11] += (double)sRT1;
+      ext[11] += (double)sRT2;
+    }
+  } else if (it.flags & 1) {
     const int nflow = (n + 31) >> 5;
     for (int kf = blockIdx.x * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
       const float4 p = __ldg(pts + 32 * kf);

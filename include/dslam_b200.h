@@ -178,6 +178,28 @@ int dslam_get_trace(dslam_ctx *c, double *rows, int max_rows, int *rows_out);
 /* counters since creation: [0] residual/Jacobian evaluations (items), [1] kernel launches, [2] LM iterations */
 int dslam_ctx_counters(dslam_ctx *c, long long out[3]);
 
+/* ---- PoseEstimator: the direct alignment of a loop-closure candidate -------------------------------
+ * src/loop_closure/pose_estimation/PoseEstimator.h:34-49, PoseEstimator.cpp:36-506 (call site
+ * src/loop_closure/LoopHandler.cpp:274-277).  The same 8-DoF Gauss-Newton as the tracker, over the matched keyframe's
+ * 3-D points (camera frame) with one stored colour per pyramid level; no abort test; the return value of estimate()
+ * is aff_good && pose_error < RES_THRES(10) && inlier_percent > INNER_PERCENT(90). */
+typedef struct dslam_pe dslam_pe;
+int dslam_pe_create(dslam_session *s, int w, int h, int levels, dslam_pe **out);
+int dslam_pe_destroy(dslam_pe *p);
+/* setting_affineOptModeA / B (deps:dso/src/util/settings.cpp:83-84), as dslam_ctx_set_affine_mode */
+int dslam_pe_set_affine_mode(dslam_pe *p, int modeA, int modeB);
+/* pts (first argument of estimate): pts_xyz[n*3] = pair.first, colors[n*levels] = pair.second[0..levels) per point;
+ * ref_ab_exposure = matched_frame->ab_exposure */
+int dslam_pe_set_points(dslam_pe *p, int n, const double *pts_xyz, const float *colors, float ref_ab_exposure);
+/* one calcRes + calcGSSSE (:84-296) at T_ref_to_new (row-major 4x4) / aff_ab on level lvl; outputs as dslam_pose_eval */
+int dslam_pe_eval(dslam_pe *p, dslam_frame *new_fh, float new_exposure, const float new_cam[4], int lvl, const double T_ref_to_new[16],
+                  const double aff_ab[2], float cutoffTH, double *H64, double *b8, double *res6, int *n_padded, double *acc48);
+/* PoseEstimator::estimate :298-506 on the points of dslam_pe_set_points.  new_cam = (fx, fy, cx, cy) of level 0 of the
+ * new frame; ref_to_new_io = row-major Matrix4d, updated in place; *ok = estimate()'s return value. */
+int dslam_pe_estimate(dslam_pe *p, dslam_frame *new_fh, float new_exposure, const float new_cam[4], int coarsest_lvl,
+                      double ref_to_new_io[16], float *pose_error, int *inlier_percent, int *ok);
+int dslam_pe_get_trace(dslam_pe *p, double *rows, int max_rows, int *rows_out);
+
 /* ---- Scan-Context database: replaces search_ringkey / search_sc ------------------------------------
  * src/loop_closure/loop_detection/search_place.h:25-57, 59-85 (call sites src/loop_closure/LoopHandler.cpp:247,
  * 256).  Descriptors: ring key = n_rings floats; signature = dense n_sectors*n_rings floats, cell index =
