@@ -78,6 +78,18 @@ class FramePyramids {
     if (it == live_.end()) throw std::runtime_error("FrameHessian has no device pyramid (makeImages not called)");
     return it->second;
   }
+  // Device pyramid of a frame whose twin may already have been released (a keyframe the LoopHandler thread kept after the
+  // front end marginalised it): rebuilt from the intensity channel of the host mirror fh->dIp[0] when it is gone.
+  dslam_frame *ensure(FrameHessian *fh) {
+    auto it = live_.find(fh);
+    if (it != live_.end()) return it->second;
+    dslam_frame *f = acquire(fh);
+    std::vector<float> color((size_t)w_ * h_);
+    const float *src = reinterpret_cast<const float *>(fh->dIp[0]);
+    for (size_t i = 0; i < color.size(); i++) color[i] = src[3 * i];
+    check(dslam_frame_make_images(f, color.data(), nullptr, nullptr, nullptr), "dslam_frame_make_images");
+    return f;
+  }
 
  private:
   dslam_frame *acquire(FrameHessian *fh) {
@@ -213,6 +225,49 @@ class TrackerAndScaler {
   FramePyramids<FrameHessian> &frames_;
   dslam_ctx *c_ = nullptr;
   int pc_n_[DSLAM_MAX_LEVELS] = {0};
+};
+
+// dso::PoseEstimator (src/loop_closure/pose_estimation/PoseEstimator.h:34-49) with the member surface LoopHandler uses
+// (src/loop_closure/LoopHandler.cpp:41, 274-277).  Vector3d: `operator[]`; Matrix4d: `operator()(row, col)`.
+template <class FrameHessian>
+class PoseEstimator {
+ public:
+  PoseEstimator(Session &s, FramePyramids<FrameHessian> &frames, int w, int h, int levels) : frames_(frames), levels_(levels) {
+    check(dslam_pe_create(s.get(), w, h, levels, &p_), "dslam_pe_create");
+  }
+  ~PoseEstimator() { dslam_pe_destroy(p_); }
+  PoseEstimator(const PoseEstimator &) = delete;
+  PoseEstimator &operator=(const PoseEstimator &) = delete;
+  void setAffineOptMode(int modeA, int modeB) { check(dslam_pe_set_affine_mode(p_, modeA, modeB), "dslam_pe_set_affine_mode"); }
+
+  template <class Vector3d, class Matrix4d>
+  bool estimate(const std::vector<std::pair<Vector3d, float *>> &pts, float ref_ab_exposure, FrameHessian *new_fh, const std::vector<float> &new_cam,
+                int coarsest_lvl, Matrix4d &ref_to_new, float &pose_error) {
+    xyz_.resize(3 * pts.size());
+    colors_.resize((size_t)levels_ * pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+      for (int k = 0; k < 3; k++) xyz_[3 * i + k] = pts[i].first[k];
+      for (int l = 0; l < levels_; l++) colors_[i * levels_ + l] = pts[i].second[l];
+    }
+    check(dslam_pe_set_points(p_, (int)pts.size(), xyz_.data(), colors_.data(), ref_ab_exposure), "dslam_pe_set_points");
+    double T[16];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) T[r * 4 + c] = ref_to_new(r, c);
+    int ok = 0;
+    check(dslam_pe_estimate(p_, frames_.ensure(new_fh), new_fh->ab_exposure, new_cam.data(), coarsest_lvl, T, &pose_error, &inlier_percent, &ok),
+          "dslam_pe_estimate");
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) ref_to_new(r, c) = T[r * 4 + c];
+    return ok != 0;
+  }
+  int inlier_percent = 0;  // 100 * lastInners[0] / pts.size() of the last call (:480)
+
+ private:
+  FramePyramids<FrameHessian> &frames_;
+  int levels_;
+  dslam_pe *p_ = nullptr;
+  std::vector<double> xyz_;
+  std::vector<float> colors_;
 };
 
 // search_ringkey + search_sc of src/loop_closure/loop_detection/search_place.h behind one database object.

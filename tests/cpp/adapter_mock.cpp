@@ -16,6 +16,11 @@ struct SE3 {  // Sophus::SE3d::data(): quaternion (x,y,z,w) + translation
 };
 struct Vec5 { double v[5]; double &operator[](int i) { return v[i]; } const double &operator[](int i) const { return v[i]; } };
 struct Vec3 { double v[3]; double &operator[](int i) { return v[i]; } };
+struct Vec3d { double v[3]; double operator[](int i) const { return v[i]; } };
+struct Mat44 {  // Eigen::Matrix4d (column-major storage, (row, col) access)
+  double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double &operator()(int r, int c) { return m[c * 4 + r]; }
+};
 struct FrameShell { int id = 0; };
 struct FrameHessian {
   Vector3f *dIp[6] = {nullptr};
@@ -81,10 +86,29 @@ int main() {
   const bool ok = tracker.trackNewestCoarse(&fh[1], pose, aff, levels - 1, minres, last);
   float scale = 1.f;
   const float rmse = tracker.optimizeScale(&fh[2], scale, levels - 1);
+  // loop-closure alignment of the keyframe's 3-D points (LoopHandler.cpp:166-178, 274-277) against the same new frame,
+  // whose device pyramid was released and is rebuilt from the host mirror
+  frames.release(&fh[1]);
+  dslam_b200::PoseEstimator<mock::FrameHessian> pose_estimator(session, frames, w, h, levels);
+  std::vector<std::pair<mock::Vec3d, float *>> pts_dso;
+  std::vector<std::vector<float>> colors;
+  for (size_t i = 0; i < pts.u.size(); i++) {
+    const double z = 10.0;
+    colors.emplace_back(levels);
+    for (int l = 0; l < levels; l++) {
+      const int ul = (int)((pts.u[i] + 0.5) / (1 << l) - 0.5 + 0.5), vl = (int)((pts.v[i] + 0.5) / (1 << l) - 0.5 + 0.5);
+      colors.back()[l] = fh[0].dIp[l][ul + vl * (w >> l)].v[0];
+    }
+    pts_dso.push_back({mock::Vec3d{{(pts.u[i] - calib.cx) / calib.fx * z, (pts.v[i] - calib.cy) / calib.fy * z, z}}, colors.back().data()});
+  }
+  mock::Mat44 ref_to_new;
+  float pose_error = 0;
+  const bool pe_ok = pose_estimator.estimate(pts_dso, 1.f, &fh[1], {calib.fx, calib.fy, calib.cx, calib.cy}, levels - 1, ref_to_new, pose_error);
+  std::printf("adapter_mock: pe_ok=%d pe_tx=%.4f (expect about -0.1) pose_error=%.3f inliers=%d%%\n", (int)pe_ok, ref_to_new(0, 3), pose_error,
+              pose_estimator.inlier_percent);
   // a 2 px shift of a plane at 10 m with f = 200 is a translation of -0.1 m (the scene moved +x, so the camera moved -x)
   std::printf("adapter_mock: ok=%d tx=%.4f (expect about -0.1) rmse0=%.3f scale=%.3f (expect about 1) scale_rmse=%.3f pc_n0=%d\n", (int)ok,
               pose.data()[4], last[0], scale, rmse, tracker.pc_n()[0]);
-  const bool pass = ok && std::fabs(pose.data()[4] + 0.1) < 0.01 && std::fabs(scale - 1.f) < 0.05f;
-  frames.release(&fh[1]);
+  const bool pass = ok && std::fabs(pose.data()[4] + 0.1) < 0.01 && std::fabs(scale - 1.f) < 0.05f && std::fabs(ref_to_new(0, 3) + 0.1) < 0.01;
   return pass ? 0 : 1;
 }
