@@ -96,6 +96,7 @@ SIGNATURES = {
     "dslam_sc_unique_id": [C.POINTER(C.c_ubyte)],
     "dslam_sc_comm_init": [vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int],
     "dslam_sc_last_scan_ms": [vp, c_f],
+    "dslam_sc_set_scan_kernel": [C.c_int],
 }
 
 _lib = None

@@ -142,6 +142,8 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
                            const float *q_sigs, const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width,
                            unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
 size_t sc_scratch_bytes(int nq);
+// scan kernel selection: 0 = by batch size (default; DSLAM_SC_SCAN=stream|tile overrides), 1 = streaming, 2 = tiled
+void sc_set_scan_flavour(int flavour);
 // ScanContext::generate on the device: moments (mean[3], cov[6]) of an n x 3 fp64 cloud; then binning + normalisation
 // with the PCA axes the host derived from them.  sig = dense fp32 [num_s * num_r], sig64 (optional) the fp64 values.
 cudaError_t launch_sc_moments(const double *pts, int n, double *out9, cudaStream_t stream);

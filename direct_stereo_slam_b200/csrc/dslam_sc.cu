@@ -524,4 +524,10 @@ int dslam_sc_last_scan_ms(dslam_scdb *db, float *ms) {
   return DSLAM_OK;
 }
 
+int dslam_sc_set_scan_kernel(int flavour) {
+  if (flavour < 0 || flavour > 2) return fail(DSLAM_EINVAL, "scan kernel flavour must be 0 (auto), 1 (stream) or 2 (tile)");
+  sc_set_scan_flavour(flavour);
+  return DSLAM_OK;
+}
+
 }  // extern "C"

@@ -18,6 +18,8 @@
 // argmin with ties going to the lowest id — the same key a multi-GPU all-reduce(min) combines.
 
 #include "dslam_kernels.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace dslam {
 
@@ -247,6 +249,188 @@ __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__re
   }
 }
 
+// ---- sector-cosine scan, batched flavour (query batches > 8): register-blocked tiles fed by TMA ----------------
+// With a batch of queries the scan is a tall-skinny product D[rows x 32] = DB[rows x n_cells] * Q^T: 16 flop per DB
+// byte at 32 queries, which is ABOVE the fp32 ridge of the machine (~72 TFLOP/s / 6.5 TB/s = 11 flop/B), so the
+// batched scan is bound by the FFMA pipe, not by HBM, and the streaming kernel above (one LDS.128 per 8 FFMA, a
+// 5-step shuffle reduction per row and query) leaves it 5x short of that.  Here a CTA owns a tile of 256 DB rows:
+// a producer warp streams [256 rows x 32 cells] boxes of the DB (TMA, 128-byte swizzle) and the matching
+// [32 queries x 32 cells] box of the query batch through a 4-stage mbarrier pipeline; each of the 8 consumer warps
+// owns 128 rows x 8 queries, a lane 4 rows x 8 queries = 32 accumulators.  Per 4 cells a lane issues 4 LDS.128 of
+// its rows (conflict-free through the swizzle) + 8 broadcast LDS.128 of the queries for 128 FFMA: 0.19 shared-memory
+// wavefronts per FFMA (the SM sustains 0.25) and no shuffles.  The finished tile goes through shared memory once
+// ([row][query], padded) so that thread (query = tid % 32, row group = tid / 32) feeds its running top-K — the same
+// packed keys and the same merge as the streaming kernel.  fp32 CUDA-core FFMA on purpose (no TF32 tensor cores):
+// the approximate ranking must keep the true winner inside the top-K that the exact re-score sees.
+constexpr int kTileRows = 256;   // DB rows per tile
+constexpr int kTileK = 32;       // cells per pipeline stage (128 B per row: one swizzle atom)
+constexpr int kTileStages = 4;
+constexpr int kTileConsumers = 256;
+constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
+constexpr int kDistStride = 36;  // floats per row of the distance tile (conflict-free STS.128 / LDS.32)
+constexpr int kStageABytes = kTileRows * kTileK * 4;  // 32 KB
+constexpr int kStageBBytes = kQChunk * kTileK * 4;    // 4 KB
+constexpr size_t kTileSmemBytes = 1024 /*alignment slack*/ + (size_t)kTileStages * (kStageABytes + kStageBBytes) +
+                                  (size_t)kTileRows * kDistStride * 4 + 2 * kTileStages * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t sc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sc_mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sc_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sc_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool sc_mbar_try_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(sc_smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void sc_mbar_wait(uint64_t *bar, uint32_t phase) {
+  while (!sc_mbar_try_wait(bar, phase)) {
+  }
+}
+__device__ __forceinline__ void sc_tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   sc_smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(sc_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sc_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); }
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+    sc_scan_tile_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_q, const float *__restrict__ keys,
+                        const int *__restrict__ ids, int n_rows, int n_cells, int key_dim, const float *__restrict__ q_keys, int nqc,
+                        float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-B alignment
+  float *sA = reinterpret_cast<float *>(base);
+  float *sB = reinterpret_cast<float *>(base + (size_t)kTileStages * kStageABytes);
+  float *sD = reinterpret_cast<float *>(base + (size_t)kTileStages * (kStageABytes + kStageBBytes));
+  uint64_t *full = reinterpret_cast<uint64_t *>(sD + kTileRows * kDistStride);
+  uint64_t *empty = full + kTileStages;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  const int n_chunks = (n_cells + kTileK - 1) / kTileK;
+  if (tid == 0) {
+    for (int s = 0; s < kTileStages; s++) {
+      sc_mbar_init(&full[s], 1);
+      sc_mbar_init(&empty[s], kTileConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTileConsumers / 32) {
+    // ---- producer warp: one lane walks (tile, chunk) and keeps kTileStages boxes in flight ----
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int c = 0; c < n_chunks; c++, it++) {
+          const int s = it % kTileStages;
+          sc_mbar_wait(&empty[s], ((it / kTileStages) & 1) ^ 1);  // passes immediately on the first lap
+          sc_mbar_expect_tx(&full[s], kStageABytes + kStageBBytes);
+          sc_tma_load_2d(reinterpret_cast<unsigned char *>(sA) + (size_t)s * kStageABytes, &map_db, c * kTileK, t * kTileRows, &full[s]);
+          sc_tma_load_2d(reinterpret_cast<unsigned char *>(sB) + (size_t)s * kStageBBytes, &map_q, c * kTileK, 0, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int qt = warp & 3, rh = warp >> 2;  // 8 queries x 128 rows per warp
+  const int q_own = lane, sub = warp;       // top-K ownership: query q_own, rows sub*32 .. sub*32+31 of every tile
+  const int sw = lane & 7;                  // 128-B swizzle: 16-B chunk index ^ (row & 7); row & 7 == lane & 7 for all 4 rows of a lane
+  TopK top;
+  top.init();
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+    for (int c = 0; c < n_chunks; c++, it++) {
+      const int s = it % kTileStages;
+      sc_mbar_wait(&full[s], (it / kTileStages) & 1);
+      const float4 *A = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sA) + (size_t)s * kStageABytes) +
+                        (size_t)(rh * 128 + lane) * (kTileK / 4);
+      const float4 *B = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sB) + (size_t)s * kStageBBytes) +
+                        (size_t)(qt * 8) * (kTileK / 4);
+#pragma unroll
+      for (int k4 = 0; k4 < kTileK / 4; k4++) {
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = A[(size_t)i * 32 * (kTileK / 4) + (k4 ^ sw)];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 b = B[j * (kTileK / 4) + k4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+            acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+            acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+            acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) sc_mbar_arrive(&empty[s]);
+    }
+    // distances of the tile -> shared [row][query]
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) d[j] = (1.0f - acc[i][j] / sc_width) / 2.0f;
+      float4 *dst = reinterpret_cast<float4 *>(sD + (size_t)(rh * 128 + i * 32 + lane) * kDistStride + qt * 8);
+      dst[0] = make_float4(d[0], d[1], d[2], d[3]);
+      dst[1] = make_float4(d[4], d[5], d[6], d[7]);
+    }
+    sc_consumer_sync();
+    if (q_own < nqc) {
+      const int row0 = t * kTileRows + sub * 32;
+#pragma unroll 4
+      for (int r = 0; r < 32; r++) {
+        const int row = row0 + r;
+        if (row >= n_rows) break;
+        bool ok = __ldg(ids + row) < max_id;
+        if (ok && ringkey_thres >= 0.f) ok = flann_l2(q_keys + (size_t)q_own * key_dim, keys + (size_t)row * key_dim, key_dim) < ringkey_thres;
+        if (ok) top.insert(make_key(sD[(size_t)(sub * 32 + r) * kDistStride + q_own], row));
+      }
+    }
+    sc_consumer_sync();
+  }
+  // CTA merge through the distance tile's storage: lists[sub][q][K]
+  u64 *lists = reinterpret_cast<u64 *>(sD);
+#pragma unroll
+  for (int i = 0; i < kScTopK; i++) lists[((size_t)sub * kQChunk + q_own) * kScTopK + i] = top.k[i];
+  sc_consumer_sync();
+  if (tid < nqc) {
+    TopK m;
+    m.init();
+    for (int wv = 0; wv < kTileConsumers / 32; wv++) {
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + tid) * kScTopK + i]);
+    }
+    u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+  }
+}
+
 // ---- exact re-score -------------------------------------------------------------------------------------------
 // search_sc's arithmetic (search_place.h:71-79) on dense descriptors: float cur_prod += double(q)*double(d) over the
 // cells where both are occupied, in ascending cell order; diff = (1 - cur_prod / sc_width) / 2.0.  The chain of
@@ -452,6 +636,67 @@ cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int
   return cudaGetLastError();
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*ScEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ScEncodeTiledFn sc_encode_tiled() {
+  static ScEncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (ScEncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 0 = choose by batch size, 1 = always the streaming kernel, 2 = always the tiled kernel (tests / sweeps)
+static int g_sc_scan_flavour = -1;
+static int sc_scan_flavour() {
+  if (g_sc_scan_flavour < 0) {
+    const char *e = getenv("DSLAM_SC_SCAN");
+    g_sc_scan_flavour = 0;
+    if (e && !strcmp(e, "stream")) g_sc_scan_flavour = 1;
+    if (e && !strcmp(e, "tile")) g_sc_scan_flavour = 2;
+  }
+  return g_sc_scan_flavour;
+}
+void sc_set_scan_flavour(int f) { g_sc_scan_flavour = f; }
+
+static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
+                                        const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
+                                        int grid, cudaStream_t stream) {
+  ScEncodeTiledFn enc = sc_encode_tiled();
+  if (!enc) return cudaErrorNotSupported;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sc_scan_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap map_db, map_q;
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint64_t gstride[1] = {(cuuint64_t)n_cells * sizeof(float)};
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)n_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kTileRows};
+    if (enc(&map_db, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sigs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)nqc};
+    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kQChunk};
+    if (enc(&map_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(q_sigs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  sc_scan_tile_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(map_db, map_q, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
+                                                                      max_id, sc_width, scratch);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                            const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *out,
                            unsigned long long *scratch, cudaStream_t stream) {
@@ -463,14 +708,26 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = num_sms();
+  const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
   for (int q0 = 0; q0 < nq; q0 += kQChunk) {
     const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
-    size_t smem = (size_t)nqc * n_cells * 4 + (size_t)nqc * key_dim * 4;
-    const size_t lists_bytes = (size_t)kScanWarps * kQChunk * kScTopK * sizeof(u64);
-    if (smem < lists_bytes) smem = lists_bytes;
-    sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
-                                                         q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch);
+    // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
+    // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
+    const int flavour = sc_scan_flavour();
+    const bool tiles = n_rows > 0 && (flavour == 2 || (flavour == 0 && nqc > 8 && n_tiles * 2 >= num_sms()));
+    int grid = num_sms();
+    if (tiles) {
+      if (grid > n_tiles) grid = n_tiles;
+      cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
+                                           ringkey_thres, max_id, sc_width, scratch, grid, stream);
+      if (e != cudaSuccess) return e;
+    } else {
+      size_t smem = (size_t)nqc * n_cells * 4 + (size_t)nqc * key_dim * 4;
+      const size_t lists_bytes = (size_t)kScanWarps * kQChunk * kScTopK * sizeof(u64);
+      if (smem < lists_bytes) smem = lists_bytes;
+      sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
+                                                           q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch);
+    }
     sc_merge_kernel<<<nqc, 32, 0, stream>>>(scratch, grid, out + (size_t)q0 * kScTopK);
   }
   return cudaGetLastError();

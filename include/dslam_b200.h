@@ -248,6 +248,11 @@ int dslam_sc_unique_id(unsigned char id128[128]);
 int dslam_sc_comm_init(dslam_scdb *db, const unsigned char id128[128], int world_size, int rank);
 /* device time of the last dslam_sc_query scan kernel(s) in ms (CUDA events on the session stream) */
 int dslam_sc_last_scan_ms(dslam_scdb *db, float *ms);
+/* Tuning / test knob (process-wide): which scan kernel dslam_sc_query uses.  0 = chosen per query batch (default: the
+ * HBM-streaming kernel for batches of <= 8 queries or small shards, the register-blocked TMA tile kernel above that;
+ * the environment variable DSLAM_SC_SCAN=stream|tile sets the initial value), 1 = always streaming, 2 = always tiled.
+ * Both produce the same top-K survivors up to fp32 summation order; the final (index, distance) is re-scored exactly. */
+int dslam_sc_set_scan_kernel(int flavour);
 
 #ifdef __cplusplus
 }

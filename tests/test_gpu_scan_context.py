@@ -40,7 +40,27 @@ def test_query_argmin_bit_exact(small_db, oracle, nq):
     assert np.array_equal(idx[known], truth[known])  # perturbed revisits find their row
 
 
-def test_query_max_id_and_ringkey_gate(small_db, oracle):
+@pytest.fixture(params=["stream", "tile"])
+def scan_kernel(request, small_db):
+    """Force one of the two scan kernels (dslam_sc_set_scan_kernel) for the test, then restore the automatic choice."""
+    small_db[0].set_scan_kernel(request.param)
+    yield request.param
+    small_db[0].set_scan_kernel("auto")
+
+
+@pytest.mark.parametrize("nq", [1, 7, 32, 33, 70])
+def test_both_scan_kernels_bit_exact(small_db, oracle, scan_kernel, nq):
+    """The HBM-streaming kernel and the register-blocked TMA tile kernel feed the same exact re-score: identical answers
+    on a database whose row count (3000) is not a multiple of the 256-row tile and for ragged query batches."""
+    db, sig, key = small_db
+    qs, qk, truth = syn.make_sc_queries(sig, key, nq, 300 + nq)
+    idx, diff = db.query(qs)
+    idx_o, diff_o = _oracle_query(oracle, qs, sig)
+    assert np.array_equal(idx, idx_o)
+    assert np.array_equal(diff.view(np.uint32), diff_o.view(np.uint32))
+
+
+def test_query_max_id_and_ringkey_gate(small_db, oracle, scan_kernel):
     db, sig, key = small_db
     qs, qk, truth = syn.make_sc_queries(sig, key, 16, 5)
     # only ids < max_id compete (the LOOP_MARGIN delay of search_ringkey, search_place.h:42-56)
@@ -177,6 +197,14 @@ def test_full_size_database_properties(session):
     idx1 = np.array([db.query(qs[i:i + 1])[0][0] for i in range(0, 64, 9)])
     assert np.array_equal(idx1, idx64[::9])
     assert 0.0 < db.last_scan_ms() < 1000.0
+    # both scan kernels agree bit for bit on the final (index, distance) at full size
+    out = {}
+    for flavour in ("stream", "tile"):
+        db.set_scan_kernel(flavour)
+        out[flavour] = db.query(qs)
+    db.set_scan_kernel("auto")
+    assert np.array_equal(out["stream"][0], out["tile"][0]) and np.array_equal(out["stream"][1].view(np.uint32), out["tile"][1].view(np.uint32))
+    assert np.array_equal(out["tile"][0], idx64)
     db.close()
 
 
