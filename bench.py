@@ -142,6 +142,12 @@ class GpuStreams:
         self.trk, self.f_new, self.f_right, self.case_of = [], [], [], []
         self.h_new, self.h_right = [], []
         ref = api.FrameHessian(session, self.w, self.h, self.levels)
+        # pinned host images live in capture arenas: the left images of a step (and the right images of its keyframes) lie
+        # back to back, so dslam_frame_upload_batch moves them in one host-to-device transfer each
+        arena_new = session.pinned((2, n_streams, self.h, self.w))
+        arena_right = session.pinned((n_streams, self.h, self.w))
+        order = sorted(range(n_streams), key=lambda i: (i % kf_every, i))  # the keyframes of a step share i % kf_every
+        slot_right = {i: k for k, i in enumerate(order)}
         for i in range(n_streams):
             c = cases[i % len(cases)]
             self.case_of.append(c)
@@ -152,10 +158,10 @@ class GpuStreams:
             fn = [api.FrameHessian(session, self.w, self.h, self.levels) for _ in range(2)]
             fr = api.FrameHessian(session, self.w, self.h, self.levels)
             # pinned host copies of the inputs (e2e) and pinned host mirrors of the left pyramid
-            hn = [session.pinned((self.h, self.w)) for _ in range(2)]
+            hn = [arena_new[0, i], arena_new[1, i]]
             hn[0][:] = c["img_new"]
             hn[1][:] = c["img_new2"]
-            hr = session.pinned((self.h, self.w))
+            hr = arena_right[slot_right[i]]
             hr[:] = c["img_right"]
             for f in fn:
                 f.alloc_host(pinned=True)
@@ -187,9 +193,9 @@ class GpuStreams:
         if e2e:
             for i in range(self.n):
                 left[i].wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
-                left[i].upload(self.h_new[i][v])
-            for i in kf:
-                self.f_right[i].upload(self.h_right[i])
+            api.upload_frames(left, [self.h_new[i][v] for i in range(self.n)])
+            if kf:
+                api.upload_frames(right, [self.h_right[i] for i in kf])
         api.build_frames(left, stage_host=3 if e2e else 0)   # two launches for all left pyramids
         if right:
             api.build_frames(right)

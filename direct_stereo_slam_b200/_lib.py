@@ -49,6 +49,7 @@ SIGNATURES = {
     "dslam_frame_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],
     "dslam_frame_destroy": [vp],
     "dslam_frame_upload": [vp, c_f],
+    "dslam_frame_upload_batch": [C.c_int, c_pp, c_pp],
     "dslam_frame_build": [vp, c_f],
     "dslam_frame_build_batch": [C.c_int, c_pp, c_f, C.c_int],
     "dslam_frame_download": [vp, c_fpp, c_fpp],

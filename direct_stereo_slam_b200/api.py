@@ -678,6 +678,18 @@ def lm_batch(pose_trackers, pose_frames, poses, affs, coarsestLvl, scale_tracker
     return ok[:n].astype(bool), poses, affs, last, rmse[:m], scales
 
 
+def upload_frames(frames, images):
+    """Raw images of n frames (dslam_frame_upload_batch): images that lie back to back in host memory go up as one transfer."""
+    n = len(frames)
+    images = [np.ascontiguousarray(im, np.float32) for im in images]
+    for f, im in zip(frames, images):
+        assert im.size == f.w * f.h
+        f._keep = (im, None)
+    fa = (C.c_void_p * n)(*[f.p for f in frames])
+    ia = (C.c_void_p * n)(*[im.ctypes.data for im in images])
+    check(frames[0].lib.dslam_frame_upload_batch(n, fa, ia))
+
+
 def build_frames(frames, B256=None, stage_host=0):
     """Pyramids of all (uploaded) frames in two kernel launches (dslam_frame_build_batch)."""
     n = len(frames)

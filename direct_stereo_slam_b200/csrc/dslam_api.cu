@@ -772,7 +772,7 @@ int dslam_session_create(int device, dslam_session **out) {
     int ranks = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
     int g = (int)(std::thread::hardware_concurrency() / (unsigned)ranks);
-    g = g > dslam_session::kLmGroups ? dslam_session::kLmGroups : (g < 1 ? 1 : g);
+    g = g > dslam_session::kLmGroupsDefault ? dslam_session::kLmGroupsDefault : (g < 1 ? 1 : g);
     s->lm_groups = g;
   }
   if (const char *e = getenv("DSLAM_LM_GROUPS")) {
@@ -1017,10 +1017,66 @@ int dslam_frame_destroy(dslam_frame *f) {
 int dslam_frame_upload(dslam_frame *f, const float *color) {
   if (!f || !color) return fail(DSLAM_EINVAL, "null argument");
   const PyramidLevels &L = f->L;
-  DSLAM_CUDA(cudaMemcpy2DAsync(L.plane[0], (size_t)L.pitch[0] * sizeof(float), color, (size_t)f->w * sizeof(float), (size_t)f->w * sizeof(float),
-                               f->h, cudaMemcpyHostToDevice, f->s->stream));
+  if (L.pitch[0] == f->w)  // dense plane: a plain 1-D copy
+    DSLAM_CUDA(cudaMemcpyAsync(L.plane[0], color, (size_t)f->w * f->h * sizeof(float), cudaMemcpyHostToDevice, f->s->stream));
+  else
+    DSLAM_CUDA(cudaMemcpy2DAsync(L.plane[0], (size_t)L.pitch[0] * sizeof(float), color, (size_t)f->w * sizeof(float), (size_t)f->w * sizeof(float),
+                                 f->h, cudaMemcpyHostToDevice, f->s->stream));
   f->uploaded = true;
   f->built = false;
+  return DSLAM_OK;
+}
+
+static bool same_geometry(const dslam_frame *a, const dslam_frame *b);
+
+// The images of a step in as few DMA transfers as possible: runs of images that are contiguous in host memory (a capture
+// ring / pinned arena, image i+1 directly behind image i) travel as ONE host-to-device copy into a session arena and are
+// dealt to the frames' level-0 planes by one small kernel per 64 frames.  PCIe moves large transfers markedly better than
+// many 1.8 MB ones when the opposite direction is busy with the host mirrors (tools/pcie_bw.py).
+int dslam_frame_upload_batch(int n, dslam_frame *const *frames, const float *const *colors) {
+  if (n < 1 || !frames || !colors) return fail(DSLAM_EINVAL, "bad argument");
+  for (int i = 0; i < n; i++) {
+    if (!frames[i] || !colors[i]) return fail(DSLAM_EINVAL, "null frame or image");
+    if (frames[i]->s != frames[0]->s) return fail(DSLAM_EINVAL, "all frames of a batch must live in one session");
+  }
+  dslam_session *s = frames[0]->s;
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  int i = 0;
+  while (i < n) {
+    dslam_frame *f0 = frames[i];
+    const size_t px = (size_t)f0->w * f0->h;
+    int j = i + 1;
+    const bool dense = f0->L.pitch[0] == f0->w && px % 4 == 0 && ((uintptr_t)colors[i] & 15) == 0;
+    while (dense && j < n && j - i < kMaxFramesPerLaunch * 8 && same_geometry(frames[j], f0) && colors[j] == colors[j - 1] + px) j++;
+    const int run = j - i;
+    if (run < 2) {
+      const int rc = dslam_frame_upload(f0, colors[i]);
+      if (rc != DSLAM_OK) return rc;
+      i = j;
+      continue;
+    }
+    if (s->upload_arena_floats < px * run) {
+      // the arena may still feed a scatter kernel queued earlier: the free is stream-ordered
+      if (s->upload_arena) DSLAM_CUDA(cudaFreeAsync(s->upload_arena, s->stream));
+      s->upload_arena = nullptr;
+      s->upload_arena_floats = 0;
+      DSLAM_CUDA(cudaMallocAsync((void **)&s->upload_arena, px * run * sizeof(float), s->stream));
+      s->upload_arena_floats = px * run;
+    }
+    DSLAM_CUDA(cudaMemcpyAsync(s->upload_arena, colors[i], px * run * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    for (int b = 0; b < run; b += kMaxFramesPerLaunch) {
+      const int cnt = run - b < kMaxFramesPerLaunch ? run - b : kMaxFramesPerLaunch;
+      PlaneBatch B;
+      for (int k = 0; k < cnt; k++) B.plane[k] = frames[i + b + k]->L.plane[0];
+      DSLAM_CUDA(launch_scatter_planes(B, cnt, (int)(px / 4), s->upload_arena + (size_t)b * px, s->stream));
+      s->launches++;
+    }
+    for (int k = i; k < j; k++) {
+      frames[k]->uploaded = true;
+      frames[k]->built = false;
+    }
+    i = j;
+  }
   return DSLAM_OK;
 }
 
@@ -1031,7 +1087,8 @@ static int frame_ensure_staging(dslam_frame *f, bool want_dIp, bool want_abs) {
   return DSLAM_OK;
 }
 
-static bool same_geometry(const dslam_frame *a, const dslam_frame *b) { return a->w == b->w && a->h == b->h && a->levels == b->levels; }
+static bool same_geometry(const dslam_frame *a, const dslam_frame *b) {
+  return a->w == b->w && a->h == b->h && a->levels == b->levels; }
 
 // point the device descriptor of a frame at its staging copies / gamma table and upload it if anything changed
 static int frame_prepare(dslam_frame *f, const float *B256, bool stage_dIp, bool stage_abs) {

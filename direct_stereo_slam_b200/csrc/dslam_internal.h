@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what);
     if (e__ != cudaSuccess) return ::dslam::cuda_fail(e__, #call); \
   } while (0)
 
-constexpr int kResultSlots = 1024;  // pinned, mapped EvalResult ring of a session (8 launches of 128 items)
+constexpr int kResultSlots = 2048;  // pinned, mapped EvalResult ring of a session (16 launches of 128 items)
 
 }  // namespace dslam
 
@@ -40,6 +40,8 @@ constexpr int kResultSlots = 1024;  // pinned, mapped EvalResult ring of a sessi
 struct dslam_session {
   int device = 0;
   cudaStream_t stream = nullptr;
+  float *upload_arena = nullptr;  // device staging of dslam_frame_upload_batch (one H2D for all images of a step)
+  size_t upload_arena_floats = 0;
   dslam::EvalResult *results_host = nullptr;  // cudaHostAllocMapped
   dslam::EvalResult *results_dev = nullptr;   // device alias of results_host
   dslam::EvalScratch scratch{nullptr, nullptr};
@@ -53,7 +55,8 @@ struct dslam_session {
   // own.  The kernels of different groups overlap on the GPU (each is latency-bound and fills a fraction of the SMs) and
   // the host-side LM algebra + launch overhead (which bounds a single thread at ~15 us per round) runs in parallel.
   // Group 0 uses `stream` / `scratch` and the calling thread.
-  static constexpr int kLmGroups = 8;
+  static constexpr int kLmGroups = 16;         // hard cap (DSLAM_LM_GROUPS)
+  static constexpr int kLmGroupsDefault = 8;   // cap of the automatic choice
   int lm_groups = 4;  // DSLAM_LM_GROUPS (1..kLmGroups)
   cudaStream_t lm_stream[kLmGroups] = {};
   dslam::EvalScratch lm_scratch[kLmGroups] = {};

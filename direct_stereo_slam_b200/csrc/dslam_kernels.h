@@ -107,6 +107,11 @@ cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t str
 cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream);
 // texels -> the reference's host layouts (Vector3f AoS + float plane) for a frame built without staging
 cudaError_t launch_unpack(const FrameBatch &B, int nframes, cudaStream_t stream);
+// contiguous arena of nframes raw images (4 * quads floats each) -> dense level-0 planes
+struct PlaneBatch {
+  float *plane[kMaxFramesPerLaunch];
+};
+cudaError_t launch_scatter_planes(const PlaneBatch &B, int nframes, int quads, const float *arena, cudaStream_t stream);
 cudaError_t launch_scale_idepth(float4 *pts, int n, float scale, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------

@@ -276,6 +276,21 @@ cudaError_t launch_unpack(const FrameBatch &B, int nframes, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+// arena of n raw images (contiguous, w*h floats each) -> the level-0 planes of n frames (pitch == w), one float4 per thread
+__global__ void __launch_bounds__(256) scatter_planes_kernel(const __grid_constant__ PlaneBatch B, const float4 *__restrict__ arena, int quads) {
+  float4 *__restrict__ dst = reinterpret_cast<float4 *>(B.plane[blockIdx.y]);
+  const float4 *__restrict__ src = arena + (size_t)blockIdx.y * quads;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < quads; i += gridDim.x * 256) dst[i] = __ldcs(src + i);
+}
+
+cudaError_t launch_scatter_planes(const PlaneBatch &B, int nframes, int quads, const float *arena, cudaStream_t stream) {
+  if (nframes < 1) return cudaSuccess;
+  int gx = (quads + 255) / 256;
+  if (gx > 64) gx = 64;
+  scatter_planes_kernel<<<dim3(gx, nframes), 256, 0, stream>>>(B, reinterpret_cast<const float4 *>(arena), quads);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scale_idepth(float4 *pts, int n, float scale, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   scale_idepth_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, scale);

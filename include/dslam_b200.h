@@ -78,6 +78,10 @@ int dslam_frame_create(dslam_session *s, int w, int h, int levels, dslam_frame *
 int dslam_frame_destroy(dslam_frame *f);
 /* H2D of the level-0 image (w*h floats, 0..255), asynchronous on the session stream */
 int dslam_frame_upload(dslam_frame *f, const float *color);
+/* the same for n frames of one session.  Runs of images that lie back to back in host memory (colors[i+1] == colors[i] + w*h:
+ * a capture ring / pinned arena) travel as ONE host-to-device transfer and are dealt to the frames on the device; other
+ * images are uploaded one by one.  Asynchronous on the session stream; the host images must stay valid until it has drained. */
+int dslam_frame_upload_batch(int n, dslam_frame *const *frames, const float *const *colors);
 /* build all levels on the device from the uploaded image.  B256 = CalibHessian::B (256 floats) applies the
  * gamma weight gw^2 to absSquaredGrad ("HCalib != 0 && setting_gammaWeightsPixelSelect == 1"); NULL = none. */
 int dslam_frame_build(dslam_frame *f, const float *B256);

@@ -91,3 +91,22 @@ def test_synthetic_scene_frames(session, oracle):
         fr.makeImages(c[key])
         _compare(fr, dIp_o, abs_o, levels, cfg["w"], cfg["h"])
         fr.close()
+
+
+def test_upload_batch_equals_single_uploads(session, oracle):
+    """dslam_frame_upload_batch: images that lie back to back in host memory travel as one transfer (+ a scatter kernel),
+    stragglers one by one — the pyramids are the same bits either way (and equal the oracle's)."""
+    w, h, levels = 320, 192, 3
+    arena = session.pinned((5, h, w))
+    for k in range(5):
+        arena[k] = _image(w, h, 40 + k)
+    lone = _image(w, h, 99)                                  # not part of the arena
+    imgs = [arena[0], arena[1], arena[2], lone, arena[4], arena[3]]  # a run of 3, a straggler, two out-of-order slots
+    frames = [api.FrameHessian(session, w, h, levels) for _ in imgs]
+    api.upload_frames(frames, imgs)
+    api.build_frames(frames)
+    for fr, im in zip(frames, imgs):
+        fr.download()
+        dIp_o, abs_o = oracle.make_images(np.array(im), levels)
+        _compare(fr, dIp_o, abs_o, levels, w, h)
+        fr.close()
