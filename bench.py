@@ -156,7 +156,7 @@ class GpuStreams:
             t.setCoarseTrackingRef(ref, c["pu"], c["pv"], c["pid"], c["pw"])
             self.trk.append(t)
             fn = [api.FrameHessian(session, self.w, self.h, self.levels) for _ in range(2)]
-            fr = api.FrameHessian(session, self.w, self.h, self.levels)
+            fr = [api.FrameHessian(session, self.w, self.h, self.levels) for _ in range(2)]  # double-buffered like the left frames
             # pinned host copies of the inputs (e2e) and pinned host mirrors of the left pyramid
             hn = [arena_new[0, i], arena_new[1, i]]
             hn[0][:] = c["img_new"]
@@ -178,38 +178,56 @@ class GpuStreams:
         for i in range(self.n):
             for v in range(2):
                 self.f_new[i][v].upload(self.h_new[i][v])
-            self.f_right[i].upload(self.h_right[i])
+            for v in range(2):
+                self.f_right[i][v].upload(self.h_right[i])
         self.s.sync()
 
     def is_kf(self, i, k):
         return (k + i) % self.kf_every == 0
 
-    def step(self, k, e2e):
+    def _prepare(self, k, e2e):
+        """Inputs + pyramids of step k: (e2e: one H2D per capture arena,) two launches for all left pyramids, two for the right
+        pyramids of the step's keyframes — on the session's pyramid stream, so that the LM rounds queued next (on the frames of
+        the PREVIOUS step) run concurrently — and (e2e) the host mirrors start draining on the frames' copy streams."""
         api = self.api
         v = k & 1
         left = [self.f_new[i][v] for i in range(self.n)]
         kf = [i for i in range(self.n) if self.is_kf(i, k)]
-        right = [self.f_right[i] for i in kf]
+        right = [self.f_right[i][v] for i in kf]
         if e2e:
             for i in range(self.n):
                 left[i].wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
             api.upload_frames(left, [self.h_new[i][v] for i in range(self.n)])
             if kf:
                 api.upload_frames(right, [self.h_right[i] for i in kf])
-        api.build_frames(left, stage_host=3 if e2e else 0)   # two launches for all left pyramids
+        api.build_frames(left, stage_host=3 if e2e else 0, overlap=True)
         if right:
-            api.build_frames(right)
-        if e2e:  # host mirrors drain on the frames' copy streams while the LM rounds run
+            api.build_frames(right, overlap=True)
+        if e2e:
             for i in range(self.n):
                 if self.is_kf(i, k):
                     left[i].download(wait=False)
                 else:
                     left[i].download(wait=False, levels=[0], abs_grad=False)
+        self.prepared = (k, e2e)
+
+    def step(self, k, e2e):
+        """One stereo frame of every stream.  Software pipeline over the steps, like a live system that receives image k+1
+        while it tracks image k: the pyramids of step k+1 are built (pyramid stream) while the LM rounds of step k run, so
+        every call does one pyramid build and one tracking pass — K steps = K builds + K tracking passes."""
+        api = self.api
+        v = k & 1
+        if getattr(self, "prepared", None) != (k, e2e):
+            self._prepare(k, e2e)        # first step of a run: nothing to overlap with
+        self._prepare(k + 1, e2e)        # next frames: H2D + pyramids (+ mirrors) overlap the LM rounds below
+        left = [self.f_new[i][v] for i in range(self.n)]
+        kf = [i for i in range(self.n) if self.is_kf(i, k)]
+        right = [self.f_right[i][v] for i in kf]
         poses = np.stack([self.case_of[i]["pose_init"][v] for i in range(self.n)])
         ok, poses, affs, last, rmse, scales = api.lm_batch(self.trk, left, poses, np.zeros((self.n, 2)), self.levels - 1,
                                                            [self.trk[i] for i in kf], right, np.ones(len(kf), np.float32))
-        # e2e: the host mirrors of this step keep draining (per-frame copy streams) while the next step computes; they are
-        # waited for when their frame object is reused (two steps later) and by drain() before the clock stops
+        # e2e: the host mirrors keep draining (per-frame copy streams) while the next step computes; they are waited for when
+        # their frame object is reused (two steps later) and by drain() before the clock stops
         return ok, poses, scales, rmse
 
     def drain(self):
@@ -409,7 +427,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=128, help="independent stereo streams per GPU advanced in lock step")
+    ap.add_argument("--streams", type=int, default=512, help="independent stereo streams per GPU advanced in lock step")
     ap.add_argument("--keyframe-every", type=int, default=5, help="every k-th frame of a stream also builds the right pyramid and optimises the scale")
     ap.add_argument("--cases", type=int, default=4, help="distinct synthetic scenes (streams cycle through them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

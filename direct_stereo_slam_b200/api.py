@@ -690,8 +690,11 @@ def upload_frames(frames, images):
     check(frames[0].lib.dslam_frame_upload_batch(n, fa, ia))
 
 
-def build_frames(frames, B256=None, stage_host=0):
-    """Pyramids of all (uploaded) frames in two kernel launches (dslam_frame_build_batch)."""
+def build_frames(frames, B256=None, stage_host=0, overlap=False):
+    """Pyramids of all (uploaded) frames in two kernel launches (dslam_frame_build_batch).  overlap=True builds them on the
+    session's pyramid stream, concurrently with tracking calls on other frames queued afterwards (stage_host bit 2)."""
+    if overlap:
+        stage_host |= 4
     n = len(frames)
     arr = (C.c_void_p * n)(*[f.p for f in frames])
     Bp = None

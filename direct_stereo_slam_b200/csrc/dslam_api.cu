@@ -80,21 +80,44 @@ struct EvalOut {           // one calcRes* + calcGSSSE* evaluation, host view
   double res6[6];          // the Vec6 of calcResPose / calcResScale
 };
 
-int choose_blocks(int n, int nitems, int num_sms) {
-  int per = (n + kEvalThreads - 1) / kEvalThreads;  // one template point per thread: shortest critical path
-  if (per < 1) per = 1;
-  const long budget = (long)num_sms * 5;            // one resident wave (96 registers x 128 threads -> 5 CTAs per SM) when many items share a launch
-  if ((long)per * nitems > budget) {
-    per = (int)(budget / nitems);
+// CTAs per item of one launch.  Every item would like one template point per thread (shortest critical path); when the
+// launch as a whole would exceed one resident wave (96 registers x 128 threads -> 5 CTAs per SM) the wave is dealt to the
+// items in proportion to their size, so that the level-0 items of a mixed round are not held to the share of the tiny
+// coarse-level items next to them.  Fills nblocks / ppt_stride / cta_begin; returns the size of the flat grid.
+// `lanes` = launches of this kind in flight at the same time (groups x lanes of a lock step): a launch that shares the GPU
+// takes a smaller slice of the resident wave — measured on B200 with 8 concurrent lanes: 2-3 CTAs per SM per launch beat 5
+// by 8 % and 8 by 17 % (the CTAs of concurrent launches queue behind each other).
+int assign_blocks(EvalItem *items, int cnt, int num_sms, int lanes) {
+  long want_total = 0;
+  for (int i = 0; i < cnt; i++) {
+    int per = (items[i].n + kEvalThreads - 1) / kEvalThreads;
     if (per < 1) per = 1;
+    if (per > kMaxBlocksPerItem) per = kMaxBlocksPerItem;
+    items[i].nblocks = per;
+    want_total += per;
   }
-  if (per > kMaxBlocksPerItem) per = kMaxBlocksPerItem;
-  return per;
+  static const int per_sm_env = [] { const char *e = getenv("DSLAM_EVAL_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 16 ? v : 0; }();
+  int per_sm = lanes <= 2 ? 5 : (12 + lanes - 1) / lanes;
+  if (per_sm < 2) per_sm = 2;
+  if (per_sm_env) per_sm = per_sm_env;
+  const long budget = (long)num_sms * per_sm;
+  int total = 0;
+  for (int i = 0; i < cnt; i++) {
+    EvalItem &it = items[i];
+    if (want_total > budget) {
+      int per = (int)((long)it.nblocks * budget / want_total);
+      it.nblocks = per < 1 ? 1 : per;
+    }
+    it.ppt_stride = it.nblocks * kEvalThreads;
+    it.cta_begin = total;
+    total += it.nblocks;
+  }
+  return total;
 }
 
 // Launch `n` prepared items (result slots [slot0, slot0 + n)) on `stream`; returns the sequence number through *seq_out.
 int launch_items(dslam_session *s, std::vector<EvalItem> &items, int slot0, cudaStream_t stream, EvalScratch scratch, unsigned *seq_out,
-                 long long *launch_counter) {
+                 long long *launch_counter, int lanes = 1) {
   const int n = (int)items.size();
   // kernel flavour: 0 = all pose, 1 = all scale, 2 = mixed (bit 1 of EvalItem::flags marks a scale item)
   int n_scale = 0;
@@ -105,15 +128,11 @@ int launch_items(dslam_session *s, std::vector<EvalItem> &items, int slot0, cuda
   EvalBatch batch;
   for (int base = 0; base < n; base += kMaxItemsPerLaunch) {
     const int cnt = n - base < kMaxItemsPerLaunch ? n - base : kMaxItemsPerLaunch;
-    int gx = 1;
     long long pts = 0;
+    const int gx = assign_blocks(&items[base], cnt, s->num_sms, lanes);
     for (int i = 0; i < cnt; i++) {
-      EvalItem &it = items[base + i];
-      it.nblocks = choose_blocks(it.n, cnt, s->num_sms);
-      it.ppt_stride = it.nblocks * kEvalThreads;
-      if (it.nblocks > gx) gx = it.nblocks;
-      batch.item[i] = it;
-      pts += it.n;
+      batch.item[i] = items[base + i];
+      pts += items[base + i].n;
     }
     const bool prof = s->prof_on;
     size_t slot = 0;
@@ -226,7 +245,7 @@ void fill_common(EvalItem &it, const dslam_ctx *c, const dslam_frame *f, int lvl
   it.maxEnergy = 2 * kHuberTH * cutoff - kHuberTH * kHuberTH;  // :726-728
   it.nblocks = 1;
   it.ppt_stride = kEvalThreads;
-  it.pad_ = 0;
+  it.cta_begin = 0;
 }
 
 // calcResPose prologue :711-720
@@ -581,7 +600,7 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
   const int total = (int)(pose.size() + scale.size());
   int ngroups = s->lm_groups;
   while (ngroups > 1 && total < 4 * ngroups) ngroups--;  // a group needs a few machines to be worth a launch of its own
-  const int slots_per_group = kResultSlots / G;
+  const int slots_per_group = (kResultSlots / ngroups) & ~1;  // result-ring slice of a group (two lanes share it half and half)
   struct Group {
     std::vector<int> members;  // >= 0: pose machine index, < 0: ~index of a scale machine
     int rc = DSLAM_OK;
@@ -595,55 +614,97 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
   }
   for (int g = 0; g < ngroups; g++)
     if ((int)grp[g].members.size() > slots_per_group) return fail(DSLAM_EINVAL, "too many machines in one lock step");
-  if (ngroups > 1) {  // the side streams start after everything queued on the session stream (pyramids, template uploads)
+  // Every group runs two launch lanes: its machines are dealt into two halves and while one half is being evaluated on the
+  // GPU the host consumes the results of the other half and prepares its next round — the LM algebra of a group (the larger
+  // part of a round at >= 32 machines) hides behind the kernel of the other lane.  A machine still sees exactly the
+  // evaluations it would see alone.
+  const int nhalves = s->lm_halves;
+  const int slots_per_half = slots_per_group / 2;
+  for (int g = 0; g < ngroups; g++)
+    if (nhalves > 1 && ((int)grp[g].members.size() + 1) / 2 > slots_per_half) return fail(DSLAM_EINVAL, "too many machines in one lock step");
+  auto two_lanes = [&](int g) { return nhalves > 1 && grp[g].members.size() >= 8; };
+  int total_lanes = 0;
+  for (int g = 0; g < ngroups; g++) total_lanes += two_lanes(g) ? 2 : 1;
+  bool any_side = ngroups > 1;
+  for (int g = 0; g < ngroups; g++) any_side |= two_lanes(g);
+  if (any_side) {  // the side streams start after everything queued on the session stream (pyramids, template uploads)
     DSLAM_CUDA(cudaEventRecord(s->lm_fork, s->stream));
     for (int g = 1; g < ngroups; g++) DSLAM_CUDA(cudaStreamWaitEvent(s->lm_stream[g], s->lm_fork, 0));
+    for (int g = 0; g < ngroups; g++)
+      if (two_lanes(g)) DSLAM_CUDA(cudaStreamWaitEvent(s->lm_stream2[g], s->lm_fork, 0));
   }
   auto now_ns = []() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto drive = [&](int g) {
     Group &gr = grp[g];
-    std::vector<EvalItem> items;
-    std::vector<int> who;
-    std::vector<EvalOut> outs;
+    struct Lane {
+      std::vector<int> members, who;
+      std::vector<EvalItem> items;
+      std::vector<EvalOut> outs;
+      unsigned seq = 0;
+      bool inflight = false;
+      int slot0 = 0;
+      cudaStream_t stream = nullptr;
+      EvalScratch scratch{nullptr, nullptr};
+    } lane[2];
+    const int nl = two_lanes(g) ? 2 : 1;
+    for (size_t k = 0; k < gr.members.size(); k++) lane[nl == 2 ? (k & 1) : 0].members.push_back(gr.members[k]);
+    lane[0].slot0 = g * slots_per_group;
+    lane[0].stream = s->lm_stream[g];
+    lane[0].scratch = s->lm_scratch[g];
+    lane[1].slot0 = g * slots_per_group + slots_per_half;
+    lane[1].stream = s->lm_stream2[g];
+    lane[1].scratch = s->lm_scratch2[g];
     long long t_prep = 0, t_launch = 0, t_wait = 0, rounds = 0;
-    for (;;) {
+    // prepare the next round of a lane and launch it; leaves inflight = false when all its machines are done
+    auto issue = [&](Lane &L) {
       const long long t0 = now_ns();
-      items.clear();
-      who.clear();
-      for (int m : gr.members) {
+      L.items.clear();
+      L.who.clear();
+      for (int m : L.members) {
         if (m >= 0) {
           if (pose[m].phase == PoseLM::DONE) continue;
-          items.emplace_back();
-          pose[m].request(items.back());
+          L.items.emplace_back();
+          pose[m].request(L.items.back());
         } else {
           if (scale[~m].phase == ScaleLM::DONE) continue;
-          items.emplace_back();
-          scale[~m].request(items.back());
+          L.items.emplace_back();
+          scale[~m].request(L.items.back());
         }
-        who.push_back(m);
+        L.who.push_back(m);
       }
       const long long t1 = now_ns();
       t_prep += t1 - t0;
-      if (items.empty()) break;
-      unsigned seq = 0;
-      gr.rc = launch_items(s, items, g * slots_per_group, s->lm_stream[g], s->lm_scratch[g], &seq, &gr.launches);
-      const long long t2 = now_ns();
-      t_launch += t2 - t1;
+      L.inflight = false;
+      if (L.items.empty()) return;
+      gr.rc = launch_items(s, L.items, L.slot0, L.stream, L.scratch, &L.seq, &gr.launches, total_lanes);
+      t_launch += now_ns() - t1;
       rounds++;
-      if (gr.rc == DSLAM_OK) gr.rc = collect_items(s, items, g * slots_per_group, s->lm_stream[g], seq, outs);
-      if (gr.rc != DSLAM_OK) {
-        gr.err = g_err;
-        break;
-      }
+      L.inflight = gr.rc == DSLAM_OK;
+    };
+    // wait for the results of a lane's launch and let its machines consume them
+    auto retire = [&](Lane &L) {
+      const long long t2 = now_ns();
+      gr.rc = collect_items(s, L.items, L.slot0, L.stream, L.seq, L.outs);
+      L.inflight = false;
+      if (gr.rc != DSLAM_OK) return;
       const long long t3 = now_ns();
       t_wait += t3 - t2;
-      gr.evals += (long long)items.size();
-      for (size_t k = 0; k < who.size(); k++) {
-        if (who[k] >= 0) pose[who[k]].consume(outs[k]);
-        else scale[~who[k]].consume(outs[k]);
+      gr.evals += (long long)L.items.size();
+      for (size_t k = 0; k < L.who.size(); k++) {
+        if (L.who[k] >= 0) pose[L.who[k]].consume(L.outs[k]);
+        else scale[~L.who[k]].consume(L.outs[k]);
       }
       t_prep += now_ns() - t3;
+    };
+    for (int l = 0; l < nl && gr.rc == DSLAM_OK; l++) issue(lane[l]);
+    while (gr.rc == DSLAM_OK && (lane[0].inflight || lane[1].inflight)) {
+      for (int l = 0; l < nl && gr.rc == DSLAM_OK; l++) {
+        if (!lane[l].inflight) continue;
+        retire(lane[l]);
+        if (gr.rc == DSLAM_OK) issue(lane[l]);
+      }
     }
+    if (gr.rc != DSLAM_OK) gr.err = g_err;
     s->t_prep_ns += t_prep;
     s->t_launch_ns += t_launch;
     s->t_wait_ns += t_wait;
@@ -678,12 +739,16 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
       set_error("%s", grp[g].err.c_str());
     }
   }
-  if (ngroups > 1) {  // later work on the session stream (next pyramids, template changes) is ordered after the side streams
-    for (int k = 1; k < ngroups; k++) {
-      DSLAM_CUDA(cudaEventRecord(s->lm_done[k], s->lm_stream[k]));
-      DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done[k], 0));
-    }
+  // later work on the session stream (next pyramids, template changes) is ordered after the side streams
+  for (int k = 1; k < ngroups; k++) {
+    DSLAM_CUDA(cudaEventRecord(s->lm_done[k], s->lm_stream[k]));
+    DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done[k], 0));
   }
+  for (int k = 0; k < ngroups; k++)
+    if (two_lanes(k)) {
+      DSLAM_CUDA(cudaEventRecord(s->lm_done2[k], s->lm_stream2[k]));
+      DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done2[k], 0));
+    }
   return rc;
 }
 
@@ -704,6 +769,17 @@ bool finish_pose(const dslam_ctx *c, PoseLM &m, float new_exposure, double *pose
   return true;
 }
 
+// Order the session stream behind the asynchronous build that last wrote `f` (no-op for synchronous builds and for
+// generations the stream already waited for: the builds of a session complete in order).
+int frame_acquire(const dslam_frame *f) {
+  dslam_session *s = f->s;
+  if (f->async_gen > s->pyr_waited) {
+    DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->pyr_ev[f->async_gen % dslam_session::kPyrEvents], 0));
+    s->pyr_waited = f->async_gen;
+  }
+  return DSLAM_OK;
+}
+
 int check_ctx_frame(const dslam_ctx *c, const dslam_frame *f, int coarsestLvl) {
   if (!c || !f) return fail(DSLAM_EINVAL, "null context or frame");
   if (c->s != f->s) return fail(DSLAM_EINVAL, "context and frame belong to different sessions");
@@ -711,7 +787,7 @@ int check_ctx_frame(const dslam_ctx *c, const dslam_frame *f, int coarsestLvl) {
   if (!f->built) return fail(DSLAM_ESTATE, "frame pyramid has not been built");
   if (f->w != c->w[0] || f->h != c->h[0] || f->levels < c->levels) return fail(DSLAM_EINVAL, "frame geometry does not match the context");
   if (coarsestLvl < 0 || coarsestLvl >= c->levels || coarsestLvl >= 5) return fail(DSLAM_EINVAL, "coarsestLvl %d out of range", coarsestLvl);
-  return DSLAM_OK;
+  return frame_acquire(f);
 }
 
 }  // namespace
@@ -757,7 +833,9 @@ int dslam_session_create(int device, dslam_session **out) {
   s->device = device;
   cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (s->num_sms <= 0) s->num_sms = 148;
-  DSLAM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  int prio_lo = 0;
+  DSLAM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &s->prio_hi));
+  DSLAM_CUDA(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, s->prio_hi));
   DSLAM_CUDA(cudaHostAlloc((void **)&s->results_host, sizeof(EvalResult) * kResultSlots, cudaHostAllocMapped));
   std::memset(s->results_host, 0, sizeof(EvalResult) * kResultSlots);  // sequence numbers start at 1
   DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->results_dev, s->results_host, 0));
@@ -780,8 +858,29 @@ int dslam_session_create(int device, dslam_session **out) {
     if (v >= 1 && v <= dslam_session::kLmGroups) s->lm_groups = v;
   }
   DSLAM_CUDA(cudaEventCreateWithFlags(&s->lm_fork, cudaEventDisableTiming));
+  {  // LM rounds are latency-critical, the overlapped pyramid builds are not: highest / lowest stream priority
+    DSLAM_CUDA(cudaStreamCreateWithPriority(&s->pyr_stream, cudaStreamNonBlocking, prio_lo));
+  }
+  if (const char *e = getenv("DSLAM_PYR_ASYNC_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 6) s->pyr_async_ctas = v;
+  }
+  DSLAM_CUDA(cudaEventCreateWithFlags(&s->pyr_in, cudaEventDisableTiming));
+  for (int k = 0; k < dslam_session::kPyrEvents; k++) DSLAM_CUDA(cudaEventCreateWithFlags(&s->pyr_ev[k], cudaEventDisableTiming));
+  // two launch lanes per group pay off when host threads are scarce (measured on B200 / 16 cores, 512 streams: +20 % at 4
+  // groups, -15 % at 8: with enough threads the extra launches cost more than the hidden host algebra gains)
+  s->lm_halves = s->lm_groups <= 4 ? 2 : 1;
+  if (const char *e = getenv("DSLAM_LM_HALVES")) s->lm_halves = atoi(e) == 1 ? 1 : 2;
+  for (int g = 0; g < dslam_session::kLmGroups; g++) {
+    DSLAM_CUDA(cudaStreamCreateWithPriority(&s->lm_stream2[g], cudaStreamNonBlocking, s->prio_hi));
+    DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch2[g].partials, sizeof(double) * kMaxItemsPerLaunch * kMaxBlocksPerItem * kPoseVals));
+    DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch2[g].counters, sizeof(int) * kMaxItemsPerLaunch * 4));
+    DSLAM_CUDA(cudaMemsetAsync(s->lm_scratch2[g].counters, 0, sizeof(int) * kMaxItemsPerLaunch * 4, s->lm_stream2[g]));
+    DSLAM_CUDA(cudaEventCreateWithFlags(&s->lm_done2[g], cudaEventDisableTiming));
+    DSLAM_CUDA(cudaStreamSynchronize(s->lm_stream2[g]));
+  }
   for (int g = 1; g < dslam_session::kLmGroups; g++) {
-    DSLAM_CUDA(cudaStreamCreateWithFlags(&s->lm_stream[g], cudaStreamNonBlocking));
+    DSLAM_CUDA(cudaStreamCreateWithPriority(&s->lm_stream[g], cudaStreamNonBlocking, s->prio_hi));
     DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch[g].partials, sizeof(double) * kMaxItemsPerLaunch * kMaxBlocksPerItem * kPoseVals));
     DSLAM_CUDA(cudaMalloc((void **)&s->lm_scratch[g].counters, sizeof(int) * kMaxItemsPerLaunch * 4));
     DSLAM_CUDA(cudaMemsetAsync(s->lm_scratch[g].counters, 0, sizeof(int) * kMaxItemsPerLaunch * 4, s->lm_stream[g]));
@@ -815,7 +914,23 @@ int dslam_session_destroy(dslam_session *s) {
     cudaEventDestroy(s->lm_done[g]);
     cudaStreamDestroy(s->lm_stream[g]);
   }
+  for (int g = 0; g < dslam_session::kLmGroups; g++) {
+    if (!s->lm_stream2[g]) continue;
+    cudaStreamSynchronize(s->lm_stream2[g]);
+    cudaFree(s->lm_scratch2[g].partials);
+    cudaFree(s->lm_scratch2[g].counters);
+    cudaEventDestroy(s->lm_done2[g]);
+    cudaStreamDestroy(s->lm_stream2[g]);
+  }
   if (s->lm_fork) cudaEventDestroy(s->lm_fork);
+  if (s->pyr_stream) {
+    cudaStreamSynchronize(s->pyr_stream);
+    cudaStreamDestroy(s->pyr_stream);
+  }
+  if (s->pyr_in) cudaEventDestroy(s->pyr_in);
+  for (int k = 0; k < dslam_session::kPyrEvents; k++)
+    if (s->pyr_ev[k]) cudaEventDestroy(s->pyr_ev[k]);
+  cudaFree(s->upload_arena);
   cudaFree(s->scratch.partials);
   cudaFree(s->scratch.counters);
   cudaFreeHost(s->results_host);
@@ -830,7 +945,10 @@ int dslam_session_destroy(dslam_session *s) {
 int dslam_session_sync(dslam_session *s) {
   if (!s) return fail(DSLAM_EINVAL, "null session");
   for (int g = 1; g < dslam_session::kLmGroups; g++) DSLAM_CUDA(cudaStreamSynchronize(s->lm_stream[g]));
+  for (int g = 0; g < dslam_session::kLmGroups; g++)
+    if (s->lm_stream2[g]) DSLAM_CUDA(cudaStreamSynchronize(s->lm_stream2[g]));
   DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  if (s->pyr_stream) DSLAM_CUDA(cudaStreamSynchronize(s->pyr_stream));
   return DSLAM_OK;
 }
 
@@ -999,6 +1117,7 @@ int dslam_frame_destroy(dslam_frame *f) {
   if (!f) return DSLAM_OK;
   cudaSetDevice(f->s->device);
   cudaStreamSynchronize(f->s->stream);
+  if (f->async_gen && f->s->pyr_stream) cudaStreamSynchronize(f->s->pyr_stream);
   cudaFree(f->block);
   cudaFree(f->dev);
   cudaFree(f->stage_dIp);
@@ -1017,6 +1136,8 @@ int dslam_frame_destroy(dslam_frame *f) {
 int dslam_frame_upload(dslam_frame *f, const float *color) {
   if (!f || !color) return fail(DSLAM_EINVAL, "null argument");
   const PyramidLevels &L = f->L;
+  const int ra = frame_acquire(f);  // an asynchronous build may still be reading the old image
+  if (ra != DSLAM_OK) return ra;
   if (L.pitch[0] == f->w)  // dense plane: a plain 1-D copy
     DSLAM_CUDA(cudaMemcpyAsync(L.plane[0], color, (size_t)f->w * f->h * sizeof(float), cudaMemcpyHostToDevice, f->s->stream));
   else
@@ -1038,6 +1159,8 @@ int dslam_frame_upload_batch(int n, dslam_frame *const *frames, const float *con
   for (int i = 0; i < n; i++) {
     if (!frames[i] || !colors[i]) return fail(DSLAM_EINVAL, "null frame or image");
     if (frames[i]->s != frames[0]->s) return fail(DSLAM_EINVAL, "all frames of a batch must live in one session");
+    const int ra = frame_acquire(frames[i]);
+    if (ra != DSLAM_OK) return ra;
   }
   dslam_session *s = frames[0]->s;
   DSLAM_CUDA(cudaSetDevice(s->device));
@@ -1093,6 +1216,8 @@ static bool same_geometry(const dslam_frame *a, const dslam_frame *b) {
 // point the device descriptor of a frame at its staging copies / gamma table and upload it if anything changed
 static int frame_prepare(dslam_frame *f, const float *B256, bool stage_dIp, bool stage_abs) {
   dslam_session *s = f->s;
+  const int ra = frame_acquire(f);
+  if (ra != DSLAM_OK) return ra;
   const float *Bd = nullptr;
   if (B256) {
     if (!f->B_dev) DSLAM_CUDA(cudaMalloc((void **)&f->B_dev, 256 * sizeof(float)));
@@ -1123,7 +1248,7 @@ static int frame_prepare(dslam_frame *f, const float *B256, bool stage_dIp, bool
 }
 
 // two launches for every run of <= kMaxFramesPerLaunch frames with the same geometry
-static int frames_build(int n, dslam_frame *const *frames, const float *B256, bool stage_dIp, bool stage_abs) {
+static int frames_build(int n, dslam_frame *const *frames, const float *B256, bool stage_dIp, bool stage_abs, bool async = false) {
   for (int i = 0; i < n; i++) {
     if (!frames[i]) return fail(DSLAM_EINVAL, "null frame");
     if (!frames[i]->uploaded) return fail(DSLAM_ESTATE, "dslam_frame_build before dslam_frame_upload");
@@ -1132,6 +1257,12 @@ static int frames_build(int n, dslam_frame *const *frames, const float *B256, bo
     if (rc != DSLAM_OK) return rc;
   }
   dslam_session *s = frames[0]->s;
+  cudaStream_t st = s->stream;
+  if (async) {  // behind everything queued on the session stream so far (uploads, the LM rounds that read these frame objects)
+    st = s->pyr_stream;
+    DSLAM_CUDA(cudaEventRecord(s->pyr_in, s->stream));
+    DSLAM_CUDA(cudaStreamWaitEvent(st, s->pyr_in, 0));
+  }
   int i = 0;
   while (i < n) {
     FrameBatch B;
@@ -1142,16 +1273,21 @@ static int frames_build(int n, dslam_frame *const *frames, const float *B256, bo
       cnt++;
     }
     if (B.G.levels > 1) {
-      DSLAM_CUDA(launch_downsample(B, cnt, s->stream));
+      DSLAM_CUDA(launch_downsample(B, cnt, st));
       s->launches++;
     }
-    DSLAM_CUDA(launch_gradients(B, cnt, s->stream));
+    DSLAM_CUDA(launch_gradients(B, cnt, st, async ? s->pyr_async_ctas : 6));
     s->launches++;
     for (int k = 0; k < cnt; k++) {
       frames[i + k]->built = true;
       frames[i + k]->staged = stage_dIp || stage_abs;
+      frames[i + k]->async_gen = async ? s->pyr_gen + 1 : 0;
     }
     i += cnt;
+  }
+  if (async) {
+    s->pyr_gen++;
+    DSLAM_CUDA(cudaEventRecord(s->pyr_ev[s->pyr_gen % dslam_session::kPyrEvents], st));
   }
   return DSLAM_OK;
 }
@@ -1163,14 +1299,18 @@ int dslam_frame_build(dslam_frame *f, const float *B256) {
 
 int dslam_frame_build_batch(int n, dslam_frame *const *frames, const float *B256, int stage_host) {
   if (n < 1 || !frames) return fail(DSLAM_EINVAL, "bad argument");
-  return frames_build(n, frames, B256, (stage_host & 1) != 0, (stage_host & 2) != 0);
+  return frames_build(n, frames, B256, (stage_host & 1) != 0, (stage_host & 2) != 0, (stage_host & 4) != 0);
 }
 
 static int frame_copy_out(dslam_frame *f, float *const *host_dIp, float *const *host_absgrad) {
   dslam_session *s = f->s;
   // the copies run on the frame's own stream, behind the kernels that filled the staging buffers
-  DSLAM_CUDA(cudaEventRecord(f->built_ev, s->stream));
-  DSLAM_CUDA(cudaStreamWaitEvent(f->copy_stream, f->built_ev, 0));
+  if (f->async_gen > s->pyr_waited) {  // built on the pyramid stream: wait for that build, not for the session stream
+    DSLAM_CUDA(cudaStreamWaitEvent(f->copy_stream, s->pyr_ev[f->async_gen % dslam_session::kPyrEvents], 0));
+  } else {
+    DSLAM_CUDA(cudaEventRecord(f->built_ev, s->stream));
+    DSLAM_CUDA(cudaStreamWaitEvent(f->copy_stream, f->built_ev, 0));
+  }
   // contiguous destination (one block for all levels) -> one DMA per array instead of one per level
   for (int pass = 0; pass < 2; pass++) {
     float *const *dst = pass == 0 ? host_dIp : host_absgrad;
@@ -1201,6 +1341,8 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
   const bool need_d = host_dIp != nullptr, need_a = host_absgrad != nullptr;
   const bool have = f->staged && (!need_d || f->stage_dIp) && (!need_a || f->stage_abs);
   if (!have) {
+    const int ra = frame_acquire(f);
+    if (ra != DSLAM_OK) return ra;
     const int rc = frame_ensure_staging(f, need_d, need_a);
     if (rc != DSLAM_OK) return rc;
     const int rp = frame_prepare(f, nullptr, f->stage_dIp != nullptr, f->stage_abs != nullptr);
@@ -1351,6 +1493,10 @@ int dslam_ref_build(dslam_ctx *c, dslam_frame *ref_frame, int npts, const int *p
   if (ref_frame->w != c->w[0] || ref_frame->h != c->h[0] || ref_frame->levels < c->levels) return fail(DSLAM_EINVAL, "frame geometry mismatch");
   dslam_session *s = c->s;
   DSLAM_CUDA(cudaSetDevice(s->device));
+  {
+    const int ra = frame_acquire(ref_frame);
+    if (ra != DSLAM_OK) return ra;
+  }
   const size_t tot = c->px_off[c->levels];
   TemplateGrids G{};
   G.levels = c->levels;

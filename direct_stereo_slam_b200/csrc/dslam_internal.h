@@ -40,6 +40,15 @@ constexpr int kResultSlots = 2048;  // pinned, mapped EvalResult ring of a sessi
 struct dslam_session {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // Asynchronous pyramid builds (dslam_frame_build_batch, stage_host bit 2) run on their own stream so that the pyramids
+  // of the NEXT frames are built while the LM rounds of the current ones run.  Every build records one event of a ring;
+  // a frame remembers the generation of its build and any later use of it orders the session stream behind that event.
+  static constexpr int kPyrEvents = 8;
+  cudaStream_t pyr_stream = nullptr;
+  int prio_hi = 0;
+  int pyr_async_ctas = 3;  // CTAs per SM of the gradient kernel in asynchronous builds (DSLAM_PYR_ASYNC_CTAS)
+  cudaEvent_t pyr_in = nullptr, pyr_ev[kPyrEvents] = {};
+  unsigned long long pyr_gen = 0, pyr_waited = 0;
   float *upload_arena = nullptr;  // device staging of dslam_frame_upload_batch (one H2D for all images of a step)
   size_t upload_arena_floats = 0;
   dslam::EvalResult *results_host = nullptr;  // cudaHostAllocMapped
@@ -61,6 +70,12 @@ struct dslam_session {
   cudaStream_t lm_stream[kLmGroups] = {};
   dslam::EvalScratch lm_scratch[kLmGroups] = {};
   cudaEvent_t lm_done[kLmGroups] = {};
+  // second launch lane of every group: a group deals its machines into two halves and keeps one half on the GPU while the
+  // host consumes / prepares the other (DSLAM_LM_HALVES=1 disables)
+  cudaStream_t lm_stream2[kLmGroups] = {};
+  dslam::EvalScratch lm_scratch2[kLmGroups] = {};
+  cudaEvent_t lm_done2[kLmGroups] = {};
+  int lm_halves = 2;
   cudaEvent_t lm_fork = nullptr;
   struct Worker {
     std::thread th;
@@ -99,6 +114,7 @@ struct dslam_frame {
   cudaEvent_t built_ev = nullptr;    // recorded on the session stream after the kernels that fill the staging copies
   cudaStream_t copy_stream = nullptr;  // D2H of the host mirrors overlaps the tracking kernels of the session stream
   bool host_pending = false;
+  unsigned long long async_gen = 0;  // generation of the asynchronous build that last wrote this frame (0 = none)
 };
 
 struct dslam_ctx {

@@ -30,9 +30,9 @@ struct alignas(16) EvalItem {
   float Ki[9];        // K^-1 of the level (flow indicators)
   float p0, p1, p2;   // pose: affLL a, affLL b, b0 ; scale: scale, unused, unused
   float cutoff, maxEnergy;
-  int nblocks;        // CTAs working on this item (<= gridDim.x)
+  int nblocks;        // CTAs working on this item
   int ppt_stride;     // = nblocks * kEvalThreads (grid stride)
-  int pad_;
+  int cta_begin;      // first CTA of this item in the flat 1-D grid of the launch (items in order, no idle CTAs)
 };
 
 struct EvalBatch {
@@ -59,7 +59,7 @@ struct EvalScratch {
 };
 
 // mode 0 = pose (8-DoF), 1 = scale (1-DoF). results_dev = device alias of the mapped EvalResult array.
-cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
+cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------
@@ -104,7 +104,7 @@ struct FrameBatch {
 };
 // all frames of the batch share the geometry G
 cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t stream);
-cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream);
+cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream, int ctas_per_sm = 6);
 // texels -> the reference's host layouts (Vector3f AoS + float plane) for a frame built without staging
 cudaError_t launch_unpack(const FrameBatch &B, int nframes, cudaStream_t stream);
 // contiguous arena of nframes raw images (4 * quads floats each) -> dense level-0 planes

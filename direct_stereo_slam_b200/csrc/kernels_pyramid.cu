@@ -257,10 +257,11 @@ cudaError_t launch_downsample(const FrameBatch &B, int nframes, cudaStream_t str
   return cudaGetLastError();
 }
 
-cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream) {
+cudaError_t launch_gradients(const FrameBatch &B, int nframes, cudaStream_t stream, int ctas_per_sm) {
   if (nframes < 1) return cudaSuccess;
   const int total = B.G.tile_begin[B.G.levels] * nframes;
-  int grid = 148 * 6;  // persistent: 6 CTAs (6 x 2 boxes of 5 KB) per SM
+  if (ctas_per_sm < 1 || ctas_per_sm > 6) ctas_per_sm = 6;
+  int grid = 148 * ctas_per_sm;  // persistent: up to 6 CTAs (6 x 2 boxes of 5 KB) per SM; fewer when the build shares the GPU with LM rounds
   if (grid > total) grid = total;
   gradient_kernel<<<grid, 256, 0, stream>>>(B, nframes);
   return cudaGetLastError();

@@ -126,7 +126,7 @@ struct BatchT {
 // acc layout: pose  [0..44] upper triangle of [J0..J7 r]^T w [J0..J7 r], [45] E, [46] shiftT, [47] shiftRT
 //             scale [0] JwJ, [1] Jwr, [2] rwr, [3] E, [4] shiftT, [5] shiftRT
 template <int MODE, int NV>
-__device__ __forceinline__ void eval_points(const EvalItem &it, double (&acc)[NV], int &nE, int &nSat, int &nInl) {
+__device__ __forceinline__ void eval_points(const EvalItem &it, int bx, double (&acc)[NV], int &nE, int &nSat, int &nInl) {
   const int tid = threadIdx.x;
   const float4 *__restrict__ tex = it.tex;
   const float4 *__restrict__ pts = it.pts;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, double (&acc)[NV
   const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
   constexpr int iE = MODE == 0 ? 45 : 3, iT = MODE == 0 ? 46 : 4, iRT = MODE == 0 ? 47 : 5;
 
-  int i = blockIdx.x * kEvalThreads + tid;
+  int i = bx * kEvalThreads + tid;
   float4 p_next = i < n ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (; i < n; i += stride) {
     const float4 p = p_next;
@@ -223,7 +223,7 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, double (&acc)[NV
   // through ~200 extra instructions per point.
   if (it.flags & 1) {
     const int nflow = (n + 31) >> 5;
-    for (int k = blockIdx.x * kEvalThreads + tid; k < nflow; k += stride) {
+    for (int k = bx * kEvalThreads + tid; k < nflow; k += stride) {
       const float4 p = __ldg(pts + 32 * k);
       const float x = p.x, y = p.y, id = p.z;
       const float s = MODE == 0 ? 1.0f : it.p0;
@@ -280,7 +280,7 @@ __device__ __forceinline__ int tri9(int g, int n) { return 9 * g - (g * (g - 1))
 // are exact in fp64, so the result differs from the per-thread FMA form only in the order of the fp64 additions.
 // b = sum J w r, sum w r^2, E and the flow sums stay per lane (12 doubles) and are folded by a 16-wide reduce-scatter.
 // Results land in sred_w[48] (this warp's slot, pre-zeroed) in the oracle's acc layout.
-__device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w, float *sJ, float *sJw, int &nE, int &nSat, int &nInl) {
+__device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double *sred_w, float *sJ, float *sJw, int &nE, int &nSat, int &nInl) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 *__restrict__ tex = it.tex;
   const float4 *__restrict__ pts = it.pts;
@@ -296,7 +296,7 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
 #pragma unroll
   for (int i = 0; i < 16; i++) ext[i] = 0.0;
 
-  int base = (blockIdx.x * (kEvalThreads / 32) + warp) * 32;
+  int base = (bx * (kEvalThreads / 32) + warp) * 32;
   float4 p_next = base + lane < n ? __ldg(pts + base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (; base < n; base += stride) {  // warp-uniform trip count: mma.sync needs all 32 lanes
     const int i = base + lane;
@@ -374,7 +374,7 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
     // PoseEstimator.cpp:191-226: same four probes, but on the raw (x, y) of the 3-D point with z replaced by 1 and
     // measured against the projection (Ku0, Kv0) of the untransformed point.
     const int nflow = (n + 31) >> 5;
-    for (int kf = blockIdx.x * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
+    for (int kf = bx * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
       const float4 p = __ldg(pts + 32 * kf);
       const float x = p.x, y = p.y, z = p.z;
       const float Ku0 = fxl * (x / z) + cxl, Kv0 = fyl * (y / z) + cyl;
@@ -399,7 +399,7 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
     }
   } else if (it.flags & 1) {
     const int nflow = (n + 31) >> 5;
-    for (int kf = blockIdx.x * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
+    for (int kf = bx * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
       const float4 p = __ldg(pts + 32 * kf);
       const float x = p.x, y = p.y, id = p.z;
       const float kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
@@ -439,14 +439,26 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, double *sred_w
 }
 
 // MODE 0 = pose items only, 1 = scale items only, 2 = mixed (bit 1 of EvalItem::flags selects scale; used when the pose
-// tracker and the scale optimiser of a stereo frame advance in the same launch).  grid = (max nblocks, nitems).
+// tracker and the scale optimiser of a stereo frame advance in the same launch).  The grid is flat: the CTAs of item 0,
+// then those of item 1, ... (EvalItem::cta_begin); a CTA finds its item by bisection over the <= 128 prefix entries in
+// constant memory, so items of very different sizes share a launch without idle CTAs.
 template <int MODE, int CAP>
 __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
-                                                           EvalResult *__restrict__ results, unsigned seq) {
+                                                           EvalResult *__restrict__ results, unsigned seq, int nitems) {
   constexpr int NV = MODE == 1 ? kScaleVals : kPoseVals;
   constexpr int NW = kEvalThreads / 32;
-  const EvalItem &it = batch.item[blockIdx.y];
-  if ((int)blockIdx.x >= it.nblocks) return;
+  int iy = 0;
+  if (CAP > 1) {  // last item whose cta_begin <= blockIdx.x
+    int lo = 0, hi = nitems - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (batch.item[mid].cta_begin <= (int)blockIdx.x) lo = mid;
+      else hi = mid - 1;
+    }
+    iy = lo;
+  }
+  const EvalItem &it = batch.item[iy];
+  const int bx = (int)blockIdx.x - it.cta_begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   DBG_MIN(0);
@@ -460,12 +472,12 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   int nE = 0, nSat = 0, nInl = 0;
   const bool scale_item = MODE == 1 || (MODE == 2 && (it.flags & 2));
   if (!scale_item) {
-    if (MODE != 1) eval_pose_mma(it, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
+    if (MODE != 1) eval_pose_mma(it, bx, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
   } else {
     double acc[kScaleVals];
 #pragma unroll
     for (int i = 0; i < kScaleVals; i++) acc[i] = 0.0;
-    eval_points<1, kScaleVals>(it, acc, nE, nSat, nInl);
+    eval_points<1, kScaleVals>(it, bx, acc, nE, nSat, nInl);
     WarpRS<kScaleVals>::run(acc, lane);
     if (WarpRS<kScaleVals>::writer(lane)) sred[warp][WarpRS<kScaleVals>::base(lane)] = acc[0];
   }
@@ -482,7 +494,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
     atomicAdd(&scnt[1], nSat);
     atomicAdd(&scnt[2], nInl);
   }
-  double *part = scratch.partials + ((size_t)blockIdx.y * kMaxBlocksPerItem + blockIdx.x) * kPoseVals;
+  double *part = scratch.partials + ((size_t)iy * kMaxBlocksPerItem + bx) * kPoseVals;
   if (tid < NV) {
     double s = sred[0][tid];
 #pragma unroll
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   // fence (cumulative over everything it observed through the barrier) and takes the ticket.  Fencing from every
   // thread costs a MEMBAR per warp and was 1/3 of the kernel's stall samples.
   __syncthreads();
-  int *cnt = scratch.counters + blockIdx.y * 4;
+  int *cnt = scratch.counters + iy * 4;
   if (tid == 0) {
     atomicAdd(cnt + 0, scnt[0]);
     atomicAdd(cnt + 1, scnt[1]);
@@ -509,8 +521,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   if (!s_last) return;
 
   // ---- last CTA of the item: ordered sum of the partials, publish to the host ---------------------------
-  EvalResult *res = results + blockIdx.y;
-  const double *pbase = scratch.partials + (size_t)blockIdx.y * kMaxBlocksPerItem * kPoseVals;
+  EvalResult *res = results + iy;
+  const double *pbase = scratch.partials + (size_t)iy * kMaxBlocksPerItem * kPoseVals;
   // 128 threads: PARTS interleaved groups per value; every thread first issues ALL its loads (independent, one L2
   // latency in total instead of one per partial) and then adds them in CTA order — the order is fixed, so the result
   // is bit-reproducible for a given launch geometry.
@@ -552,22 +564,29 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
 }
 
 template <int MODE, int CAP>
-cudaError_t launch_cap(const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results, unsigned seq,
+cudaError_t launch_cap(const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results, unsigned seq,
                        cudaStream_t stream) {
   BatchT<CAP> b;
   for (int i = 0; i < nitems; i++) b.item[i] = batch.item[i];
-  eval_kernel<MODE, CAP><<<dim3(grid_x, nitems), kEvalThreads, 0, stream>>>(b, scratch, results, seq);
+  eval_kernel<MODE, CAP><<<total_ctas, kEvalThreads, 0, stream>>>(b, scratch, results, seq, nitems);
   return cudaGetLastError();
 }
 
+// The items travel in kernel-parameter space; the cost of a launch (host side and front end) grows with the size of the
+// parameter block (176 B per item), so the capacity is chosen close to the item count.
 template <int MODE>
-cudaError_t launch_mode(const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results, unsigned seq,
+cudaError_t launch_mode(const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results, unsigned seq,
                         cudaStream_t stream) {
-  if (nitems <= 1) return launch_cap<MODE, 1>(batch, nitems, grid_x, scratch, results, seq, stream);
-  if (nitems <= 8) return launch_cap<MODE, 8>(batch, nitems, grid_x, scratch, results, seq, stream);
-  if (nitems <= 16) return launch_cap<MODE, 16>(batch, nitems, grid_x, scratch, results, seq, stream);
-  if (nitems <= 32) return launch_cap<MODE, 32>(batch, nitems, grid_x, scratch, results, seq, stream);
-  return launch_cap<MODE, kMaxItemsPerLaunch>(batch, nitems, grid_x, scratch, results, seq, stream);
+  if (nitems <= 1) return launch_cap<MODE, 1>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 4) return launch_cap<MODE, 4>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 8) return launch_cap<MODE, 8>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 16) return launch_cap<MODE, 16>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 24) return launch_cap<MODE, 24>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 32) return launch_cap<MODE, 32>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 48) return launch_cap<MODE, 48>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 64) return launch_cap<MODE, 64>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  if (nitems <= 96) return launch_cap<MODE, 96>(batch, nitems, total_ctas, scratch, results, seq, stream);
+  return launch_cap<MODE, kMaxItemsPerLaunch>(batch, nitems, total_ctas, scratch, results, seq, stream);
 }
 
 }  // namespace
@@ -581,12 +600,12 @@ cudaError_t debug_times(unsigned long long *out8, int reset) {
 }
 #endif
 
-cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int grid_x, EvalScratch scratch, EvalResult *results_dev,
+cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream) {
-  if (nitems < 1 || nitems > kMaxItemsPerLaunch || grid_x < 1 || grid_x > kMaxBlocksPerItem) return cudaErrorInvalidValue;
-  if (mode == 0) return launch_mode<0>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
-  if (mode == 1) return launch_mode<1>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
-  return launch_mode<2>(batch, nitems, grid_x, scratch, results_dev, seq, stream);
+  if (nitems < 1 || nitems > kMaxItemsPerLaunch || total_ctas < nitems || total_ctas > nitems * kMaxBlocksPerItem) return cudaErrorInvalidValue;
+  if (mode == 0) return launch_mode<0>(batch, nitems, total_ctas, scratch, results_dev, seq, stream);
+  if (mode == 1) return launch_mode<1>(batch, nitems, total_ctas, scratch, results_dev, seq, stream);
+  return launch_mode<2>(batch, nitems, total_ctas, scratch, results_dev, seq, stream);
 }
 
 }  // namespace dslam

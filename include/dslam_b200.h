@@ -87,7 +87,11 @@ int dslam_frame_upload_batch(int n, dslam_frame *const *frames, const float *con
 int dslam_frame_build(dslam_frame *f, const float *B256);
 /* the same for n uploaded frames of one session in two kernel launches in total (per run of 64 frames of equal geometry);
  * stage_host bit 0 / bit 1 also fill the device-side staging copies of dIp / absSquaredGrad so that a following
- * dslam_frame_download is a plain D2H copy */
+ * dslam_frame_download is a plain D2H copy.
+ * stage_host bit 2 = asynchronous build: the kernels run on the session's pyramid stream, ordered behind everything queued
+ * on the session stream so far (the uploads of these frames, earlier tracking calls that read these frame objects), and every
+ * later call that takes one of these frames is ordered behind the build — but tracking calls on OTHER frames queued
+ * afterwards run concurrently with it.  This is how the pyramids of frame k+1 are built while frame k is being tracked. */
 int dslam_frame_build_batch(int n, dslam_frame *const *frames, const float *B256, int stage_host);
 /* asynchronous D2H into the reference's host layouts: host_dIp[l] = Eigen::Vector3f[w_l*h_l] (I,dx,dy AoS),
  * host_absgrad[l] = float[w_l*h_l]; either array (or single entries) may be NULL. */

@@ -110,3 +110,29 @@ def test_upload_batch_equals_single_uploads(session, oracle):
         dIp_o, abs_o = oracle.make_images(np.array(im), levels)
         _compare(fr, dIp_o, abs_o, levels, w, h)
         fr.close()
+
+
+def test_async_build_overlaps_tracking_and_stays_ordered(session, oracle):
+    """stage_host bit 2 (build on the pyramid stream): the pyramid, its host mirror and a tracking call on the frame are the
+    same bits as with a synchronous build; a tracking call on ANOTHER frame queued after the asynchronous build is unaffected;
+    re-uploading a frame whose asynchronous build may still be in flight is ordered behind it."""
+    from helpers import IDENT7, GpuCase, OracleCase
+
+    oc = OracleCase(oracle, "tiny", 5)
+    gc = GpuCase(session, oc, template="device")
+    c = oc.case
+    ref = gc.trk.trackNewestCoarse(gc.f_new, IDENT7, (0, 0), oc.levels - 1)          # synchronous baseline
+    levels, w, h = oc.levels, oc.w, oc.h
+    f2 = api.FrameHessian(session, w, h, levels)
+    for rep in range(3):
+        f2.upload(c["img_right"] if rep == 1 else c["img_new"])
+        api.build_frames([f2], stage_host=3, overlap=True)
+        other = gc.trk.trackNewestCoarse(gc.f_new, IDENT7, (0, 0), oc.levels - 1)    # other frame: runs beside the build
+        assert other[0] == ref[0] and np.array_equal(other[1], ref[1])
+        f2.download()
+        dIp_o, abs_o = oracle.make_images(c["img_right"] if rep == 1 else c["img_new"], levels)
+        _compare(f2, dIp_o, abs_o, levels, w, h)
+    got = gc.trk.trackNewestCoarse(f2, IDENT7, (0, 0), oc.levels - 1)                # the asynchronously built frame itself
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    f2.close()
+    gc.close()

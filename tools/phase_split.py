@@ -32,7 +32,7 @@ def pyr_only(k):
     kf = [i for i in range(st.n) if st.is_kf(i, k)]
     api.build_frames(left)
     if kf:
-        api.build_frames([st.f_right[i] for i in kf])
+        api.build_frames([st.f_right[i][v] for i in kf])
 
 
 def lm_only(k):
@@ -40,7 +40,7 @@ def lm_only(k):
     left = [st.f_new[i][v] for i in range(st.n)]
     kf = [i for i in range(st.n) if st.is_kf(i, k)]
     poses = np.stack([st.case_of[i]["pose_init"][v] for i in range(st.n)])
-    api.lm_batch(st.trk, left, poses, np.zeros((st.n, 2)), st.levels - 1, [st.trk[i] for i in kf], [st.f_right[i] for i in kf], np.ones(len(kf), np.float32))
+    api.lm_batch(st.trk, left, poses, np.zeros((st.n, 2)), st.levels - 1, [st.trk[i] for i in kf], [st.f_right[i][v] for i in kf], np.ones(len(kf), np.float32))
 
 
 for k in range(2):  # all pyramids exist before the LM-only pass
