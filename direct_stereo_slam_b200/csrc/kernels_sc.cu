@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__re
 // With a batch of queries the scan is a tall-skinny product D[rows x 32] = DB[rows x n_cells] * Q^T: 16 flop per DB
 // byte at 32 queries, which is ABOVE the fp32 ridge of the machine (~72 TFLOP/s / 6.5 TB/s = 11 flop/B), so the
 // batched scan is bound by the FFMA pipe, not by HBM, and the streaming kernel above (one LDS.128 per 8 FFMA, a
-// 5-step shuffle reduction per row and query) leaves it 5x short of that.  Here a CTA owns a tile of 256 DB rows:
-// a producer warp streams [256 rows x 32 cells] boxes of the DB (TMA, 128-byte swizzle) and the matching
+// 5-step shuffle reduction per row and query) leaves it 5x short of that.  Here a CTA works on tiles of 256 DB rows:
+// a producer warp streams [4 x 64 rows x 32 cells] boxes of the DB (TMA, 128-byte swizzle) and the matching
 // [32 queries x 32 cells] box of the query batch through a 4-stage mbarrier pipeline; each of the 8 consumer warps
 // owns 128 rows x 8 queries, a lane 4 rows x 8 queries = 32 accumulators.  Per 4 cells a lane issues 4 LDS.128 of
 // its rows (conflict-free through the swizzle) + 8 broadcast LDS.128 of the queries for 128 FFMA: 0.19 shared-memory
@@ -308,10 +308,42 @@ __device__ __forceinline__ void sc_tma_load_2d(void *dst, const CUtensorMap *map
 }
 __device__ __forceinline__ void sc_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); }
 
+// Work split: the database is cut into groups of 64 rows; CTA c owns the contiguous run of groups [c * gpc, (c+1) * gpc) and
+// walks it in tiles of up to 4 groups, so all CTAs carry the same load to within one group (a 256-row tile granularity
+// would leave 12 % of the machine idle at 100k rows / 148 SMs).  A partial last tile loads and multiplies only its groups.
+constexpr int kGroupRows = 64;
+constexpr int kGroupsPerTile = kTileRows / kGroupRows;
+constexpr int kGroupBytes = kGroupRows * kTileK * 4;  // 8 KB per TMA box
+
+// One pipeline stage (32 cells) of a tile with NG row groups: per 4 cells a lane reads its NG rows (LDS.128, conflict-free
+// through the swizzle) and the 8 queries of its warp (broadcast LDS.128).  Packed FP32 FMAs (FFMA2, sm_100: two FMAs on a
+// 64-bit register pair per instruction); the pairs run along the cell index — (a.x, a.y) * (b.x, b.y) are adjacent registers
+// of the LDS.128 results — into an even-cell and an odd-cell partial sum per (row, query), added at the end of the tile.
+// Measured: 10 % faster than scalar FFMA (same FMA pipe — a 3-register FFMA issues every other cycle per sub-partition,
+// 64 lanes / clock / SM — but half the issue slots).
+template <int NG>
+__device__ __forceinline__ void sc_tile_stage(const float4 *__restrict__ A, const float4 *__restrict__ B, int sw, float2 (&acc)[4][8]) {
+#pragma unroll
+  for (int k4 = 0; k4 < kTileK / 4; k4++) {
+    float4 a[NG];
+#pragma unroll
+    for (int i = 0; i < NG; i++) a[i] = A[(size_t)i * kGroupRows * (kTileK / 4) + (k4 ^ sw)];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float4 b = B[j * (kTileK / 4) + k4];
+#pragma unroll
+      for (int i = 0; i < NG; i++) {
+        acc[i][j] = __ffma2_rn(make_float2(a[i].x, a[i].y), make_float2(b.x, b.y), acc[i][j]);
+        acc[i][j] = __ffma2_rn(make_float2(a[i].z, a[i].w), make_float2(b.z, b.w), acc[i][j]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTileThreads, 1)
     sc_scan_tile_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_q, const float *__restrict__ keys,
                         const int *__restrict__ ids, int n_rows, int n_cells, int key_dim, const float *__restrict__ q_keys, int nqc,
-                        float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch) {
+                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-B alignment
   float *sA = reinterpret_cast<float *>(base);
@@ -321,7 +353,10 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   uint64_t *empty = full + kTileStages;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
+  const int g_begin = blockIdx.x * groups_per_cta;
+  const int g_end = min(g_begin + groups_per_cta, n_groups);
+  const int row_end = min(g_end * kGroupRows, n_rows);
   const int n_chunks = (n_cells + kTileK - 1) / kTileK;
   if (tid == 0) {
     for (int s = 0; s < kTileStages; s++) {
@@ -333,15 +368,17 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   __syncthreads();
 
   if (warp == kTileConsumers / 32) {
-    // ---- producer warp: one lane walks (tile, chunk) and keeps kTileStages boxes in flight ----
+    // ---- producer warp: one lane walks (tile, chunk) and keeps kTileStages stages in flight ----
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int g0 = g_begin; g0 < g_end; g0 += kGroupsPerTile) {
+        const int ng = min(kGroupsPerTile, g_end - g0);
         for (int c = 0; c < n_chunks; c++, it++) {
           const int s = it % kTileStages;
           sc_mbar_wait(&empty[s], ((it / kTileStages) & 1) ^ 1);  // passes immediately on the first lap
-          sc_mbar_expect_tx(&full[s], kStageABytes + kStageBBytes);
-          sc_tma_load_2d(reinterpret_cast<unsigned char *>(sA) + (size_t)s * kStageABytes, &map_db, c * kTileK, t * kTileRows, &full[s]);
+          sc_mbar_expect_tx(&full[s], ng * kGroupBytes + kStageBBytes);
+          unsigned char *dst = reinterpret_cast<unsigned char *>(sA) + (size_t)s * kStageABytes;
+          for (int g = 0; g < ng; g++) sc_tma_load_2d(dst + (size_t)g * kGroupBytes, &map_db, c * kTileK, (g0 + g) * kGroupRows, &full[s]);
           sc_tma_load_2d(reinterpret_cast<unsigned char *>(sB) + (size_t)s * kStageBBytes, &map_q, c * kTileK, 0, &full[s]);
         }
       }
@@ -350,42 +387,31 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   }
 
   // ---- consumers ----
-  const int qt = warp & 3, rh = warp >> 2;  // 8 queries x 128 rows per warp
-  const int q_own = lane, sub = warp;       // top-K ownership: query q_own, rows sub*32 .. sub*32+31 of every tile
-  const int sw = lane & 7;                  // 128-B swizzle: 16-B chunk index ^ (row & 7); row & 7 == lane & 7 for all 4 rows of a lane
+  // warp = (query octet qt, row half rh); lane owns rows g * 64 + rh * 32 + lane of the tile's groups g = 0..3
+  const int qt = warp & 3, rh = warp >> 2;
+  const int q_own = lane, sub = warp;  // top-K ownership: query q_own, tile rows sub*32 .. sub*32+31
+  const int sw = lane & 7;             // 128-B swizzle: 16-B chunk index ^ (row & 7); row & 7 == lane & 7 for all rows of a lane
   TopK top;
   top.init();
   int it = 0;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    float acc[4][8];
+  for (int g0 = g_begin; g0 < g_end; g0 += kGroupsPerTile) {
+    const int ng = min(kGroupsPerTile, g_end - g0);
+    float2 acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+      for (int j = 0; j < 8; j++) acc[i][j] = make_float2(0.f, 0.f);
     for (int c = 0; c < n_chunks; c++, it++) {
       const int s = it % kTileStages;
       sc_mbar_wait(&full[s], (it / kTileStages) & 1);
       const float4 *A = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sA) + (size_t)s * kStageABytes) +
-                        (size_t)(rh * 128 + lane) * (kTileK / 4);
+                        (size_t)(rh * 32 + lane) * (kTileK / 4);
       const float4 *B = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sB) + (size_t)s * kStageBBytes) +
                         (size_t)(qt * 8) * (kTileK / 4);
-#pragma unroll
-      for (int k4 = 0; k4 < kTileK / 4; k4++) {
-        float4 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = A[(size_t)i * 32 * (kTileK / 4) + (k4 ^ sw)];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const float4 b = B[j * (kTileK / 4) + k4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
-            acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
-            acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
-            acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
-          }
-        }
-      }
+      if (ng == 4) sc_tile_stage<4>(A, B, sw, acc);
+      else if (ng == 3) sc_tile_stage<3>(A, B, sw, acc);  // partial last tile of the CTA's run: only its ng groups were loaded
+      else if (ng == 2) sc_tile_stage<2>(A, B, sw, acc);
+      else sc_tile_stage<1>(A, B, sw, acc);
       __syncwarp();
       if (lane == 0) sc_mbar_arrive(&empty[s]);
     }
@@ -394,18 +420,18 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     for (int i = 0; i < 4; i++) {
       float d[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) d[j] = (1.0f - acc[i][j] / sc_width) / 2.0f;
-      float4 *dst = reinterpret_cast<float4 *>(sD + (size_t)(rh * 128 + i * 32 + lane) * kDistStride + qt * 8);
+      for (int j = 0; j < 8; j++) d[j] = (1.0f - (acc[i][j].x + acc[i][j].y) / sc_width) / 2.0f;
+      float4 *dst = reinterpret_cast<float4 *>(sD + (size_t)(i * kGroupRows + rh * 32 + lane) * kDistStride + qt * 8);
       dst[0] = make_float4(d[0], d[1], d[2], d[3]);
       dst[1] = make_float4(d[4], d[5], d[6], d[7]);
     }
     sc_consumer_sync();
     if (q_own < nqc) {
-      const int row0 = t * kTileRows + sub * 32;
+      const int row0 = g0 * kGroupRows + sub * 32;
 #pragma unroll 4
       for (int r = 0; r < 32; r++) {
         const int row = row0 + r;
-        if (row >= n_rows) break;
+        if (row >= row_end) break;
         bool ok = __ldg(ids + row) < max_id;
         if (ok && ringkey_thres >= 0.f) ok = flann_l2(q_keys + (size_t)q_own * key_dim, keys + (size_t)row * key_dim, key_dim) < ringkey_thres;
         if (ok) top.insert(make_key(sD[(size_t)(sub * 32 + r) * kDistStride + q_own], row));
@@ -680,7 +706,7 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
   const cuuint64_t gstride[1] = {(cuuint64_t)n_cells * sizeof(float)};
   {
     const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)n_rows};
-    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kTileRows};
+    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kGroupRows};
     if (enc(&map_db, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sigs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
@@ -692,8 +718,10 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
+  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
+  const int groups_per_cta = (n_groups + grid - 1) / grid;
   sc_scan_tile_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(map_db, map_q, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
-                                                                      max_id, sc_width, scratch);
+                                                                      max_id, sc_width, groups_per_cta, scratch);
   return cudaGetLastError();
 }
 
@@ -717,7 +745,8 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
     const bool tiles = n_rows > 0 && (flavour == 2 || (flavour == 0 && nqc > 8 && n_tiles * 2 >= num_sms()));
     int grid = num_sms();
     if (tiles) {
-      if (grid > n_tiles) grid = n_tiles;
+      const int n_groups = (n_rows + 63) / 64;
+      if (grid > n_groups) grid = n_groups;
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
                                            ringkey_thres, max_id, sc_width, scratch, grid, stream);
       if (e != cudaSuccess) return e;
