@@ -11,8 +11,12 @@ kernel launches, and every Levenberg-Marquardt round of all pose trackers AND sc
 residual / Jacobian kernel.  Workload: synthetic stereo pairs 1232x368 (KITTI 1241x376 after the calibration crop), 2000 active
 points -> ~10k template pixels at level 0, 5 pyramid levels.
 
+The steps are software-pipelined like a live system that receives image k+1 while it tracks image k: the pyramids of step k+1
+are built on the session's pyramid stream while the LM rounds of step k run (K timed steps = K pyramid builds + K tracking passes).
+
   value  : frames/s with the raw images already resident in HBM (pyramid build + tracking + scale optimisation timed)
-  e2e    : the same through the C ABI with HOST buffers: pinned-host images uploaded inside the timed region, the left
+  e2e    : the same through the C ABI with HOST buffers: pinned-host images (capture arenas: one H2D per arena and step)
+           uploaded inside the timed region, the left
            pyramid mirrored back into the reference's host layouts for the untouched DSO code that reads it (level-0 dI on
            every frame — ImmaturePoint::traceOn; all levels of dIp + absSquaredGrad on keyframes — pixel selector, BA,
            LoopHandler), poses / scales returned to the host
@@ -56,14 +60,16 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the pose kernel from the committed ncu --set full capture (profiles/), or None."""
+    """(dram bytes per launch of the pose kernel, where that figure comes from) from the committed ncu --set full capture
+    (profiles/), or (None, None)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("pose_eval_dram_bytes_per_launch")
+            t = json.load(open(p))
+            return t.get("pose_eval_dram_bytes_per_launch"), t.get("source")
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
 class ClockSampler:
@@ -172,6 +178,7 @@ class GpuStreams:
         ref.close()
         session.sync()
         self.pc_n0 = [t.ref_level(0)[0].size for t in self.trk]
+        self.plans = {}
 
     def upload_inputs(self):
         """Raw images into HBM (outside the timed region of the device-resident measurement)."""
@@ -185,24 +192,38 @@ class GpuStreams:
     def is_kf(self, i, k):
         return (k + i) % self.kf_every == 0
 
+    def _plans(self, k):
+        """Pointer arrays / result buffers of step k's calls, built once per (frame parity, keyframe phase)."""
+        key = (k & 1, k % self.kf_every)
+        if key not in self.plans:
+            api, v = self.api, k & 1
+            kf = [i for i in range(self.n) if self.is_kf(i, k)]
+            left = [self.f_new[i][v] for i in range(self.n)]
+            right = [self.f_right[i][v] for i in kf]
+            self.plans[key] = {
+                "kf": kf, "left": left,
+                "left_fb": api.FrameBatchPlan(left, [self.h_new[i][v] for i in range(self.n)]),
+                "right_fb": api.FrameBatchPlan(right, [self.h_right[i] for i in kf]) if kf else None,
+                "lm": api.LmBatchPlan(self.trk, left, [self.trk[i] for i in kf], right, self.levels - 1),
+                "poses": np.stack([self.case_of[i]["pose_init"][v] for i in range(self.n)]),
+                "affs": np.zeros((self.n, 2)), "scales": np.ones(len(kf), np.float32)}
+        return self.plans[key]
+
     def _prepare(self, k, e2e):
         """Inputs + pyramids of step k: (e2e: one H2D per capture arena,) two launches for all left pyramids, two for the right
         pyramids of the step's keyframes — on the session's pyramid stream, so that the LM rounds queued next (on the frames of
         the PREVIOUS step) run concurrently — and (e2e) the host mirrors start draining on the frames' copy streams."""
-        api = self.api
-        v = k & 1
-        left = [self.f_new[i][v] for i in range(self.n)]
-        kf = [i for i in range(self.n) if self.is_kf(i, k)]
-        right = [self.f_right[i][v] for i in kf]
+        P = self._plans(k)
+        left = P["left"]
         if e2e:
-            for i in range(self.n):
-                left[i].wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
-            api.upload_frames(left, [self.h_new[i][v] for i in range(self.n)])
-            if kf:
-                api.upload_frames(right, [self.h_right[i] for i in kf])
-        api.build_frames(left, stage_host=3 if e2e else 0, overlap=True)
-        if right:
-            api.build_frames(right, overlap=True)
+            for f in left:
+                f.wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
+            P["left_fb"].upload()
+            if P["right_fb"]:
+                P["right_fb"].upload()
+        P["left_fb"].build(stage_host=3 if e2e else 0, overlap=True)
+        if P["right_fb"]:
+            P["right_fb"].build(overlap=True)
         if e2e:
             for i in range(self.n):
                 if self.is_kf(i, k):
@@ -215,17 +236,11 @@ class GpuStreams:
         """One stereo frame of every stream.  Software pipeline over the steps, like a live system that receives image k+1
         while it tracks image k: the pyramids of step k+1 are built (pyramid stream) while the LM rounds of step k run, so
         every call does one pyramid build and one tracking pass — K steps = K builds + K tracking passes."""
-        api = self.api
-        v = k & 1
         if getattr(self, "prepared", None) != (k, e2e):
             self._prepare(k, e2e)        # first step of a run: nothing to overlap with
         self._prepare(k + 1, e2e)        # next frames: H2D + pyramids (+ mirrors) overlap the LM rounds below
-        left = [self.f_new[i][v] for i in range(self.n)]
-        kf = [i for i in range(self.n) if self.is_kf(i, k)]
-        right = [self.f_right[i][v] for i in kf]
-        poses = np.stack([self.case_of[i]["pose_init"][v] for i in range(self.n)])
-        ok, poses, affs, last, rmse, scales = api.lm_batch(self.trk, left, poses, np.zeros((self.n, 2)), self.levels - 1,
-                                                           [self.trk[i] for i in kf], right, np.ones(len(kf), np.float32))
+        P = self._plans(k)
+        ok, poses, affs, last, rmse, scales = P["lm"].run(P["poses"], P["affs"], P["scales"])
         # e2e: the host mirrors keep draining (per-frame copy streams) while the next step computes; they are waited for when
         # their frame object is reused (two steps later) and by drain() before the clock stops
         return ok, poses, scales, rmse
@@ -527,7 +542,7 @@ def main():
                         "d2h_bytes_per_step": streams.d2h_bytes() * world},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "eval_kernel (fused calcRes*+calcGSSSE* of all pose / scale items of an LM round)", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1], "peak_source": peak_src,
                              "launches_timed": p["launches"], "avg_launch_us": (p["ms"] * 1e3 / p["launches"]) if p["launches"] else None,
                              "points_per_launch": (p["points"] / p["launches"]) if p["launches"] else None,
                              "scale_kernel_gbs": (BYTES_PER_POINT * prof["scale"]["points"] / (prof["scale"]["ms"] * 1e-3) / 1e9)

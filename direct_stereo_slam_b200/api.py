@@ -678,6 +678,69 @@ def lm_batch(pose_trackers, pose_frames, poses, affs, coarsestLvl, scale_tracker
     return ok[:n].astype(bool), poses, affs, last, rmse[:m], scales
 
 
+class LmBatchPlan:
+    """A fixed set of tracking + scale jobs that is run again and again (the streams of a capture rig): the pointer arrays and
+    result buffers of lm_batch are built once.  run() = dslam_lm_batch; same results as lm_batch()."""
+
+    def __init__(self, pose_trackers, pose_frames, scale_trackers, scale_frames, coarsestLvl, minResForAbort=None):
+        self.n, self.m = len(pose_trackers), len(scale_trackers)
+        n, m = self.n, self.m
+        self.lib = (pose_trackers or scale_trackers)[0].lib
+        self.pose_trackers = list(pose_trackers)
+        self._keep = (list(pose_frames), list(scale_trackers), list(scale_frames))
+        self.pc = (C.c_void_p * max(n, 1))(*[t.p for t in pose_trackers])
+        self.pf = (C.c_void_p * max(n, 1))(*[f.p for f in pose_frames])
+        self.sc = (C.c_void_p * max(m, 1))(*[t.p for t in scale_trackers])
+        self.sf = (C.c_void_p * max(m, 1))(*[f.p for f in scale_frames])
+        self.expo = np.ascontiguousarray([f.ab_exposure for f in pose_frames] or [1.0], np.float32)
+        self.mr = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+        self.lvl = coarsestLvl
+        self.poses = np.zeros((n, 7))
+        self.affs = np.zeros((n, 2))
+        self.last = np.empty((n, 5))
+        self.flow = np.empty((n, 3))
+        self.ok = np.zeros(max(n, 1), np.int32)
+        self.scales = np.zeros(m, np.float32)
+        self.rmse = np.empty(max(m, 1), np.float32)
+
+    def run(self, poses, affs, scales):
+        n, m = self.n, self.m
+        if n:
+            self.poses[...] = poses
+            self.affs[...] = affs
+        if m:
+            self.scales[...] = scales
+        check(self.lib.dslam_lm_batch(n, self.pc, self.pf, _fp(self.expo), _dp(self.poses) if n else None, _dp(self.affs) if n else None, self.lvl,
+                                      _dp(self.mr), _dp(self.last) if n else None, _dp(self.flow) if n else None, _ip(self.ok), m, self.sc, self.sf,
+                                      _fp(self.scales) if m else None, self.lvl, _fp(self.rmse)))
+        for i, t in enumerate(self.pose_trackers):
+            t.lastFlowIndicators = self.flow[i]
+        return self.ok[:n].astype(bool), self.poses, self.affs, self.last, self.rmse[:m], self.scales
+
+
+class FrameBatchPlan:
+    """A fixed set of frames whose images arrive from fixed host buffers: pointer arrays built once.
+    upload() = dslam_frame_upload_batch, build() = dslam_frame_build_batch."""
+
+    def __init__(self, frames, images=None):
+        self.frames = list(frames)
+        self.lib = frames[0].lib
+        self.n = len(frames)
+        self.fa = (C.c_void_p * self.n)(*[f.p for f in frames])
+        self.images = None
+        if images is not None:
+            self.images = [np.ascontiguousarray(im, np.float32) for im in images]
+            for f, im in zip(frames, self.images):
+                assert im.size == f.w * f.h
+            self.ia = (C.c_void_p * self.n)(*[im.ctypes.data for im in self.images])
+
+    def upload(self):
+        check(self.lib.dslam_frame_upload_batch(self.n, self.fa, self.ia))
+
+    def build(self, stage_host=0, overlap=False):
+        check(self.lib.dslam_frame_build_batch(self.n, self.fa, None, stage_host | (4 if overlap else 0)))
+
+
 def upload_frames(frames, images):
     """Raw images of n frames (dslam_frame_upload_batch): images that lie back to back in host memory go up as one transfer."""
     n = len(frames)

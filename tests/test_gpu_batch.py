@@ -68,6 +68,12 @@ def test_lm_batch_equals_separate_calls(session, oracle):
     # one launch per round: no more launches than the longest machine needs evaluations
     worst = max(len(g.trk.trace()) for g in gcs) + 60
     assert launches <= worst
+    # the reusable plan objects (pointer arrays built once) are the same call
+    plan = api.LmBatchPlan(trk, left, [trk[1], trk[2]], [gcs[1].f_right, gcs[2].f_right], ocs[0].levels - 1)
+    for _ in range(2):
+        ok2, poses2, affs2, last2, rmse2, scales2 = plan.run(np.tile(IDENT7, (3, 1)), np.zeros((3, 2)), [1.0, 1.0])
+        assert np.array_equal(ok2, ok) and np.array_equal(poses2, poses) and np.array_equal(affs2, affs)
+        assert np.array_equal(rmse2, rmse) and np.array_equal(scales2, scales)
     # and against the oracle
     for i, oc in enumerate(ocs):
         ok_o, pose_o, aff_o, _, _ = oc.trk.track_newest_coarse(1, IDENT7, (0, 0), oc.levels - 1)

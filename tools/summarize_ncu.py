@@ -70,24 +70,37 @@ def full_report(rep, title, out_md):
 
 
 if __name__ == "__main__":
+    # processes whichever captures are present under gpurun_out/ (scratch); summaries of absent ones are left as committed
     g = os.path.join(ROOT, "gpurun_out")
     p = os.path.join(ROOT, "profiles")
     os.makedirs(p, exist_ok=True)
-    launch_list(os.path.join(g, "launches_r01c.csv"), "r01 launch list: bench.py --streams 32 --steps 2 --warmup 3 (KITTI 1232x368, 8 LM groups, DMMA eval kernel)",
-                os.path.join(p, "r01_launches.md"))
-    ev = full_report(os.path.join(g, "prof_eval_r01c.ncu-rep"), "r01 eval_kernel (fused residual / Jacobian / DMMA normal equations) inside bench.py, 32 streams / 8 groups",
-                     os.path.join(p, "r01_eval_kernel.md"))
-    full_report(os.path.join(g, "prof_eval128_dmma.ncu-rep"), "r01 eval_kernel, 128 pose items of 9.9k points in one launch (tools/one_eval.py kitti 128)",
-                os.path.join(p, "r01_eval_kernel_128items.md"))
-    py = full_report(os.path.join(g, "prof_pyr_r01c.ncu-rep"), "r01 pyramid kernels inside bench.py (32 frames per launch)", os.path.join(p, "r01_pyramid_kernels.md"))
-    sc = full_report(os.path.join(g, "prof_sc_r01c.ncu-rep"), "r01 Scan-Context kernels, 100k descriptors (tools/sc_sweep.py; first launches: Q=1)", os.path.join(p, "r01_scan_context_kernels.md"))
-    traffic = {}
-    tr = [to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]) for d in ev if "dram__bytes_read.sum" in d]
-    if tr:
-        traffic["pose_eval_dram_bytes_per_launch"] = sum(tr) / len(tr)
-        traffic["source"] = "profiles/r01_eval_kernel.md (mean over %d captured launches of the eval kernel inside bench.py --streams 32)" % len(tr)
-    for d in py + sc:
-        if "dram__bytes_read.sum" in d:
-            traffic.setdefault("other", {}).setdefault(d["kernel"], []).append(to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]))
-    json.dump(traffic, open(os.path.join(p, "traffic.json"), "w"), indent=1)
+    WANT.extend(["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+                 "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+                 "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "dram__bytes_read.sum.per_second"])
+
+    def have(name):
+        return os.path.exists(os.path.join(g, name))
+
+    traffic_path = os.path.join(p, "traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    if have("launches_r01d.csv"):
+        launch_list(os.path.join(g, "launches_r01d.csv"), "r01 launch list: bench.py --streams 32 --steps 2 --warmup 3 (KITTI 1232x368, flat-grid DMMA eval kernel, "
+                    "pyramids on the overlap stream)", os.path.join(p, "r01_launches.md"))
+    if have("prof_eval_r01d.ncu-rep"):
+        ev = full_report(os.path.join(g, "prof_eval_r01d.ncu-rep"), "r01 eval_kernel (fused residual / Jacobian / DMMA normal equations, flat grid) inside bench.py, "
+                         "32 streams / 8 groups", os.path.join(p, "r01_eval_kernel.md"))
+        tr = [to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"]) for d in ev if "dram__bytes_read.sum" in d]
+        if tr:
+            traffic["pose_eval_dram_bytes_per_launch"] = sum(tr) / len(tr)
+            traffic["source"] = "profiles/r01_eval_kernel.md (mean over %d captured launches of the eval kernel inside bench.py --streams 32)" % len(tr)
+    if have("prof_eval128_r01d.ncu-rep"):
+        full_report(os.path.join(g, "prof_eval128_r01d.ncu-rep"), "r01 eval_kernel, 128 pose items of 9.9k points in one launch (tools/one_eval.py kitti 128)",
+                    os.path.join(p, "r01_eval_kernel_128items.md"))
+    if have("s3_sc_tile2.ncu-rep"):
+        sc = full_report(os.path.join(g, "s3_sc_tile2.ncu-rep"), "r01 sc_scan_tile_kernel (register-blocked TMA tile scan, FFMA2, balanced 64-row groups), 100k descriptors x 32 "
+                         "queries (tools/sc_one.py 100000 32 tile)", os.path.join(p, "r01_sc_tile_kernel.md"))
+        for d in sc:
+            if "dram__bytes_read.sum" in d:
+                traffic.setdefault("other", {})[d["kernel"]] = [to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])]
+    json.dump(traffic, open(traffic_path, "w"), indent=1)
     print(json.dumps(traffic, indent=1))
