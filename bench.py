@@ -506,8 +506,21 @@ def main():
     for k in range(min(args.steps, 5)):
         streams.step(k, False)
     prof = session.profile_read()
-    session.profile(False)
     counters = [t.counters() for t in streams.trk]
+    # the same kernel with the GPU to itself: one launch of 128 pose hypotheses of one stream's level-0 template (1.27 M points),
+    # CUDA events around the launch — what the kernel does when it is not queueing behind 7 other lanes and the pyramid stream
+    session.sync()
+    rng = np.random.default_rng(5)
+    hyp = np.tile(streams.case_of[0]["pose_init"][0], (128, 1))
+    hyp[:, 4:] += rng.normal(0, 0.01, (128, 3))
+    hyp_aff = rng.normal(0, [0.01, 1.0], (128, 2))
+    for _ in range(3):
+        streams.trk[0].calcResAndGSPose(streams.f_new[0][0], 0, hyp, hyp_aff)
+    session.profile_read()
+    for _ in range(10):
+        streams.trk[0].calcResAndGSPose(streams.f_new[0][0], 0, hyp, hyp_aff)
+    alone = session.profile_read()["pose"]
+    session.profile(False)
 
     if dist is not None:
         import torch
@@ -546,7 +559,15 @@ def main():
                              "launches_timed": p["launches"], "avg_launch_us": (p["ms"] * 1e3 / p["launches"]) if p["launches"] else None,
                              "points_per_launch": (p["points"] / p["launches"]) if p["launches"] else None,
                              "scale_kernel_gbs": (BYTES_PER_POINT * prof["scale"]["points"] / (prof["scale"]["ms"] * 1e-3) / 1e9)
-                             if prof["scale"]["ms"] > 0 else None},
+                             if prof["scale"]["ms"] > 0 else None,
+                             "note": "achieved / frac are the launches of the timed configuration: 8 LM lanes and the pyramid stream share the GPU, "
+                                     "so the event-timed duration of a launch is mostly queueing; kernel_alone is the same kernel in one launch of "
+                                     "128 hypotheses x the level-0 template with the GPU to itself",
+                             "kernel_alone": ({"launches_timed": alone["launches"], "points_per_launch": alone["points"] / alone["launches"],
+                                               "avg_launch_us": alone["ms"] * 1e3 / alone["launches"],
+                                               "achieved": BYTES_PER_POINT * alone["points"] / (alone["ms"] * 1e-3) / 1e9,
+                                               "frac": BYTES_PER_POINT * alone["points"] / (alone["ms"] * 1e-3) / 1e9 / peak}
+                                              if alone["launches"] and alone["ms"] > 0 else None)},
                 "clocks": clocks,
                 "host_ms_per_step": {k: (v / (args.steps + warmup) if k != "launches" else v) for k, v in host_times.items()},
                 "lm": {"evals_per_frame": float(np.sum([c["evals"] for c in counters])) / (args.streams * (2 * warmup + 2 * args.steps + min(args.steps, 5))),

@@ -68,3 +68,16 @@ def test_library_is_in_tree_and_has_no_link_time_cuda_driver_dependency():
     assert os.path.dirname(_lib.LIB_PATH) == os.path.join(ROOT, "direct_stereo_slam_b200")
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "libnccl" not in out and "libcudart" not in out
+
+
+def test_argument_validation_needs_no_device():
+    """Bad arguments are rejected before anything touches CUDA (same error behaviour with and without a GPU)."""
+    lib = _lib.load()
+    assert lib.dslam_sc_set_scan_kernel(3) == _lib.EINVAL and b"flavour" in lib.dslam_last_error()
+    assert lib.dslam_sc_set_scan_kernel(-1) == _lib.EINVAL
+    for f in (1, 2, 0):  # process-wide knob, no device needed; leave it on "auto"
+        assert lib.dslam_sc_set_scan_kernel(f) == 0
+    assert lib.dslam_frame_upload_batch(0, None, None) == _lib.EINVAL
+    assert lib.dslam_frame_upload_batch(2, None, None) == _lib.EINVAL
+    assert lib.dslam_frame_build_batch(0, None, None, 4) == _lib.EINVAL
+    assert lib.dslam_frame_upload(None, None) == _lib.EINVAL
