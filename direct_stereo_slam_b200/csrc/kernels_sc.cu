@@ -742,7 +742,8 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
     // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
     // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
     const int flavour = sc_scan_flavour();
-    const bool tiles = n_rows > 0 && (flavour == 2 || (flavour == 0 && nqc > 8 && n_tiles * 2 >= num_sms()));
+    // (a shard smaller than one 64-row TMA box always takes the streaming kernel)
+    const bool tiles = n_rows >= 64 && (flavour == 2 || (flavour == 0 && nqc > 8 && n_tiles * 2 >= num_sms()));
     int grid = num_sms();
     if (tiles) {
       const int n_groups = (n_rows + 63) / 64;

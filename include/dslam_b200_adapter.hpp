@@ -65,6 +65,22 @@ class FramePyramids {
     const float *B = (HCalib != nullptr && gamma_weights) ? HCalib->B : nullptr;  // HessianBlocks.cpp:182-188
     check(dslam_frame_make_images(f, color, B, dIp, ag), "dslam_frame_make_images");
   }
+  // The same, but the pyramid is built on the session's pyramid stream (dslam_frame_build_batch, stage_host bit 2): call it
+  // for the image that has just arrived BEFORE tracking the previous frame — the build then runs beside those LM rounds —
+  // and every later call that takes `fh` is ordered behind it automatically.
+  template <class CalibHessian>
+  void makeImagesOverlapped(FrameHessian *fh, const float *color, CalibHessian *HCalib, bool gamma_weights) {
+    dslam_frame *f = acquire(fh);
+    float *dIp[DSLAM_MAX_LEVELS] = {nullptr}, *ag[DSLAM_MAX_LEVELS] = {nullptr};
+    for (int l = 0; l < levels_; l++) {
+      dIp[l] = reinterpret_cast<float *>(fh->dIp[l]);
+      ag[l] = fh->absSquaredGrad[l];
+    }
+    const float *B = (HCalib != nullptr && gamma_weights) ? HCalib->B : nullptr;
+    check(dslam_frame_upload(f, color), "dslam_frame_upload");
+    check(dslam_frame_build_batch(1, &f, B, 1 | 2 | 4), "dslam_frame_build_batch");
+    check(dslam_frame_download(f, dIp, ag), "dslam_frame_download");
+  }
   void wait_host(FrameHessian *fh) { check(dslam_frame_wait_host(at(fh)), "dslam_frame_wait_host"); }
   // call from FrameHessian::~FrameHessian / FrameHessian::release
   void release(FrameHessian *fh) {

@@ -72,7 +72,8 @@ int main() {
       fh[k].absSquaredGrad[l] = store.back().data();
     }
     render(k == 0 ? 0.f : (k == 1 ? 2.f : 6.f), img);  // disparity f*b/z = 200*0.3/10 = 6 px for the right camera
-    frames.makeImages(&fh[k], img.data(), &calib, false);
+    if (k == 1) frames.makeImagesOverlapped(&fh[k], img.data(), &calib, false);  // the new frame: built on the pyramid stream
+    else frames.makeImages(&fh[k], img.data(), &calib, false);
     frames.wait_host(&fh[k]);
   }
   dslam_b200::ActivePoints pts;
