@@ -236,3 +236,64 @@ def test_generate_matches_oracle(session, oracle):
     idx, diff = db.query(sig)
     assert idx[0] == 3 and diff[0] < 0.1
     db.close()
+
+
+def _lidar_cloud(rng, n=5000):
+    """'Imitated LiDAR' cloud of SURVEY.md §8d config 2: n points inside a 40 m sphere; every place has its own anisotropy and a few
+    dense structures so that ring keys and signatures differ between places."""
+    sig = rng.uniform(4.0, 22.0, 3)
+    pts = rng.normal(0, sig, (n, 3))
+    for _ in range(int(rng.integers(2, 6))):
+        k = int(rng.integers(100, 600))
+        pts[rng.integers(0, n, k)] = rng.normal(rng.uniform(-25, 25, 3), rng.uniform(0.5, 3.0, 3), (k, 3))
+    return pts
+
+
+def test_loop_closure_chain_malaga_config(session, oracle):
+    """BASELINE configs[2], loop-closure half: 2000 keyframes' clouds -> ScanContext::generate on the device (appended device to
+    device) -> 50 revisits (database clouds + N(0, 0.2 m) jitter) -> the reference's two stages, search_ringkey (k = 3, squared L2 <
+    0.1) then search_sc over its candidates.  Every stage equals the oracle run on the same descriptors: candidates and ring-key
+    distances, winner and sector-cosine distance, bit for bit; and the brute-force scan (no ring-key stage) finds the revisits."""
+    rng = np.random.default_rng(7)
+    n_db, n_q = 2000, 50
+    db = api.ScanContextDB(session, n_db)
+    clouds, keys, sigs = [], [], []
+    for i in range(n_db):
+        pts = _lidar_cloud(rng)
+        rk, sig, _, _ = db.generate(pts, append=True)
+        clouds.append(pts if i < n_q * 7 else None)
+        keys.append(rk)
+        sigs.append(sig)
+    keys, sigs = np.stack(keys), np.stack(sigs)
+    assert len(db) == n_db
+    rows = rng.choice(n_q * 7, n_q, replace=False)
+    q_keys, q_sigs = [], []
+    for r in rows:
+        rk, sig, _, _ = db.generate(clouds[r] + rng.normal(0, 0.2, clouds[r].shape))
+        q_keys.append(rk)
+        q_sigs.append(sig)
+    q_keys, q_sigs = np.stack(q_keys), np.stack(q_sigs)
+    assert len(db) == n_db  # generate without append leaves the database alone
+    cand, cdist = db.search_ringkey(q_keys, k=3, thres=0.1)
+    found_two_stage = 0
+    for q in range(n_q):
+        c_o, d_o = oracle.search_ringkey(q_keys[q], keys, k=3, thres=0.1)
+        got = cand[q][cand[q] >= 0]
+        assert np.array_equal(got, c_o) and np.array_equal(cdist[q, :len(c_o)].view(np.uint32), d_o.view(np.uint32))
+        if len(c_o) == 0:
+            continue
+        i_g, d_g = db.search_sc(q_sigs[q], cand[q])
+        i_o, dd_o = oracle.search_sc_dense(q_sigs[q], sigs, c_o)
+        assert i_g[0] == i_o and d_g[0] == np.float32(dd_o)
+        found_two_stage += int(i_g[0] == rows[q])
+    # exhaustive scan of the same queries (both scan kernels): bit-exact against the oracle, and it finds the places
+    idx_o, diff_o = _oracle_query(oracle, q_sigs, sigs)
+    for flavour in ("stream", "tile"):
+        db.set_scan_kernel(flavour)
+        idx, diff = db.query(q_sigs)
+        assert np.array_equal(idx, idx_o) and np.array_equal(diff.view(np.uint32), diff_o.view(np.uint32))
+    db.set_scan_kernel("auto")
+    found_scan = int(np.sum(idx_o == rows))
+    print("revisits found: two-stage (FLANN-style k=3 ring-key gate) %d / %d, exhaustive scan %d / %d" % (found_two_stage, n_q, found_scan, n_q))
+    assert found_scan >= int(0.8 * n_q)
+    db.close()
