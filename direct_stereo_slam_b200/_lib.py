@@ -48,6 +48,7 @@ SIGNATURES = {
     "dslam_host_free": [vp],
     "dslam_frame_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],
     "dslam_frame_destroy": [vp],
+    "dslam_plan_eval_launch": [C.c_int, c_i, C.c_int, C.c_int, c_i, c_i, c_i],
     "dslam_frame_upload": [vp, c_f],
     "dslam_frame_upload_batch": [C.c_int, c_pp, c_pp],
     "dslam_frame_build": [vp, c_f],

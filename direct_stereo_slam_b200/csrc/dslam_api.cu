@@ -1019,6 +1019,22 @@ int dslam_debug_kernel_times(dslam_session *s, unsigned long long *out8, int res
 }
 #endif
 
+int dslam_plan_eval_launch(int n_items, const int *n_points, int num_sms, int lanes, int *nblocks, int *cta_begin, int *total_ctas) {
+  if (n_items < 1 || n_items > kMaxItemsPerLaunch || !n_points || !nblocks || !cta_begin || !total_ctas || num_sms < 1 || lanes < 1)
+    return fail(DSLAM_EINVAL, "bad argument");
+  std::vector<EvalItem> items((size_t)n_items);
+  for (int i = 0; i < n_items; i++) {
+    if (n_points[i] < 0) return fail(DSLAM_EINVAL, "negative point count");
+    items[i].n = n_points[i];
+  }
+  *total_ctas = assign_blocks(items.data(), n_items, num_sms, lanes);
+  for (int i = 0; i < n_items; i++) {
+    nblocks[i] = items[i].nblocks;
+    cta_begin[i] = items[i].cta_begin;
+  }
+  return DSLAM_OK;
+}
+
 int dslam_host_alloc(unsigned long long bytes, void **out) {
   if (!out) return fail(DSLAM_EINVAL, "null argument");
   DSLAM_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

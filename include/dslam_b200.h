@@ -66,6 +66,10 @@ int dslam_session_profile_read(dslam_session *s, double out[12]);
 /* host-side time split of the lock-step LM driver since the last call, in ms: out[0] LM algebra + item preparation,
  * out[1] kernel launches, out[2] waiting for results, out[3] number of launches */
 int dslam_session_host_times(dslam_session *s, double out[4]);
+/* Diagnostics (pure host logic, needs no device): how one evaluation launch would be laid out.  n_points[i] = template points of
+ * work item i (n_items <= 128), num_sms = SMs of the device, lanes = launches of this kind in flight at the same time.  Outputs:
+ * nblocks[i] = CTAs of item i, cta_begin[i] = its first CTA in the flat grid, *total_ctas = grid size. */
+int dslam_plan_eval_launch(int n_items, const int *n_points, int num_sms, int lanes, int *nblocks, int *cta_begin, int *total_ctas);
 /* pinned host memory helpers (cudaHostAlloc) so callers can make H2D/D2H truly asynchronous */
 int dslam_host_alloc(unsigned long long bytes, void **out);
 int dslam_host_free(void *p);

@@ -99,3 +99,40 @@ def test_product_package_never_touches_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "libdslam_oracle" not in src and "orc_" not in src, f
+
+
+def test_eval_launch_plan_invariants():
+    """The flat CTA grid of an evaluation launch (dslam_plan_eval_launch, pure host logic): every item gets >= 1 CTA, the prefix is
+    consistent, a launch within its budget gives every item one point per thread, an over-budget launch is dealt in proportion to
+    the item sizes, and launches that share the GPU take a smaller slice."""
+    import ctypes as C
+
+    from direct_stereo_slam_b200 import _lib
+
+    lib = _lib.load()
+
+    def plan(n_points, num_sms=148, lanes=1):
+        n = len(n_points)
+        pts = (C.c_int * n)(*n_points)
+        nb, cb, tot = (C.c_int * n)(), (C.c_int * n)(), C.c_int(0)
+        assert lib.dslam_plan_eval_launch(n, pts, num_sms, lanes, nb, cb, C.byref(tot)) == 0
+        nb, cb = list(nb), list(cb)
+        assert all(b >= 1 for b in nb) and cb[0] == 0 and tot.value == sum(nb)
+        assert all(cb[i + 1] == cb[i] + nb[i] for i in range(n - 1))
+        return nb, tot.value
+
+    # within the budget: one template point per thread (128 threads per CTA), capped at 96 CTAs per item
+    nb, tot = plan([9871, 4453, 130, 0, 1, 40000])
+    assert nb == [78, 35, 2, 1, 1, 96]
+    # over the budget (one resident wave = 5 CTAs per SM): proportional to the item sizes, small items keep their single CTA
+    sizes = [9871] * 8 + [400] * 56
+    nb, tot = plan(sizes)
+    assert tot <= 148 * 5 + len(sizes) and nb[0] > 10 * nb[-1] and len(set(nb[:8])) == 1 and len(set(nb[8:])) == 1
+    flat = plan([9871] * 64)[0]
+    assert len(set(flat)) == 1 and 148 * 5 - 64 <= sum(flat) <= 148 * 5
+    # launches that share the GPU (8 lanes in flight) take a smaller slice each
+    assert plan([9871] * 64, lanes=8)[1] < plan([9871] * 64, lanes=1)[1]
+    assert plan([9871] * 64, lanes=8)[1] >= 148 * 2 - 64
+    # argument checking
+    assert lib.dslam_plan_eval_launch(0, None, 148, 1, None, None, None) == _lib.EINVAL
+    assert lib.dslam_plan_eval_launch(129, (C.c_int * 129)(), 148, 1, (C.c_int * 129)(), (C.c_int * 129)(), C.byref(C.c_int())) == _lib.EINVAL
