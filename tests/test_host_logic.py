@@ -136,3 +136,27 @@ def test_eval_launch_plan_invariants():
     # argument checking
     assert lib.dslam_plan_eval_launch(0, None, 148, 1, None, None, None) == _lib.EINVAL
     assert lib.dslam_plan_eval_launch(129, (C.c_int * 129)(), 148, 1, (C.c_int * 129)(), (C.c_int * 129)(), C.byref(C.c_int())) == _lib.EINVAL
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: runs the reference's CPU path (no GPU needed), prints ONE JSON line with the contract's keys;
+    under torchrun only rank 0 works, the other ranks exit 0 silently."""
+    import json
+    import subprocess
+    import sys
+
+    bench = os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "1", "--cases", "1"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "stereo_frames_per_sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] == 0 and d["config"]["workload"].startswith("kitti_1232x368")
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
