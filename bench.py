@@ -351,51 +351,87 @@ def make_cpu_stream(orc_mod, o, case, phase, kf_every):
     return CpuStream(orc_mod, o if o is not None else orc_mod.Oracle(native=True), case, phase=phase, kf_every=kf_every), "port"
 
 
+def _ref_frames(st, k0, k1):
+    """Frames [k0, k1) of a CPU stream.  RefCpuStream: the whole loop on the C side (the reference's own makeImages incl. its
+    new[] / delete[], trackNewestCoarse, optimizeScale; no per-frame Python or numpy work); oracle port: per-frame calls."""
+    if isinstance(st, RefCpuStream):
+        c = st.case
+        st.trk.run_frames(k0, k1, st.phase, st.kf_every, c["img_new"], c["img_new2"], c["img_right"], np.stack(c["pose_init"]), st.levels - 1)
+    else:
+        for k in range(k0, k1):
+            st.frame(k)
+
+
 def cpu_single_core(cases, kf_every=5, budget_s=12.0):
     import oracle as orc
 
     st, kind = make_cpu_stream(orc, None, cases[0], 0, kf_every)
-    st.frame(0)  # warm-up
-    n, t0 = 0, time.perf_counter()
+    _ref_frames(st, 0, 5)  # warm-up
+    n, chunk, t0 = 0, 20, time.perf_counter()
     while True:
-        st.frame(n)
-        n += 1
+        _ref_frames(st, n, n + chunk)
+        n += chunk
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 4000:
             break
-    how = ("the reference's own TrackerAndScaler.cpp / makeImages compiled in place (oracle/_ref, -O3 -march=x86-64-v3)" if kind == "reference"
-           else "oracle port (-O3 -march=native, SSE accumulation order)")
+    how = ("the reference's own TrackerAndScaler.cpp / makeImages compiled in place (oracle/_ref, -O3 -march=x86-64-v3), frame loop on the C side"
+           if kind == "reference" else "oracle port (-O3 -march=native, SSE accumulation order)")
     return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": kind,
             "sample": "%d stereo frames of %s on one core, %s, %.1f s" % (n, WORKLOAD, how, dt)}
 
 
-def cpu_all_cores(cases, steps, warmup, threads, kf_every=5):
+def _cpu_proc_main(idx, core, n_cases, kf_every, warmup, steps, barrier, out_q):
+    """One independent stereo stream in its own PROCESS pinned to one core — the reference is single-threaded per rig, and
+    threads of one process contend on the allocator / page-fault path of the ~10 MB per-frame pyramids (round-1 harness)."""
+    try:
+        if core is not None:
+            os.sched_setaffinity(0, {core})
+    except OSError:
+        pass
     import oracle as orc
 
-    made = [make_cpu_stream(orc, None, cases[i % len(cases)], i, kf_every) for i in range(threads)]
-    sts, kind = [m[0] for m in made], made[0][1]
+    cases = make_cases(1, seed0=1000 + idx % n_cases)
+    st, kind = make_cpu_stream(orc, None, cases[0], idx, kf_every)
+    barrier.wait()
+    _ref_frames(st, 0, warmup)
+    barrier.wait()
+    t0 = time.perf_counter()
+    _ref_frames(st, warmup, warmup + steps)
+    t1 = time.perf_counter()
+    out_q.put((idx, t0, t1, kind))
 
-    def run(k0, k1):
-        def work(st):
-            for k in range(k0, k1):
-                st.frame(k)
-        th = [threading.Thread(target=work, args=(st,)) for st in sts]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        return time.perf_counter() - t0
 
-    run(0, warmup)
-    dt = run(warmup, warmup + steps)
-    return threads * steps / dt, dt, kind
+def cpu_procs(n_procs, steps, warmup, n_cases=4, kf_every=5):
+    """(frames/s, span seconds, kind) of n_procs independent stereo streams, one process per core; the span is
+    max(end) - min(start) over the processes (CLOCK_MONOTONIC is system wide)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    cores = sorted(os.sched_getaffinity(0))
+    barrier, q = ctx.Barrier(n_procs), ctx.Queue()
+    procs = [ctx.Process(target=_cpu_proc_main, args=(i, cores[i % len(cores)], n_cases, kf_every, warmup, steps, barrier, q)) for i in range(n_procs)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=1800) for _ in procs]
+    for pr in procs:
+        pr.join()
+    span = max(r[2] for r in res) - min(r[1] for r in res)
+    return n_procs * steps / span, span, res[0][3]
+
+
+def cpu_all_cores(steps, warmup, n_cases=4, kf_every=5):
+    """Reference arm: every usable host core runs its own stream.  Also reports the 1-process rate measured the same way,
+    so that harness throttling would be visible as an efficiency well below 1."""
+    n = len(os.sched_getaffinity(0))
+    fps1, _, _ = cpu_procs(1, max(steps, 20), warmup, n_cases, kf_every)
+    fps, span, kind = cpu_procs(n, steps, warmup, n_cases, kf_every)
+    return fps, span, kind, n, {"procs_1_fps": fps1, "procs_%d_fps" % n: fps, "efficiency_vs_linear": fps / (n * fps1)}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # Scan-Context shard (the only piece that shards): 100k descriptors over the ranks, query batch of 32
 # ----------------------------------------------------------------------------------------------------------------------
-def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1, 32), reps=20):
+def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1, 32, 256), reps=20):
     """100k descriptors row-sharded over the ranks; per query batch: scan + exact re-score (+ one NCCL all-reduce(min))."""
     sig, key = syn.make_sc_database(n_db, 2024)
     rows = api.shard_rows(n_db, world, rank)
@@ -436,6 +472,210 @@ def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# single-stream latency (what ONE stereo rig at 30 Hz sees; src/main.cpp:212-265 -> src/FrontEnd.cpp:585-686)
+# ----------------------------------------------------------------------------------------------------------------------
+def bench_latency(api, session, case, kf_every=5, frames=60):
+    """One stereo stream, frame after frame, in FrontEnd::addActiveStereoFrame's order: makeImages(left) [pinned host image ->
+    device pyramid -> level-0 dI mirrored back to the host for ImmaturePoint::traceOn; all levels + absSquaredGrad on keyframes],
+    trackNewCoarse with the 83-hypothesis list of src/FrontEnd.cpp:147-180 (dslam_track_new_coarse: the first hypothesis is
+    evaluated alone and normally accepted, :244-246), and on every kf_every-th frame makeImages(right) + optimizeScale(1.0).
+    Host clock around each call; median over the frames."""
+    cfg = case["cfg"]
+    w, h = cfg["w"], cfg["h"]
+    levels = api.pyr_levels_used(w, h)
+    K = np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+    trk = api.TrackerAndScaler(session, w, h, syn.t_stereo(cfg).reshape(-1), K, K0=K, levels=levels)
+    ref = api.FrameHessian(session, w, h, levels)
+    ref.makeImages(case["img_ref"], host=False)
+    trk.setCoarseTrackingRef(ref, case["pu"], case["pv"], case["pid"], case["pw"])
+    fl = [api.FrameHessian(session, w, h, levels) for _ in range(2)]
+    fr = api.FrameHessian(session, w, h, levels)
+    for f in fl:
+        f.alloc_host(pinned=True)
+    imgs = [session.pinned((h, w)), session.pinned((h, w))]
+    imgs[0][:] = case["img_new"]
+    imgs[1][:] = case["img_new2"]
+    img_r = session.pinned((h, w))
+    img_r[:] = case["img_right"]
+    ident = IDENT7
+    tries = []
+    for v in range(2):
+        xi = case["xi_true"] * (1.0 if v == 0 else 0.6) * 0.9
+        tries.append(syn.frontend_pose_tries(case["pose_init"][v], syn.pose7(*syn.se3_exp_mat(xi * 2)), syn.pose7(*syn.se3_exp_mat(xi * 0.5)), ident))
+    session.sync()
+    T = {"make_images_left_call": [], "track_new_coarse": [], "mirror_wait": [], "frame_nonkf": [], "make_images_right+optimize_scale": [], "frame_kf": []}
+    last = np.full(5, 100.0)
+    tries_used = []
+    for k in range(-5, frames):
+        v, kf = k & 1, (k % kf_every == 0)
+        f = fl[v]
+        t0 = time.perf_counter()
+        f.upload(imgs[v])
+        f.build()
+        if kf:
+            f.download(wait=False)
+        else:
+            f.download(wait=False, levels=[0], abs_grad=False)
+        t1 = time.perf_counter()
+        r = trk.trackNewCoarse(f, tries[v], (0.0, 0.0), levels - 1, last)
+        t2 = time.perf_counter()
+        f.wait_host()
+        t3 = time.perf_counter()
+        if kf:
+            fr.upload(img_r)
+            fr.build()
+            trk.optimizeScale(fr, 1.0, levels - 1)
+        t4 = time.perf_counter()
+        last = np.where(np.isfinite(r["achievedRes"]), r["achievedRes"], last)
+        if k < 0:
+            continue
+        tries_used.append(r["tryIterations"])
+        T["make_images_left_call"].append(t1 - t0)
+        T["track_new_coarse"].append(t2 - t1)
+        T["mirror_wait"].append(t3 - t2)
+        if kf:
+            T["make_images_right+optimize_scale"].append(t4 - t3)
+            T["frame_kf"].append(t4 - t0)
+        else:
+            T["frame_nonkf"].append(t3 - t0)
+    # the pyramid alone (upload + build, device complete), and the full makeImages contract (all levels mirrored, blocking)
+    pyr, full = [], []
+    for k in range(20):
+        t0 = time.perf_counter()
+        fl[0].upload(imgs[0])
+        fl[0].build()
+        session.sync()
+        pyr.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        fl[1].upload(imgs[1])
+        fl[1].build()
+        fl[1].download(wait=True)
+        full.append(time.perf_counter() - t0)
+    med = {k: float(np.median(v)) * 1e3 for k, v in T.items() if v}
+    out = {"streams": 1, "unit": "ms", "frames": frames, "keyframe_every": kf_every, "hypotheses_offered": int(len(tries[0])),
+           "hypotheses_tried_mean": float(np.mean(tries_used)), "median_ms": med,
+           "pyramid_h2d+build_ms": float(np.median(pyr)) * 1e3, "make_images_all_levels_mirrored_ms": float(np.median(full)) * 1e3,
+           "frame_ms_amortised": (float(np.sum(T["frame_nonkf"])) + float(np.sum(T["frame_kf"]))) / frames * 1e3}
+    out["frames_per_sec_single_stream"] = 1e3 / out["frame_ms_amortised"]
+    for x in [trk, ref, fr] + fl:
+        x.close()
+    return out
+
+
+def cpu_latency(cases, kf_every=5, frames=60):
+    """The same per-frame sequence on the reference's own code (one core), split into its phases (reft_run_frames)."""
+    import oracle as orc
+
+    st, kind = make_cpu_stream(orc, None, cases[0], 0, kf_every)
+    if not isinstance(st, RefCpuStream):
+        return None
+    _ref_frames(st, 0, 5)
+    _ref_frames(st, 0, frames)
+    ph = st.trk.last_phase_s
+    nkf = len([k for k in range(frames) if k % kf_every == 0])
+    return {"kind": kind, "cores": 1, "unit": "ms", "make_images_left": ph[0] / frames * 1e3, "track_newest_coarse": ph[1] / frames * 1e3,
+            "make_images_right+optimize_scale": ph[2] / max(nkf, 1) * 1e3, "frame_ms_amortised": float(ph.sum()) / frames * 1e3}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: synthetic 1920x1200, 8000 active points, B pose hypotheses per call (the HBM-roofline run)
+# ----------------------------------------------------------------------------------------------------------------------
+def bench_sweep_config3(api, session, peak, batches=(1, 8, 64, 512), reps=10):
+    c = syn.make_tracking_case("synth1920", 42, with_right=False)
+    cfg = c["cfg"]
+    w, h = cfg["w"], cfg["h"]
+    levels = api.pyr_levels_used(w, h)
+    K = np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+    trk = api.TrackerAndScaler(session, w, h, syn.t_stereo(cfg).reshape(-1), K, K0=K, levels=levels)
+    ref = api.FrameHessian(session, w, h, levels)
+    ref.makeImages(c["img_ref"], host=False)
+    pcn = trk.setCoarseTrackingRef(ref, c["pu"], c["pv"], c["pid"], c["pw"])
+    f = api.FrameHessian(session, w, h, levels)
+    f.makeImages(c["img_new"], host=False)
+    rng = np.random.default_rng(42)
+    out = {"workload": "synthetic_1920x1200_8000pts", "template_points_lvl0": int(pcn[0]), "levels": levels, "batches": {}}
+    session.profile(True)
+    for B in batches:
+        hyp = np.stack([syn.pose7(*syn.se3_exp_mat(c["xi_true"] * (1 + rng.uniform(-0.02, 0.02, 6)))) for _ in range(B)])
+        aff = np.tile(np.array(c["aff_true"]), (B, 1)) * (1 + rng.uniform(-0.02, 0.02, (B, 2)))
+        for lvl in (0,):
+            for _ in range(3):
+                trk.calcResAndGSPose(f, lvl, hyp, aff)
+            session.profile_read()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                trk.calcResAndGSPose(f, lvl, hyp, aff)
+            call_us = (time.perf_counter() - t0) / reps * 1e6
+            r = session.profile_read()["pose"]
+            gbs = BYTES_PER_POINT * r["points"] / (r["ms"] * 1e-3) / 1e9
+            out["batches"]["B%d" % B] = {"hypotheses": B, "launches_per_call": r["launches"] // reps, "kernel_us_per_call": r["ms"] * 1e3 / reps,
+                                         "call_us_host_clock": call_us, "points_per_call": r["points"] // reps, "achieved_gbs": gbs, "frac": gbs / peak}
+    session.profile(False)
+    for x in (trk, ref, f):
+        x.close()
+    return out
+
+
+def parity_check(api, session, case):
+    """Checker leg (the one other place bench.py runs oracle/): the GPU's trackNewestCoarse on scene 0 against the oracle in
+    its fp64-accumulating mode (the parity target) and in its reference-faithful mode 0 (4-lane x 3-tier fp32
+    SSE accumulation, bit-identical to the reference's own compiled TrackerAndScaler.cpp).  noise_floor = the distance of the
+    per-iteration increments to the mode-0 trace where the accept / reject sequences coincide: the reference's own
+    summation noise, which no fp64-accumulating implementation can be closer to."""
+    import oracle as orc
+
+    def rel(a, b):
+        return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+    o = orc.Oracle()
+    cfg = case["cfg"]
+    w, h = cfg["w"], cfg["h"]
+    levels = orc.pyr_levels_used(w, h)
+    K = np.array([cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"]], np.float32)
+    T = syn.t_stereo(cfg)
+    d_ref, _ = o.make_images(case["img_ref"], levels)
+    d_new, _ = o.make_images(case["img_new"], levels)
+    ot = o.tracker(w, h, levels, K, K, T)
+    ot.make_coarse_depth(case["pu"], case["pv"], case["pid"], case["pw"], d_ref)
+    ot.set_ref_aff(1.0, 0.0, 0.0)
+    ot.set_new_frame(d_new, 1.0)
+    init = case["pose_init"][0]
+    r1 = ot.track_newest_coarse(1, init, (0.0, 0.0), levels - 1)
+    t1 = ot.trace()
+    r0 = ot.track_newest_coarse(0, init, (0.0, 0.0), levels - 1)
+    t0 = ot.trace()
+    trk = api.TrackerAndScaler(session, w, h, T.reshape(-1), K, K0=K, levels=levels)
+    ref = api.FrameHessian(session, w, h, levels)
+    ref.makeImages(case["img_ref"], host=False)
+    trk.setCoarseTrackingRef(ref, case["pu"], case["pv"], case["pid"], case["pw"])
+    f = api.FrameHessian(session, w, h, levels)
+    f.makeImages(case["img_new"], host=False)
+    ok, pose, aff, last = trk.trackNewestCoarse(f, init, (0.0, 0.0), levels - 1)
+    tg = trk.trace()
+    for x in (trk, ref, f):
+        x.close()
+
+    def inc_dist(ta, tb):
+        n, worst, errs = 0, 0.0, []
+        for a, b in zip(ta, tb):
+            if not np.array_equal(a[:3], b[:3]):
+                break
+            n += 1
+            if b[1] >= 0:
+                errs.append(rel(a[7:15], b[7:15]))
+        return n, (max(errs) if errs else 0.0), (float(np.median(errs)) if errs else 0.0)
+
+    n1, w1, m1 = inc_dist(tg, t1)
+    n0, w0, m0 = inc_dist(tg, t0)
+    return {"workload": WORKLOAD + " scene 0, trackNewestCoarse from pose_init", "lm_rows": int(len(tg)),
+            "vs_fp64_oracle": {"rows_coinciding": n1, "rows": int(len(t1)), "inc_rel_worst": w1, "final_pose_rel": rel(pose, r1[1]), "ok_equal": bool(ok == r1[0]),
+                               "tolerance": 1e-5},
+            "noise_floor": {"what": "vs the oracle's reference-faithful mode 0 (fp32 SSE accumulation order, bit-identical to the compiled reference)",
+                            "rows_coinciding": n0, "rows": int(len(t0)), "inc_rel_worst": w0, "inc_rel_median": m0, "final_pose_rel": rel(pose, r0[1]),
+                            "ok_equal": bool(ok == r0[0])}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,6 +687,7 @@ def main():
     ap.add_argument("--cases", type=int, default=4, help="distinct synthetic scenes (streams cycle through them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scan-context", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-stream latency, the config-3 sweep and the parity check")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -456,17 +697,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = os.cpu_count() or 1
-        cases = make_cases(min(args.cases, 4))
-        fps, dt, kind = cpu_all_cores(cases, args.steps, warmup, threads, args.keyframe_every)
+        fps, dt, kind, threads, per_core = cpu_all_cores(args.steps, warmup, min(args.cases, 4), args.keyframe_every)
         line = {"metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "impl": "reference",
                 "config": {"workload": WORKLOAD, "frames_per_step": threads, "keyframe_every": args.keyframe_every,
                            "note": "the reference's own TrackerAndScaler.cpp / FrameHessian::makeImages source compiled in place against Eigen/Sophus "
-                                   "stand-ins (oracle/ref_build.py) when kind == reference, else the oracle port; one independent stereo stream per host thread"},
+                                   "stand-ins (oracle/ref_build.py) when kind == reference, else the oracle port; one independent stereo stream per "
+                                   "host core, each in its own process pinned to that core, frame loop on the C side"},
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                                 "sample": "%d threads x %d stereo frames of %s" % (threads, args.steps, WORKLOAD)},
+                                 "sample": "%d processes x %d stereo frames of %s" % (threads, args.steps, WORKLOAD), "per_core_scaling": per_core},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -520,7 +760,31 @@ def main():
     for _ in range(10):
         streams.trk[0].calcResAndGSPose(streams.f_new[0][0], 0, hyp, hyp_aff)
     alone = session.profile_read()["pose"]
+    # the scale flavour of the kernel alone: 128 scales of one stream's level-0 template against its right pyramid
+    sc_vals = np.linspace(0.8, 1.25, 128).astype(np.float32)
+    for _ in range(3):
+        streams.trk[0].calcResAndGSScale(streams.f_right[0][0], 0, sc_vals)
+    session.profile_read()
+    for _ in range(10):
+        streams.trk[0].calcResAndGSScale(streams.f_right[0][0], 0, sc_vals)
+    alone_scale = session.profile_read()["scale"]
     session.profile(False)
+    # the pyramid kernels alone: all left pyramids of a step (two launches per 64 frames) on the session stream, CUDA events
+    P0 = streams._plans(0)
+    for _ in range(2):
+        P0["left_fb"].build(stage_host=0, overlap=False)
+    session.sync()
+    session.mark(0)
+    for _ in range(3):
+        P0["left_fb"].build(stage_host=0, overlap=False)
+    session.mark(1)
+    session.sync()
+    pyr_ms = session.elapsed_ms() / 3
+    pyr_bytes = args.streams * (4 * streams.w * streams.h + 16 * sum((streams.w >> l) * (streams.h >> l) for l in range(streams.levels)))
+    latency = sweep3 = None
+    if rank == 0 and not args.no_extras:
+        latency = bench_latency(api, session, cases[0], args.keyframe_every)
+        sweep3 = bench_sweep_config3(api, session, measured_peak()[0])
 
     if dist is not None:
         import torch
@@ -567,15 +831,37 @@ def main():
                                                "avg_launch_us": alone["ms"] * 1e3 / alone["launches"],
                                                "achieved": BYTES_PER_POINT * alone["points"] / (alone["ms"] * 1e-3) / 1e9,
                                                "frac": BYTES_PER_POINT * alone["points"] / (alone["ms"] * 1e-3) / 1e9 / peak}
-                                              if alone["launches"] and alone["ms"] > 0 else None)},
+                                              if alone["launches"] and alone["ms"] > 0 else None),
+                             "scale_kernel_alone": ({"launches_timed": alone_scale["launches"], "points_per_launch": alone_scale["points"] / alone_scale["launches"],
+                                                     "avg_launch_us": alone_scale["ms"] * 1e3 / alone_scale["launches"],
+                                                     "achieved": BYTES_PER_POINT * alone_scale["points"] / (alone_scale["ms"] * 1e-3) / 1e9,
+                                                     "frac": BYTES_PER_POINT * alone_scale["points"] / (alone_scale["ms"] * 1e-3) / 1e9 / peak}
+                                                    if alone_scale["launches"] and alone_scale["ms"] > 0 else None),
+                             "pyramid": {"kernels": "downsample_chain_kernel + gradient_kernel, all %d left pyramids of a step" % args.streams,
+                                         "bytes_per_frame": pyr_bytes // args.streams, "ms_per_step": pyr_ms,
+                                         "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak,
+                                         "note": "algorithmic bytes = read 4*P0 + write 16*sum(P_l) per frame (SURVEY.md 8d)"},
+                             "aggregate": {"eval_bytes_per_step": BYTES_PER_POINT * p["points"] / min(args.steps, 5),
+                                           "pyramid_bytes_per_step": pyr_bytes * (1 + 1.0 / args.keyframe_every),
+                                           "gbs": (BYTES_PER_POINT * p["points"] / min(args.steps, 5) + pyr_bytes * (1 + 1.0 / args.keyframe_every)) / (ms / args.steps * 1e-3) / 1e9,
+                                           "note": "algorithmic bytes of all kernels of a step / ms_per_step of the timed run (the lanes overlap, so per-launch "
+                                                   "event times do not add up to the step)"},
+                             "sweep": sweep3},
                 "clocks": clocks,
                 "host_ms_per_step": {k: (v / (args.steps + warmup) if k != "launches" else v) for k, v in host_times.items()},
                 "lm": {"evals_per_frame": float(np.sum([c["evals"] for c in counters])) / (args.streams * (2 * warmup + 2 * args.steps + min(args.steps, 5))),
                        "note": "fused residual+Jacobian evaluations (pose + scale LM rounds) per stereo frame"}}
+        line["roofline"]["frac_aggregate"] = line["roofline"]["aggregate"]["gbs"] / peak
         if sc is not None:
             line["scan_context"] = sc
+        if latency is not None:
+            line["latency"] = {"gpu": latency}
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_single_core(cases, args.keyframe_every)
+            if latency is not None:
+                line["latency"]["cpu_reference"] = cpu_latency(cases, args.keyframe_every)
+            if not args.no_extras:
+                line["parity"] = parity_check(api, session, cases[0])
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -72,6 +72,35 @@ def pose7(R, t):
     return np.concatenate([R_to_quat(R), np.asarray(t, float)])
 
 
+def quat_mul(a, b):
+    """Hamilton product of two (x, y, z, w) quaternions."""
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+ROT_SIGNS = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (-1, 1, 0), (0, -1, 1), (-1, 0, 1),
+             (1, -1, 0), (0, 1, -1), (1, 0, -1), (-1, -1, 0), (0, -1, -1), (-1, 0, -1), (-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1),
+             (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+
+
+def frontend_pose_tries(const_motion7, double_motion7, half_motion7, zero_motion7):
+    """The 83 initialisations FrontEnd::trackNewCoarse tries in order (src/FrontEnd.cpp:147-180): constant / double / half /
+    zero motion, zero motion from the keyframe, then constant motion composed with 26 sign patterns x 3 small rotations
+    (rot_delta = 0.02, 0.03, 0.04; the float loop `< 0.05` ends there).  Poses are (qx, qy, qz, qw, tx, ty, tz)."""
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    tries = [np.asarray(const_motion7, np.float64), np.asarray(double_motion7, np.float64), np.asarray(half_motion7, np.float64),
+             np.asarray(zero_motion7, np.float64), ident]
+    base = tries[0]
+    for d in (0.02, 0.03, 0.04):
+        for sgn in ROT_SIGNS:
+            q = np.array([sgn[0] * d, sgn[1] * d, sgn[2] * d, 1.0])
+            q /= np.linalg.norm(q)  # the SE3(Quaterniond, t) constructor normalises
+            tries.append(np.concatenate([quat_mul(base[:4], q), base[4:]]))  # base * SE3(q, 0): rotation composes, translation stays
+    return np.stack(tries)
+
+
 class Scene:
     def __init__(self, cfg, seed, n_waves=32, n_boxes=12):
         self.cfg = cfg

@@ -590,6 +590,20 @@ class ReferenceTracker:
         self.L.reft_get_K(self.p, lvl, _fp(out))
         return out
 
+    def run_frames(self, k0, k1, phase, kf_every, img_new0, img_new1, img_right, pose_init_2x7, coarsest):
+        """Frames [k0, k1) of one stereo stream entirely on the C side (reft_run_frames): makeImages(left) + trackNewestCoarse,
+        on keyframes makeImages(right) + optimizeScale(1.0).  Returns (#frames tracked OK, last pose7, last scale)."""
+        imgs = [np.ascontiguousarray(a, np.float32) for a in (img_new0, img_new1, img_right)]
+        init = np.ascontiguousarray(pose_init_2x7, np.float64).reshape(14)
+        pose = np.zeros(7, np.float64)
+        scale = C.c_float(0)
+        self.L.reft_run_frames.restype = C.c_int
+        self.L.reft_run_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_d, C.c_int, c_d, C.POINTER(C.c_float), c_d]
+        self.last_phase_s = np.zeros(3, np.float64)  # seconds in makeImages(left), trackNewestCoarse, keyframe work (right pyramid + scale)
+        good = self.L.reft_run_frames(self.p, k0, k1, phase, kf_every, _fp(imgs[0]), _fp(imgs[1]), _fp(imgs[2]), _dp(init), coarsest, _dp(pose),
+                                      C.byref(scale), _dp(self.last_phase_s))
+        return good, pose, scale.value
+
 
 _REF_LIBS = {}
 

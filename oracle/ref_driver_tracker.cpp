@@ -10,6 +10,7 @@
 //
 // What this pins: every formula and the whole control flow of the hot path as written in the reference's source text.
 // What it cannot pin: the evaluation order real Eigen / Sophus give those expressions (restated in oracle/shim).
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -184,8 +185,10 @@ float reft_optimize_scale(void *p, float *scale_io, int coarsestLvl) {
 // concatenated); rows 0 and h-1 of dx, dy, absSquaredGrad are whatever `new[]` returned in the reference — zeroed here
 // before the call is not possible (the function allocates), so they are zeroed afterwards.
 void refimg_make_images(const float *color, int w, int h, int levels, const float *B256, float *dIp_all, float *absg_all) {
-  pyrLevelsUsed = levels;
-  for (int l = 0; l < levels; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+  if (pyrLevelsUsed != levels || wG[0] != w || hG[0] != h) {  // globals of the reference; only touched when the geometry changes
+    pyrLevelsUsed = levels;
+    for (int l = 0; l < levels; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+  }
   FrameHessian fh;
   CalibHessian calib{0, 0, 0, 0};
   if (B256) for (int i = 0; i < 256; i++) calib.B[i] = B256[i];
@@ -204,6 +207,55 @@ void refimg_make_images(const float *color, int w, int h, int levels, const floa
     delete[] fh.dIp[l];
     delete[] fh.absSquaredGrad[l];
   }
+}
+
+// One stereo stream driven the way FrontEnd drives it, entirely on the C side (timed CPU baseline of bench.py): per frame
+// `new FrameHessian; makeImages(left, &HCalib)` + trackNewestCoarse (src/FrontEnd.cpp:585-606, 204-206); on keyframes
+// `makeImages(right, 0)` + optimizeScale from seed 1.0 (:676-680, 992).  The frames own their pyramids exactly as in the
+// reference (new[] inside makeImages, delete[] when the frame goes) — no copies, no Python objects, no globals written per
+// frame.  Frame k uses image k & 1 and pose_init k & 1; it is a keyframe when (k + phase) % kf_every == 0.
+// Returns the number of frames whose tracking succeeded; pose7_out / scale_out receive the last results.
+int reft_run_frames(void *p, int k0, int k1, int phase, int kf_every, const float *img_new0, const float *img_new1, const float *img_right,
+                    const double *pose_init_2x7, int coarsestLvl, double *pose7_out, float *scale_out, double *phase_s /* [3] or null */) {
+  RefTracker &R = *(RefTracker *)p;
+  typedef std::chrono::steady_clock Clk;
+  double t_img = 0, t_trk = 0, t_kf = 0;
+  for (int i = 0; i < 256; i++) R.calib.B[i] = (float)i;  // identity response (HessianBlocks.h:329-330)
+  int good = 0;
+  Vec5 mr, lr;
+  for (int i = 0; i < 5; i++) mr[i] = NAN;
+  for (int k = k0; k < k1; k++) {
+    const int v = k & 1;
+    Frame *f = new Frame();
+    f->fh.shell = &f->shell;
+    f->fh.ab_exposure = 1.0f;
+    const Clk::time_point c0 = Clk::now();
+    f->fh.makeImages(const_cast<float *>(v ? img_new1 : img_new0), &R.calib);
+    const Clk::time_point c1 = Clk::now();
+    R.trk->new_frame_ = &f->fh;
+    SE3 pose = SE3::from7(pose_init_2x7 + 7 * v);
+    AffLight aff(0, 0);
+    good += R.trk->trackNewestCoarse(&f->fh, pose, aff, coarsestLvl, mr, lr) ? 1 : 0;
+    if (pose7_out) pose.to7(pose7_out);
+    const Clk::time_point c2 = Clk::now();
+    t_img += std::chrono::duration<double>(c1 - c0).count();
+    t_trk += std::chrono::duration<double>(c2 - c1).count();
+    if ((k + phase) % kf_every == 0) {
+      Frame *f1 = new Frame();
+      f1->fh.shell = &f1->shell;
+      f1->fh.makeImages(const_cast<float *>(img_right), nullptr);
+      float scale = 1.0f;
+      R.trk->optimizeScale(&f1->fh, scale, coarsestLvl);
+      if (scale_out) *scale_out = scale;
+      for (int l = 0; l < R.levels; l++) { delete[] f1->fh.dIp[l]; delete[] f1->fh.absSquaredGrad[l]; }
+      delete f1;
+      t_kf += std::chrono::duration<double>(Clk::now() - c2).count();
+    }
+    for (int l = 0; l < R.levels; l++) { delete[] f->fh.dIp[l]; delete[] f->fh.absSquaredGrad[l]; }
+    delete f;
+  }
+  if (phase_s) { phase_s[0] = t_img; phase_s[1] = t_trk; phase_s[2] = t_kf; }
+  return good;
 }
 
 void reft_get_K(void *p, int lvl, float out[17]) {
