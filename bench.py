@@ -444,7 +444,11 @@ def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1
         dist.broadcast_object_list(ident, src=0)
         db.attach_comm(ident[0], world, rank)
     peak, _ = measured_peak()
-    out = {"db_rows": n_db, "rows_per_gpu": int(len(rows)), "collective": "ncclAllReduce(min, uint64 x Q)" if world > 1 else "none", "batches": {}}
+    mode = db.exchange_mode()
+    out = {"db_rows": n_db, "rows_per_gpu": int(len(rows)),
+           "exchange": {"nvlink-mailbox": "system-scope atomic-min of packed (distance, id) keys into every rank's HBM mailbox over NVLink, fused into the re-score kernel",
+                        "nccl": "ncclAllReduce(min, uint64 x Q)", "none": "none (one GPU)"}[mode], "batches": {}}
+    full = None
     for nq in batches:
         qs, qk, truth = syn.make_sc_queries(sig, key, nq, 77)
         for _ in range(3):
@@ -468,6 +472,16 @@ def bench_scan_context(api, session, rank, world, dist, n_db=100_000, batches=(1
         gbs = len(rows) * (db.n_cells + db.n_rings) * 4 / (scan_ms * 1e-3) / 1e9
         out["batches"]["Q%d" % nq] = {"query_latency_ms": lat_ms, "scan_kernel_ms": scan_ms, "scan_gbs_per_gpu": gbs, "scan_frac_of_hbm_peak": gbs / peak,
                                       "revisits_found": int(np.sum(idx[known] == truth[known])), "revisits": int(known.sum())}
+        if world > 1 and rank == 0:
+            # parity of the sharded answer: the same batch against an UNSHARDED copy of the database on this GPU (non-collective
+            # call) must give the same argmin and the same distance bits
+            if full is None:
+                full = api.ScanContextDB(session, n_db + 8)
+                full.add(key, sig)
+            dref, iref = api.unpack_key(full.query_keys(qs))
+            out["batches"]["Q%d" % nq]["equals_unsharded"] = bool(np.array_equal(iref, idx) and np.array_equal(dref.view(np.uint32), diff.view(np.uint32)))
+    if full is not None:
+        full.close()
     db.close()
     return out
 

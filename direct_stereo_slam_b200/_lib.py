@@ -85,7 +85,14 @@ SIGNATURES = {
     "dslam_get_trace": [vp, c_d, C.c_int, c_i],
     "dslam_ctx_counters": [vp, C.POINTER(C.c_longlong)],
     "dslam_sc_create": [vp, C.c_int, C.c_int, C.c_int, c_pp],
+    "dslam_sc_create_ex": [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_pp],
     "dslam_sc_destroy": [vp],
+    "dslam_sc_add64": [vp, C.c_int, c_f, c_d, c_i],
+    "dslam_sc_save": [vp, C.c_char_p],
+    "dslam_sc_load": [vp, C.c_char_p, c_i],
+    "dslam_sc_search_sc64": [vp, C.c_int, c_d, c_i, C.c_int, c_i, c_f],
+    "dslam_sc_query64": [vp, C.c_int, c_f, c_d, C.c_float, C.c_int, c_i, c_f],
+    "dslam_sc_exchange_mode": [vp, c_i],
     "dslam_sc_add": [vp, C.c_int, c_f, c_f, c_i],
     "dslam_sc_add_sparse": [vp, c_f, c_i, c_d, C.c_int, C.c_int],
     "dslam_sc_generate": [vp, c_d, C.c_int, C.c_double, c_f, c_f, c_d, c_d, C.c_int, C.c_int],

@@ -481,13 +481,16 @@ class ScanContextDB:
 
     KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
 
-    def __init__(self, session, capacity, n_sectors=60, n_rings=20):
+    def __init__(self, session, capacity, n_sectors=60, n_rings=20, fp64=False):
+        """capacity = initial allocation (the tables grow); fp64 keeps the reference's double signature values next to the
+        fp32 scan table so that the exact re-score multiplies doubles like search_place.h:71-77."""
         self.s = session
         self.lib = session.lib
         self.n_sectors, self.n_rings = n_sectors, n_rings
         self.n_cells = n_sectors * n_rings
+        self.fp64 = bool(fp64)
         p = C.c_void_p()
-        check(self.lib.dslam_sc_create(session.p, n_sectors, n_rings, capacity, C.byref(p)))
+        check(self.lib.dslam_sc_create_ex(session.p, n_sectors, n_rings, capacity, 1 if fp64 else 0, C.byref(p)))
         self.p = p
         self.world, self.rank = 1, 0
 
@@ -513,6 +516,23 @@ class ScanContextDB:
         assert ringkeys.shape[1] == self.n_rings and sigs.shape[1] == self.n_cells and len(sigs) == len(ringkeys)
         ids = None if global_ids is None else np.ascontiguousarray(global_ids, np.int32)
         check(self.lib.dslam_sc_add(self.p, len(sigs), _fp(ringkeys), _fp(sigs), _ip(ids)))
+
+    def add64(self, ringkeys, sigs64, global_ids=None):
+        ringkeys = np.ascontiguousarray(np.atleast_2d(ringkeys), np.float32)
+        sigs64 = np.ascontiguousarray(np.atleast_2d(sigs64), np.float64)
+        assert ringkeys.shape[1] == self.n_rings and sigs64.shape[1] == self.n_cells and len(sigs64) == len(ringkeys)
+        ids = None if global_ids is None else np.ascontiguousarray(global_ids, np.int32)
+        check(self.lib.dslam_sc_add64(self.p, len(sigs64), _fp(ringkeys), _dp(sigs64), _ip(ids)))
+
+    def save(self, path):
+        """Dump the shard as a .scdb file (format: include/dslam_b200.h)."""
+        check(self.lib.dslam_sc_save(self.p, str(path).encode()))
+
+    def load(self, path):
+        """Append the rows of a .scdb file; returns the number of rows read."""
+        n = C.c_int(0)
+        check(self.lib.dslam_sc_load(self.p, str(path).encode(), C.byref(n)))
+        return n.value
 
     def add_sparse(self, ringkey, idx, val, global_id=-1):
         ringkey = np.ascontiguousarray(ringkey, np.float32)
@@ -547,6 +567,15 @@ class ScanContextDB:
         check(self.lib.dslam_sc_search_sc(self.p, nq, _fp(sigs), _ip(candidates), candidates.shape[1], _ip(idx), _fp(diff)))
         return idx, diff
 
+    def search_sc64(self, sigs64, candidates):
+        sigs64 = np.ascontiguousarray(np.atleast_2d(sigs64), np.float64)
+        candidates = np.ascontiguousarray(np.atleast_2d(candidates), np.int32)
+        nq = len(sigs64)
+        idx = np.empty(nq, np.int32)
+        diff = np.empty(nq, np.float32)
+        check(self.lib.dslam_sc_search_sc64(self.p, nq, _dp(sigs64), _ip(candidates), candidates.shape[1], _ip(idx), _fp(diff)))
+        return idx, diff
+
     def query(self, sigs, ringkeys=None, ringkey_thres=-1.0, max_id=2**31 - 1):
         sigs = np.ascontiguousarray(np.atleast_2d(sigs), np.float32)
         nq = len(sigs)
@@ -555,6 +584,21 @@ class ScanContextDB:
         diff = np.empty(nq, np.float32)
         check(self.lib.dslam_sc_query(self.p, nq, _fp(rk), _fp(sigs), ringkey_thres, max_id, _ip(idx), _fp(diff)))
         return idx, diff
+
+    def query64(self, sigs64, ringkeys=None, ringkey_thres=-1.0, max_id=2**31 - 1):
+        sigs64 = np.ascontiguousarray(np.atleast_2d(sigs64), np.float64)
+        nq = len(sigs64)
+        rk = None if ringkeys is None else np.ascontiguousarray(np.atleast_2d(ringkeys), np.float32)
+        idx = np.empty(nq, np.int32)
+        diff = np.empty(nq, np.float32)
+        check(self.lib.dslam_sc_query64(self.p, nq, _fp(rk), _dp(sigs64), ringkey_thres, max_id, _ip(idx), _fp(diff)))
+        return idx, diff
+
+    def exchange_mode(self):
+        """'nvlink-mailbox' when the sharded query combines its keys through peer memory, 'nccl' for the all-reduce fallback."""
+        m = C.c_int(0)
+        check(self.lib.dslam_sc_exchange_mode(self.p, C.byref(m)))
+        return "nvlink-mailbox" if m.value else ("nccl" if self.world > 1 else "none")
 
     def query_keys(self, sigs, ringkeys=None, ringkey_thres=-1.0, max_id=2**31 - 1):
         sigs = np.ascontiguousarray(np.atleast_2d(sigs), np.float32)

@@ -154,11 +154,27 @@ void sc_set_scan_flavour(int flavour);
 cudaError_t launch_sc_moments(const double *pts, int n, double *out9, cudaStream_t stream);
 cudaError_t launch_sc_bin_finalize(const double *pts, int n, const double mean[3], const double v9[9], double lidar_range, int num_s, int num_r,
                                    unsigned long long *cells, float *ringkey, float *sig, double *sig64, cudaStream_t stream);
-// exact re-score of the scan's survivors in search_sc's arithmetic -> per-query best packed (dist, GLOBAL id) key
-cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const float *sigs, const int *ids, const float *q_sigs, int nq, int n_cells,
-                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, cudaStream_t stream);
+// NVLink mailbox exchange of the per-query best keys (kernels_sc.cu: sc_rescore_topk_kernel).  keys[r] / arrived[r] are THIS
+// rank's mappings of rank r's mailbox (own allocation for r == rank, CUDA IPC mappings otherwise).
+constexpr int kScXchgMaxQ = 1024;
+constexpr unsigned long long kScXchgErrorKey = ~0ull - 1;  // published instead of a key when a peer did not arrive in time
+struct ScExchange {
+  int world = 1, rank = 0;
+  unsigned long long *keys[8] = {};
+  unsigned *arrived[8] = {};
+};
+size_t sc_exchange_bytes();  // size of one rank's mailbox allocation; keys first, counters at sc_exchange_arrived_offset()
+size_t sc_exchange_arrived_offset();
+// exact re-score of the scan's survivors in search_sc's arithmetic -> per-query best packed (dist, GLOBAL id) key, published
+// to host_words (mapped pinned, 2 self-validating words per query: high / low 32 key bits | seq) — after the mailbox
+// exchange when xchg->world > 1.  fp64: sigs / q_sigs are double tables (the reference's SigType values).
+cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq, int n_cells,
+                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, unsigned long long *host_words,
+                                   unsigned seq, const ScExchange *xchg, unsigned xchg_seq, int q0, unsigned *ticket, cudaStream_t stream);
 // exact distances of explicit (query, local row) pairs; row < 0 = skip (+inf)
-cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const float *sigs, const float *q_sigs, int n_cells,
+cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const void *sigs, int fp64, const void *q_sigs, int n_cells,
                                     int sc_width, float *diff_out, cudaStream_t stream);
+cudaError_t launch_sc_widen(const float *src, double *dst, size_t n, cudaStream_t stream);
+cudaError_t launch_sc_narrow(const double *src, float *dst, size_t n, cudaStream_t stream);
 
 }  // namespace dslam

@@ -2,11 +2,14 @@
 //
 // Replaces search_ringkey / search_sc (src/loop_closure/loop_detection/search_place.h:25-57, 59-85; call sites
 // src/loop_closure/LoopHandler.cpp:247, 256).  The database is a device-resident dense fp32 table (4,800 B per
-// descriptor + 80 B ring key); a query batch is answered by ONE streaming pass over the local shard
-// (sc_scan_kernel), an exact re-score of the K survivors in the reference's arithmetic on the device
-// (sc_rescore_topk_kernel) and — when the database is sharded over several GPUs — one NCCL all-reduce(min) of
-// the packed (distance, id) keys over NVLink.  Rows are appended in id order, so "lowest id wins ties" is the
-// same rule on every shard and across shards.
+// descriptor + 80 B ring key; optionally an fp64 side table with the reference's double values for the exact
+// re-score); a query batch is answered by ONE pass over the local shard (sc_scan_kernel / sc_scan_tile_kernel, the
+// merge of the per-CTA lists fused into the last CTA), an exact re-score of the K survivors in the reference's
+// arithmetic (sc_rescore_topk_kernel) which also PUBLISHES the result: straight into mapped pinned host memory as
+// self-validating words on one GPU, and — when the database is sharded over several GPUs — after an NVLink mailbox
+// exchange of the packed (distance, id) keys (system-scope atomic-min into every peer's HBM through CUDA IPC mappings;
+// no library collective on the query path; NCCL bootstraps the mappings and remains as the fallback exchange).
+// Rows are appended in id order, so "lowest id wins ties" is the same rule on every shard and across shards.
 //
 // NCCL is loaded with dlopen at dslam_sc_comm_init so that the library has no link-time dependency on it (the
 // process usually already holds torch's bundled libnccl.so.2, which dlopen then returns).
@@ -78,17 +81,25 @@ inline int key_id(u64 key) { return (int)(unsigned)(key & 0xffffffffull); }
 struct dslam_scdb {
   dslam_session *s = nullptr;
   int n_sectors = 0, n_rings = 0, n_cells = 0, capacity = 0, n = 0;
+  bool fp64 = false;                     // keep the reference's double signature values for the exact re-score
   float *d_sigs = nullptr, *d_keys = nullptr;
+  double *d_sigs64 = nullptr;
   int *d_ids = nullptr;
   std::vector<int> ids;                  // global id of every local row (ascending)
   std::unordered_map<int, int> row_of;   // global id -> local row
   // query-side buffers (grown on demand)
   int qcap = 0;
   float *d_qsigs = nullptr, *d_qkeys = nullptr;
+  double *d_qsigs64 = nullptr;
   u64 *d_topk = nullptr, *d_exact = nullptr, *d_best = nullptr, *d_gather = nullptr, *d_scratch = nullptr;
   size_t scratch_bytes = 0;
   u64 *h_keys = nullptr;  // pinned: max(qcap * K * world, ...)
   size_t h_keys_cap = 0;
+  u64 *h_words = nullptr, *d_words = nullptr;  // mapped pinned result words (2 per query) the re-score kernel publishes into
+  unsigned seq = 0;                            // sequence number carried by those words
+  float *h_qstage = nullptr;                   // pinned staging of small query batches (the caller's arrays are pageable)
+  size_t h_qstage_bytes = 0;
+  unsigned *d_ticket = nullptr;                // ticket of the re-score grid
   int paircap = 0;
   int *d_pair_q = nullptr, *d_pair_row = nullptr;
   float *d_pair_diff = nullptr;
@@ -104,6 +115,12 @@ struct dslam_scdb {
   bool have_scan_time = false;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // NVLink mailbox exchange (kernels_sc.cu): own mailbox + IPC mappings of the peers'
+  void *d_mail = nullptr;
+  void *peer_mail[8] = {};
+  dslam::ScExchange xchg;
+  bool p2p = false;
+  unsigned xseq = 0;  // exchange sequence number: advances identically on every rank (collective calls)
 };
 
 using namespace dslam;
@@ -113,23 +130,37 @@ namespace {
 int ensure_query_buffers(dslam_scdb *db, int nq) {
   const int world = db->world;
   if (nq > db->qcap) {
-    cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best); cudaFree(db->d_gather);
+    cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_qsigs64); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best);
+    cudaFree(db->d_gather);
+    if (db->h_words) cudaFreeHost(db->h_words);
     db->d_qsigs = db->d_qkeys = nullptr;
+    db->d_qsigs64 = nullptr;
     db->d_topk = db->d_exact = db->d_best = db->d_gather = nullptr;
+    db->h_words = db->d_words = nullptr;
+    db->qcap = 0;
     const int cap = std::max(32, nq);
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs, (size_t)cap * db->n_cells * sizeof(float)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qkeys, (size_t)cap * db->n_rings * sizeof(float)));
+    if (db->fp64) DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs64, (size_t)cap * db->n_cells * sizeof(double)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_topk, (size_t)cap * kScTopK * sizeof(u64)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_exact, (size_t)cap * kScTopK * sizeof(u64)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_best, (size_t)cap * sizeof(u64)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_gather, (size_t)cap * kScTopK * sizeof(u64) * world));
+    DSLAM_CUDA(cudaHostAlloc((void **)&db->h_words, (size_t)cap * 2 * sizeof(u64), cudaHostAllocMapped));
+    std::memset(db->h_words, 0, (size_t)cap * 2 * sizeof(u64));
+    DSLAM_CUDA(cudaHostGetDevicePointer((void **)&db->d_words, db->h_words, 0));
     db->qcap = cap;
+  }
+  if (!db->d_ticket) {
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_ticket, 256));
+    DSLAM_CUDA(cudaMemsetAsync(db->d_ticket, 0, 256, db->s->stream));
   }
   const size_t sb = sc_scratch_bytes(nq);
   if (sb > db->scratch_bytes) {
     cudaFree(db->d_scratch);
     db->d_scratch = nullptr;
     DSLAM_CUDA(cudaMalloc((void **)&db->d_scratch, sb));
+    DSLAM_CUDA(cudaMemsetAsync(db->d_scratch, 0, sb, db->s->stream));  // the tickets of the fused merges live in its tail
     db->scratch_bytes = sb;
   }
   const size_t hk = (size_t)std::max(32, nq) * kScTopK * world;
@@ -152,12 +183,77 @@ int ensure_stage(dslam_scdb *db, size_t floats) {
   return DSLAM_OK;
 }
 
-int upload_queries(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs) {
+// Room for `need` rows: the device tables grow geometrically (new allocation + device-to-device copy on the session
+// stream) — the reference's FLANN index and loop_frames_ grow without bound (src/loop_closure/LoopHandler.cpp:225-229).
+int ensure_capacity(dslam_scdb *db, int need) {
+  if (need <= db->capacity) return DSLAM_OK;
+  long cap = db->capacity;
+  while (cap < need) cap = cap + cap / 2 + 64;
+  if (cap > 0x7fffff00L) return fail(DSLAM_ENOMEM, "database too large");
+  dslam_session *s = db->s;
+  float *sigs = nullptr, *keys = nullptr;
+  double *sigs64 = nullptr;
+  int *ids = nullptr;
+  cudaError_t e = cudaMalloc((void **)&sigs, (size_t)cap * db->n_cells * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&keys, (size_t)cap * db->n_rings * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ids, (size_t)cap * sizeof(int));
+  if (e == cudaSuccess && db->fp64) e = cudaMalloc((void **)&sigs64, (size_t)cap * db->n_cells * sizeof(double));
+  if (e == cudaSuccess && db->n > 0) {
+    e = cudaMemcpyAsync(sigs, db->d_sigs, (size_t)db->n * db->n_cells * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(keys, db->d_keys, (size_t)db->n * db->n_rings * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ids, db->d_ids, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess && db->fp64)
+      e = cudaMemcpyAsync(sigs64, db->d_sigs64, (size_t)db->n * db->n_cells * sizeof(double), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(sigs); cudaFree(keys); cudaFree(ids); cudaFree(sigs64);
+    return cuda_fail(e, "growing the Scan-Context tables");
+  }
+  cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids); cudaFree(db->d_sigs64);
+  db->d_sigs = sigs; db->d_keys = keys; db->d_ids = ids; db->d_sigs64 = sigs64;
+  db->capacity = (int)cap;
+  return DSLAM_OK;
+}
+
+// Query descriptors onto the device.  Small batches go through a pinned staging buffer (the caller's arrays are pageable:
+// a pageable cudaMemcpyAsync is a synchronous staged copy inside the driver); fp64 databases keep both precisions of the
+// queries: fp32 for the scan, fp64 for the exact re-score.
+int upload_queries(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs, const double *sigs64 = nullptr) {
   const int rc = ensure_query_buffers(db, nq);
   if (rc != DSLAM_OK) return rc;
-  if (sigs) DSLAM_CUDA(cudaMemcpyAsync(db->d_qsigs, sigs, (size_t)nq * db->n_cells * sizeof(float), cudaMemcpyHostToDevice, db->s->stream));
-  if (ringkeys)
-    DSLAM_CUDA(cudaMemcpyAsync(db->d_qkeys, ringkeys, (size_t)nq * db->n_rings * sizeof(float), cudaMemcpyHostToDevice, db->s->stream));
+  cudaStream_t st = db->s->stream;
+  const size_t sig_b = (sigs || sigs64) ? (size_t)nq * db->n_cells * (sigs64 ? sizeof(double) : sizeof(float)) : 0;
+  const size_t key_b = ringkeys ? (size_t)nq * db->n_rings * sizeof(float) : 0;
+  const void *sig_src = sigs64 ? (const void *)sigs64 : (const void *)sigs;
+  const void *key_src = ringkeys;
+  if (sig_b + key_b > 0 && sig_b + key_b <= (1u << 20)) {
+    if (sig_b + key_b > db->h_qstage_bytes) {
+      DSLAM_CUDA(cudaStreamSynchronize(st));
+      if (db->h_qstage) cudaFreeHost(db->h_qstage);
+      db->h_qstage = nullptr;
+      const size_t cap = std::max<size_t>(sig_b + key_b, 256u << 10);
+      DSLAM_CUDA(cudaHostAlloc((void **)&db->h_qstage, cap, cudaHostAllocDefault));
+      db->h_qstage_bytes = cap;
+    }
+    // the previous query's copy out of the staging buffer completed before its result was read (every query waits)
+    unsigned char *st8 = reinterpret_cast<unsigned char *>(db->h_qstage);
+    if (sig_src) { std::memcpy(st8, sig_src, sig_b); sig_src = st8; }
+    if (key_src) { std::memcpy(st8 + sig_b, key_src, key_b); key_src = st8 + sig_b; }
+  }
+  if (sigs64) {
+    if (!db->fp64) return fail(DSLAM_ESTATE, "fp64 queries need a database created with DSLAM_SC_FP64");
+    DSLAM_CUDA(cudaMemcpyAsync(db->d_qsigs64, sig_src, sig_b, cudaMemcpyHostToDevice, st));
+    DSLAM_CUDA(launch_sc_narrow(db->d_qsigs64, db->d_qsigs, (size_t)nq * db->n_cells, st));
+    db->s->launches++;
+  } else if (sigs) {
+    DSLAM_CUDA(cudaMemcpyAsync(db->d_qsigs, sig_src, sig_b, cudaMemcpyHostToDevice, st));
+    if (db->fp64) {
+      DSLAM_CUDA(launch_sc_widen(db->d_qsigs, db->d_qsigs64, (size_t)nq * db->n_cells, st));
+      db->s->launches++;
+    }
+  }
+  if (ringkeys) DSLAM_CUDA(cudaMemcpyAsync(db->d_qkeys, key_src, key_b, cudaMemcpyHostToDevice, st));
   return DSLAM_OK;
 }
 
@@ -166,10 +262,15 @@ int nccl_fail(ncclResult_t r, const char *what) {
   return fail(DSLAM_ENCCL, "NCCL error %d (%s) in %s", (int)r, api ? api->GetErrorString(r) : "?", what);
 }
 
-// scan + exact re-score of the local shard: d_best[q] = packed (exact dist, global id) or ~0
-int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs, float ringkey_thres, int max_id) {
+// how the re-score kernel hands its result on
+enum Publish { kToDevice = 0 /* d_best only */, kToHost = 1 /* local keys -> host words */, kExchange = 2 /* NVLink mailboxes -> host words */ };
+
+// scan + exact re-score of the local shard: d_best[q] = packed (exact dist, global id) or ~0; published as requested
+int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs, const double *sigs64, float ringkey_thres, int max_id, Publish pub,
+                unsigned *seq_out) {
   if (ringkey_thres >= 0.f && !ringkeys) return fail(DSLAM_EINVAL, "ring-key gate requested without query ring keys");
-  int rc = upload_queries(db, nq, ringkeys, sigs);
+  if (pub == kExchange && nq > kScXchgMaxQ) return fail(DSLAM_EINVAL, "at most %d queries per sharded batch", kScXchgMaxQ);
+  int rc = upload_queries(db, nq, ringkeys, sigs, sigs64);
   if (rc != DSLAM_OK) return rc;
   dslam_session *s = db->s;
   DSLAM_CUDA(cudaEventRecord(db->ev0, s->stream));
@@ -177,10 +278,41 @@ int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs
                             max_id, (float)db->n_sectors, db->d_topk, db->d_scratch, s->stream));
   DSLAM_CUDA(cudaEventRecord(db->ev1, s->stream));
   db->have_scan_time = true;
-  s->launches += 2 * ((nq + 31) / 32);
-  DSLAM_CUDA(launch_sc_rescore_topk(db->d_topk, db->d_sigs, db->d_ids, db->d_qsigs, nq, db->n_cells, db->n_sectors, db->d_exact, db->d_best,
-                                    s->stream));
+  s->launches += (nq + 31) / 32;
+  if (++db->seq == 0) ++db->seq;  // never 0: the words start out as 0
+  const unsigned seq = db->seq;
+  if (seq_out) *seq_out = seq;
+  const void *tab = db->fp64 ? (const void *)db->d_sigs64 : (const void *)db->d_sigs;
+  const void *qtab = db->fp64 ? (const void *)db->d_qsigs64 : (const void *)db->d_qsigs;
+  DSLAM_CUDA(launch_sc_rescore_topk(db->d_topk, tab, db->fp64 ? 1 : 0, db->d_ids, qtab, nq, db->n_cells, db->n_sectors, db->d_exact, db->d_best,
+                                    pub == kToDevice ? nullptr : db->d_words, seq, pub == kExchange ? &db->xchg : nullptr,
+                                    pub == kExchange ? db->xseq++ : 0u, 0, db->d_ticket, s->stream));
   s->launches++;
+  return DSLAM_OK;
+}
+
+// wait for the 2 * nq self-validating words of query `seq` (mapped pinned memory the re-score kernel writes)
+int wait_words(dslam_scdb *db, int nq, unsigned seq, u64 *keys_out) {
+  const volatile u64 *w = db->h_words;
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  for (int k = 0; k < 2 * nq; k++) {
+    while ((unsigned)(w[k] & 0xffffffffull) != seq) {
+      if ((++spins & 0x3fff) == 0) {
+        const cudaError_t q = cudaStreamQuery(db->s->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "Scan-Context query");
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > db->s->timeout_s)
+          return fail(DSLAM_ETIMEOUT, "Scan-Context query did not publish its result within %.1f s", db->s->timeout_s);
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  for (int q = 0; q < nq; q++) {
+    keys_out[q] = (w[2 * q] & 0xffffffff00000000ull) | (w[2 * q + 1] >> 32);
+    if (keys_out[q] == kScXchgErrorKey) return fail(DSLAM_ETIMEOUT, "a peer rank did not join the Scan-Context query exchange in time");
+  }
   return DSLAM_OK;
 }
 
@@ -188,7 +320,7 @@ int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs
 
 extern "C" {
 
-int dslam_sc_create(dslam_session *s, int n_sectors, int n_rings, int capacity, dslam_scdb **out) {
+int dslam_sc_create_ex(dslam_session *s, int n_sectors, int n_rings, int capacity, int flags, dslam_scdb **out) {
   if (!s || !out) return fail(DSLAM_EINVAL, "null argument");
   *out = nullptr;
   if (n_sectors < 1 || n_rings < 1 || capacity < 1) return fail(DSLAM_EINVAL, "bad database geometry");
@@ -199,13 +331,15 @@ int dslam_sc_create(dslam_session *s, int n_sectors, int n_rings, int capacity, 
   dslam_scdb *db = new (std::nothrow) dslam_scdb();
   if (!db) return fail(DSLAM_ENOMEM, "out of host memory");
   db->s = s; db->n_sectors = n_sectors; db->n_rings = n_rings; db->n_cells = n_cells; db->capacity = capacity;
+  db->fp64 = (flags & DSLAM_SC_FP64) != 0;
   cudaError_t e = cudaMalloc((void **)&db->d_sigs, (size_t)capacity * n_cells * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_keys, (size_t)capacity * n_rings * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void **)&db->d_ids, (size_t)capacity * sizeof(int));
+  if (e == cudaSuccess && db->fp64) e = cudaMalloc((void **)&db->d_sigs64, (size_t)capacity * n_cells * sizeof(double));
   if (e == cudaSuccess) e = cudaEventCreate(&db->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&db->ev1);
   if (e != cudaSuccess) {
-    cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids);
+    cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids); cudaFree(db->d_sigs64);
     delete db;
     return cuda_fail(e, "dslam_sc_create");
   }
@@ -213,19 +347,29 @@ int dslam_sc_create(dslam_session *s, int n_sectors, int n_rings, int capacity, 
   return DSLAM_OK;
 }
 
+int dslam_sc_create(dslam_session *s, int n_sectors, int n_rings, int capacity, dslam_scdb **out) {
+  return dslam_sc_create_ex(s, n_sectors, n_rings, capacity, 0, out);
+}
+
 int dslam_sc_destroy(dslam_scdb *db) {
   if (!db) return DSLAM_OK;
   cudaSetDevice(db->s->device);
   cudaStreamSynchronize(db->s->stream);
+  for (int r = 0; r < 8; r++)
+    if (db->peer_mail[r]) cudaIpcCloseMemHandle(db->peer_mail[r]);
   if (db->comm) {
     NcclApi *api = nccl_api();
     if (api) api->CommDestroy(db->comm);
   }
-  cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids);
-  cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best); cudaFree(db->d_gather);
+  cudaFree(db->d_mail);
+  cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids); cudaFree(db->d_sigs64);
+  cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_qsigs64); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best);
+  cudaFree(db->d_gather); cudaFree(db->d_ticket);
   cudaFree(db->d_pts); cudaFree(db->d_mom); cudaFree(db->d_gen_sig64); cudaFree(db->d_cells); cudaFree(db->d_gen_sig); cudaFree(db->d_gen_key);
   cudaFree(db->d_scratch); cudaFree(db->d_pair_q); cudaFree(db->d_pair_row); cudaFree(db->d_pair_diff);
   if (db->h_keys) cudaFreeHost(db->h_keys);
+  if (db->h_words) cudaFreeHost(db->h_words);
+  if (db->h_qstage) cudaFreeHost(db->h_qstage);
   if (db->h_stage) cudaFreeHost(db->h_stage);
   cudaEventDestroy(db->ev0);
   cudaEventDestroy(db->ev1);
@@ -233,22 +377,9 @@ int dslam_sc_destroy(dslam_scdb *db) {
   return DSLAM_OK;
 }
 
-int dslam_sc_add(dslam_scdb *db, int n, const float *ringkeys, const float *sigs_dense, const int *global_ids) {
-  if (!db || n < 0) return fail(DSLAM_EINVAL, "bad argument");
-  if (n == 0) return DSLAM_OK;
-  if (!ringkeys || !sigs_dense) return fail(DSLAM_EINVAL, "null descriptor array");
-  if (db->n + n > db->capacity) return fail(DSLAM_ENOMEM, "database capacity %d exceeded (%d + %d)", db->capacity, db->n, n);
-  int last = db->ids.empty() ? -1 : db->ids.back();
-  for (int i = 0; i < n; i++) {
-    const int id = global_ids ? global_ids[i] : db->n + i;
-    if (id <= last) return fail(DSLAM_EINVAL, "global ids must be strictly ascending within a shard (%d after %d)", id, last);
-    last = id;
-  }
+// common tail of the append entry points: ids, bookkeeping
+static int sc_append_ids(dslam_scdb *db, int n, const int *global_ids) {
   dslam_session *s = db->s;
-  DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs + (size_t)db->n * db->n_cells, sigs_dense, (size_t)n * db->n_cells * sizeof(float), cudaMemcpyHostToDevice,
-                             s->stream));
-  DSLAM_CUDA(cudaMemcpyAsync(db->d_keys + (size_t)db->n * db->n_rings, ringkeys, (size_t)n * db->n_rings * sizeof(float), cudaMemcpyHostToDevice,
-                             s->stream));
   const size_t base = db->ids.size();
   for (int i = 0; i < n; i++) {
     const int id = global_ids ? global_ids[i] : db->n + i;
@@ -256,23 +387,76 @@ int dslam_sc_add(dslam_scdb *db, int n, const float *ringkeys, const float *sigs
     db->ids.push_back(id);
   }
   DSLAM_CUDA(cudaMemcpyAsync(db->d_ids + db->n, db->ids.data() + base, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-  // ids vector may reallocate on a later append: make sure the copy has consumed it
+  // the caller's arrays (and the ids vector, which may reallocate on a later append) must have been consumed on return
   DSLAM_CUDA(cudaStreamSynchronize(s->stream));
   db->n += n;
   return DSLAM_OK;
 }
+static int sc_check_append(dslam_scdb *db, int n, const int *global_ids) {
+  int last = db->ids.empty() ? -1 : db->ids.back();
+  for (int i = 0; i < n; i++) {
+    const int id = global_ids ? global_ids[i] : db->n + i;
+    if (id <= last) return fail(DSLAM_EINVAL, "global ids must be strictly ascending within a shard (%d after %d)", id, last);
+    last = id;
+  }
+  return ensure_capacity(db, db->n + n);
+}
+
+int dslam_sc_add(dslam_scdb *db, int n, const float *ringkeys, const float *sigs_dense, const int *global_ids) {
+  if (!db || n < 0) return fail(DSLAM_EINVAL, "bad argument");
+  if (n == 0) return DSLAM_OK;
+  if (!ringkeys || !sigs_dense) return fail(DSLAM_EINVAL, "null descriptor array");
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  const int rc = sc_check_append(db, n, global_ids);
+  if (rc != DSLAM_OK) return rc;
+  dslam_session *s = db->s;
+  DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs + (size_t)db->n * db->n_cells, sigs_dense, (size_t)n * db->n_cells * sizeof(float), cudaMemcpyHostToDevice,
+                             s->stream));
+  if (db->fp64)
+    DSLAM_CUDA(launch_sc_widen(db->d_sigs + (size_t)db->n * db->n_cells, db->d_sigs64 + (size_t)db->n * db->n_cells, (size_t)n * db->n_cells, s->stream));
+  DSLAM_CUDA(cudaMemcpyAsync(db->d_keys + (size_t)db->n * db->n_rings, ringkeys, (size_t)n * db->n_rings * sizeof(float), cudaMemcpyHostToDevice,
+                             s->stream));
+  return sc_append_ids(db, n, global_ids);
+}
+
+// the reference's values (SigType = vector<pair<int, double>>, ScanContext.h:24) kept as doubles for the exact re-score
+int dslam_sc_add64(dslam_scdb *db, int n, const float *ringkeys, const double *sigs_dense64, const int *global_ids) {
+  if (!db || n < 0) return fail(DSLAM_EINVAL, "bad argument");
+  if (!db->fp64) return fail(DSLAM_ESTATE, "dslam_sc_add64 needs a database created with DSLAM_SC_FP64");
+  if (n == 0) return DSLAM_OK;
+  if (!ringkeys || !sigs_dense64) return fail(DSLAM_EINVAL, "null descriptor array");
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  const int rc = sc_check_append(db, n, global_ids);
+  if (rc != DSLAM_OK) return rc;
+  dslam_session *s = db->s;
+  DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs64 + (size_t)db->n * db->n_cells, sigs_dense64, (size_t)n * db->n_cells * sizeof(double), cudaMemcpyHostToDevice,
+                             s->stream));
+  DSLAM_CUDA(launch_sc_narrow(db->d_sigs64 + (size_t)db->n * db->n_cells, db->d_sigs + (size_t)db->n * db->n_cells, (size_t)n * db->n_cells, s->stream));
+  DSLAM_CUDA(cudaMemcpyAsync(db->d_keys + (size_t)db->n * db->n_rings, ringkeys, (size_t)n * db->n_rings * sizeof(float), cudaMemcpyHostToDevice,
+                             s->stream));
+  return sc_append_ids(db, n, global_ids);
+}
 
 int dslam_sc_add_sparse(dslam_scdb *db, const float *ringkey, const int *idx, const double *val, int nnz, int global_id) {
   if (!db || !ringkey || nnz < 0 || (nnz > 0 && (!idx || !val))) return fail(DSLAM_EINVAL, "bad argument");
-  const int rc = ensure_stage(db, (size_t)db->n_cells);
+  const int rc = ensure_stage(db, (size_t)db->n_cells * 2);
   if (rc != DSLAM_OK) return rc;
   DSLAM_CUDA(cudaStreamSynchronize(db->s->stream));
+  const int id = global_id < 0 ? (db->ids.empty() ? 0 : db->ids.back() + 1) : global_id;
+  if (db->fp64) {  // the double values travel unrounded; the fp32 scan copy is derived on the device
+    double *st = reinterpret_cast<double *>(db->h_stage);
+    std::memset(st, 0, sizeof(double) * db->n_cells);
+    for (int i = 0; i < nnz; i++) {
+      if (idx[i] < 0 || idx[i] >= db->n_cells) return fail(DSLAM_EINVAL, "cell index %d out of range", idx[i]);
+      st[idx[i]] = val[i];
+    }
+    return dslam_sc_add64(db, 1, ringkey, st, &id);
+  }
   std::memset(db->h_stage, 0, sizeof(float) * db->n_cells);
   for (int i = 0; i < nnz; i++) {
     if (idx[i] < 0 || idx[i] >= db->n_cells) return fail(DSLAM_EINVAL, "cell index %d out of range", idx[i]);
-    db->h_stage[idx[i]] = (float)val[i];  // the device format is fp32
+    db->h_stage[idx[i]] = (float)val[i];  // fp32 database: the device format is fp32
   }
-  const int id = global_id < 0 ? (db->ids.empty() ? 0 : db->ids.back() + 1) : global_id;
   return dslam_sc_add(db, 1, ringkey, db->h_stage, &id);
 }
 
@@ -280,12 +464,15 @@ int dslam_sc_add_sparse(dslam_scdb *db, const float *ringkey, const int *idx, co
 int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar_range, float *ringkey_out, float *sig_dense_out,
                       double *sig_dense64_out, double tfm_pca_rig[16], int append, int global_id) {
   if (!db || !pts_xyz || n < 1 || !(lidar_range > 0)) return fail(DSLAM_EINVAL, "bad argument");
-  if (append && db->n + 1 > db->capacity) return fail(DSLAM_ENOMEM, "database capacity %d exceeded", db->capacity);
   const int last = db->ids.empty() ? -1 : db->ids.back();
   const int id = global_id < 0 ? last + 1 : global_id;
   if (append && id <= last) return fail(DSLAM_EINVAL, "global ids must be strictly ascending within a shard (%d after %d)", id, last);
   dslam_session *s = db->s;
   DSLAM_CUDA(cudaSetDevice(s->device));
+  if (append) {
+    const int rc = ensure_capacity(db, db->n + 1);
+    if (rc != DSLAM_OK) return rc;
+  }
   if (n > db->pts_cap) {
     cudaFree(db->d_pts);
     db->d_pts = nullptr;
@@ -323,6 +510,9 @@ int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar
   s->launches += 3;
   if (append) {  // the new descriptor goes into the database without touching the host
     DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs + (size_t)db->n * db->n_cells, db->d_gen_sig, (size_t)db->n_cells * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    if (db->fp64)
+      DSLAM_CUDA(cudaMemcpyAsync(db->d_sigs64 + (size_t)db->n * db->n_cells, db->d_gen_sig64, (size_t)db->n_cells * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s->stream));
     DSLAM_CUDA(cudaMemcpyAsync(db->d_keys + (size_t)db->n * db->n_rings, db->d_gen_key, (size_t)db->n_rings * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
     DSLAM_CUDA(cudaMemcpyAsync(db->d_ids + db->n, &id, sizeof(int), cudaMemcpyHostToDevice, s->stream));
   }
@@ -336,6 +526,79 @@ int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar
     db->n += 1;
   }
   return DSLAM_OK;
+}
+
+// ---- on-disk format (.scdb): the database shard as it lives in HBM ---------------------------------------------------
+//   header (64 bytes): magic "SCDB", u32 version = 1, u32 n_sectors, u32 n_rings, u32 rows, u32 flags (bit 0: fp64 table
+//   follows), 40 reserved bytes; then int32 ids[rows], fp32 ringkeys[rows][n_rings], fp32 sigs[rows][n_cells] and, with
+//   flag bit 0, fp64 sigs64[rows][n_cells].  Little endian, no padding.
+struct ScdbHeader {
+  char magic[4];
+  unsigned version, n_sectors, n_rings, rows, flags;
+  unsigned char reserved[40];
+};
+static_assert(sizeof(ScdbHeader) == 64, "ScdbHeader layout");
+
+int dslam_sc_save(dslam_scdb *db, const char *path) {
+  if (!db || !path) return fail(DSLAM_EINVAL, "null argument");
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(DSLAM_EINVAL, "cannot open %s for writing", path);
+  ScdbHeader h;
+  std::memset(&h, 0, sizeof(h));
+  std::memcpy(h.magic, "SCDB", 4);
+  h.version = 1; h.n_sectors = (unsigned)db->n_sectors; h.n_rings = (unsigned)db->n_rings; h.rows = (unsigned)db->n; h.flags = db->fp64 ? 1u : 0u;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  if (db->n > 0) ok = ok && fwrite(db->ids.data(), sizeof(int), (size_t)db->n, f) == (size_t)db->n;
+  std::vector<unsigned char> buf;
+  cudaError_t ce = cudaSuccess;
+  auto dump = [&](const void *dev, size_t bytes) {
+    if (bytes == 0 || ce != cudaSuccess) return;
+    buf.resize(bytes);
+    ce = cudaMemcpyAsync(buf.data(), dev, bytes, cudaMemcpyDeviceToHost, db->s->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(db->s->stream);
+    if (ce == cudaSuccess) ok = ok && fwrite(buf.data(), 1, bytes, f) == bytes;
+  };
+  dump(db->d_keys, (size_t)db->n * db->n_rings * sizeof(float));
+  dump(db->d_sigs, (size_t)db->n * db->n_cells * sizeof(float));
+  if (db->fp64) dump(db->d_sigs64, (size_t)db->n * db->n_cells * sizeof(double));
+  ok = (fclose(f) == 0) && ok;
+  if (ce != cudaSuccess) return cuda_fail(ce, "dslam_sc_save");
+  return ok ? DSLAM_OK : fail(DSLAM_EINVAL, "short write to %s", path);
+}
+
+// appends the rows of the file (its ids must ascend past the rows already present; geometry must match)
+int dslam_sc_load(dslam_scdb *db, const char *path, int *rows_out) {
+  if (!db || !path) return fail(DSLAM_EINVAL, "null argument");
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(DSLAM_EINVAL, "cannot open %s", path);
+  ScdbHeader h;
+  int rc = DSLAM_OK;
+  std::vector<int> ids;
+  std::vector<float> keys, sigs;
+  std::vector<double> sigs64;
+  if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "SCDB", 4) != 0 || h.version != 1)
+    rc = fail(DSLAM_EINVAL, "%s is not a version-1 .scdb file", path);
+  else if ((int)h.n_sectors != db->n_sectors || (int)h.n_rings != db->n_rings)
+    rc = fail(DSLAM_EINVAL, "%s holds %ux%u descriptors, the database %dx%d", path, h.n_sectors, h.n_rings, db->n_sectors, db->n_rings);
+  else {
+    const size_t n = h.rows;
+    ids.resize(n); keys.resize(n * db->n_rings); sigs.resize(n * db->n_cells);
+    bool ok = n == 0 || (fread(ids.data(), sizeof(int), n, f) == n && fread(keys.data(), sizeof(float), keys.size(), f) == keys.size() &&
+                         fread(sigs.data(), sizeof(float), sigs.size(), f) == sigs.size());
+    if (ok && (h.flags & 1u) && db->fp64 && n > 0) {
+      sigs64.resize(n * db->n_cells);
+      ok = fread(sigs64.data(), sizeof(double), sigs64.size(), f) == sigs64.size();
+    }
+    if (!ok) rc = fail(DSLAM_EINVAL, "%s is truncated", path);
+  }
+  fclose(f);
+  if (rc != DSLAM_OK) return rc;
+  if (rows_out) *rows_out = (int)h.rows;
+  if (h.rows == 0) return DSLAM_OK;
+  if (!sigs64.empty()) return dslam_sc_add64(db, (int)h.rows, keys.data(), sigs64.data(), ids.data());
+  return dslam_sc_add(db, (int)h.rows, keys.data(), sigs.data(), ids.data());
 }
 
 int dslam_sc_size(dslam_scdb *db, int *n_local) {
@@ -386,16 +649,19 @@ int dslam_sc_search_ringkey(dslam_scdb *db, int nq, const float *ringkeys, int k
   return DSLAM_OK;
 }
 
-int dslam_sc_search_sc(dslam_scdb *db, int nq, const float *sigs_dense, const int *candidates, int n_cand, int *res_idx, float *res_diff) {
-  if (!db || nq < 1 || !sigs_dense || !candidates || n_cand < 1 || !res_idx || !res_diff) return fail(DSLAM_EINVAL, "bad argument");
+static int sc_search_sc_impl(dslam_scdb *db, int nq, const float *sigs_dense, const double *sigs_dense64, const int *candidates, int n_cand,
+                             int *res_idx, float *res_diff) {
+  if (!db || nq < 1 || (!sigs_dense && !sigs_dense64) || !candidates || n_cand < 1 || !res_idx || !res_diff) return fail(DSLAM_EINVAL, "bad argument");
   if (db->world > 1) return fail(DSLAM_ESTATE, "dslam_sc_search_sc needs the candidates' rows on this rank; use dslam_sc_query on a sharded database");
-  int rc = upload_queries(db, nq, nullptr, sigs_dense);
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  int rc = upload_queries(db, nq, nullptr, sigs_dense, sigs_dense64);
   if (rc != DSLAM_OK) return rc;
   const int np = nq * n_cand;
   if (np > db->paircap) {
     cudaFree(db->d_pair_q); cudaFree(db->d_pair_row); cudaFree(db->d_pair_diff);
     db->d_pair_q = db->d_pair_row = nullptr;
     db->d_pair_diff = nullptr;
+    db->paircap = 0;
     DSLAM_CUDA(cudaMalloc((void **)&db->d_pair_q, (size_t)np * sizeof(int)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_pair_row, (size_t)np * sizeof(int)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_pair_diff, (size_t)np * sizeof(float)));
@@ -417,7 +683,9 @@ int dslam_sc_search_sc(dslam_scdb *db, int nq, const float *sigs_dense, const in
   dslam_session *s = db->s;
   DSLAM_CUDA(cudaMemcpyAsync(db->d_pair_q, pq.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, s->stream));
   DSLAM_CUDA(cudaMemcpyAsync(db->d_pair_row, prow.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-  DSLAM_CUDA(launch_sc_rescore_pairs(db->d_pair_q, db->d_pair_row, np, db->d_sigs, db->d_qsigs, db->n_cells, db->n_sectors, db->d_pair_diff,
+  const void *tab = db->fp64 ? (const void *)db->d_sigs64 : (const void *)db->d_sigs;
+  const void *qtab = db->fp64 ? (const void *)db->d_qsigs64 : (const void *)db->d_qsigs;
+  DSLAM_CUDA(launch_sc_rescore_pairs(db->d_pair_q, db->d_pair_row, np, tab, db->fp64 ? 1 : 0, qtab, db->n_cells, db->n_sectors, db->d_pair_diff,
                                      s->stream));
   s->launches++;
   std::vector<float> diff((size_t)np);
@@ -441,15 +709,21 @@ int dslam_sc_search_sc(dslam_scdb *db, int nq, const float *sigs_dense, const in
   return DSLAM_OK;
 }
 
+int dslam_sc_search_sc(dslam_scdb *db, int nq, const float *sigs_dense, const int *candidates, int n_cand, int *res_idx, float *res_diff) {
+  return sc_search_sc_impl(db, nq, sigs_dense, nullptr, candidates, n_cand, res_idx, res_diff);
+}
+int dslam_sc_search_sc64(dslam_scdb *db, int nq, const double *sigs_dense64, const int *candidates, int n_cand, int *res_idx, float *res_diff) {
+  return sc_search_sc_impl(db, nq, nullptr, sigs_dense64, candidates, n_cand, res_idx, res_diff);
+}
+
 int dslam_sc_query_keys(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs_dense, float ringkey_thres, int max_id,
                         unsigned long long *keys_out) {
   if (!db || nq < 1 || !sigs_dense || !keys_out) return fail(DSLAM_EINVAL, "bad argument");
-  const int rc = local_query(db, nq, ringkeys, sigs_dense, ringkey_thres, max_id);
+  DSLAM_CUDA(cudaSetDevice(db->s->device));
+  unsigned seq = 0;
+  const int rc = local_query(db, nq, ringkeys, sigs_dense, nullptr, ringkey_thres, max_id, kToHost, &seq);
   if (rc != DSLAM_OK) return rc;
-  DSLAM_CUDA(cudaMemcpyAsync(db->h_keys, db->d_best, (size_t)nq * sizeof(u64), cudaMemcpyDeviceToHost, db->s->stream));
-  DSLAM_CUDA(cudaStreamSynchronize(db->s->stream));
-  std::memcpy(keys_out, db->h_keys, (size_t)nq * sizeof(u64));
-  return DSLAM_OK;
+  return wait_words(db, nq, seq, keys_out);
 }
 
 int dslam_sc_decode_key(unsigned long long key, int *id, float *dist) {
@@ -463,27 +737,56 @@ int dslam_sc_decode_key(unsigned long long key, int *id, float *dist) {
   return DSLAM_OK;
 }
 
-int dslam_sc_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs_dense, float ringkey_thres, int max_id, int *res_idx,
-                   float *res_diff) {
-  if (!db || nq < 1 || !sigs_dense || !res_idx) return fail(DSLAM_EINVAL, "bad argument");
-  const int rc = local_query(db, nq, ringkeys, sigs_dense, ringkey_thres, max_id);
-  if (rc != DSLAM_OK) return rc;
+// One query batch against the whole (possibly sharded) database.  Single GPU: scan -> re-score -> the kernel writes the
+// result words the host spins on.  Sharded: the re-score kernel additionally min-combines the keys in every rank's NVLink
+// mailbox and publishes the combined keys (collective call: every rank passes the same batch).  Fallback exchange
+// (no peer access, or DSLAM_SC_EXCHANGE=nccl): one ncclAllReduce(min, uint64 x Q) + a D2H copy.
+static int sc_query_impl(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs_dense, const double *sigs_dense64, float ringkey_thres,
+                         int max_id, int *res_idx, float *res_diff) {
+  if (!db || nq < 1 || (!sigs_dense && !sigs_dense64) || !res_idx) return fail(DSLAM_EINVAL, "bad argument");
   dslam_session *s = db->s;
-  if (db->comm) {
-    NcclApi *api = nccl_api();
-    const ncclResult_t r = api->AllReduce(db->d_best, db->d_best, (size_t)nq, ncclUint64, ncclMin, db->comm, s->stream);
-    if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+  DSLAM_CUDA(cudaSetDevice(s->device));
+  const int chunk_max = db->comm && db->p2p ? kScXchgMaxQ : nq;
+  std::vector<u64> keys((size_t)nq);
+  for (int q0 = 0; q0 < nq; q0 += chunk_max) {
+    const int nqc = std::min(chunk_max, nq - q0);
+    const float *rk = ringkeys ? ringkeys + (size_t)q0 * db->n_rings : nullptr;
+    const float *sg = sigs_dense ? sigs_dense + (size_t)q0 * db->n_cells : nullptr;
+    const double *sg64 = sigs_dense64 ? sigs_dense64 + (size_t)q0 * db->n_cells : nullptr;
+    unsigned seq = 0;
+    if (db->comm && !db->p2p) {
+      int rc = local_query(db, nqc, rk, sg, sg64, ringkey_thres, max_id, kToDevice, &seq);
+      if (rc != DSLAM_OK) return rc;
+      NcclApi *api = nccl_api();
+      const ncclResult_t r = api->AllReduce(db->d_best, db->d_best, (size_t)nqc, ncclUint64, ncclMin, db->comm, s->stream);
+      if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+      DSLAM_CUDA(cudaMemcpyAsync(db->h_keys, db->d_best, (size_t)nqc * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+      DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+      std::memcpy(keys.data() + q0, db->h_keys, (size_t)nqc * sizeof(u64));
+    } else {
+      int rc = local_query(db, nqc, rk, sg, sg64, ringkey_thres, max_id, db->comm ? kExchange : kToHost, &seq);
+      if (rc != DSLAM_OK) return rc;
+      rc = wait_words(db, nqc, seq, keys.data() + q0);
+      if (rc != DSLAM_OK) return rc;
+    }
   }
-  DSLAM_CUDA(cudaMemcpyAsync(db->h_keys, db->d_best, (size_t)nq * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
-  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
   for (int q = 0; q < nq; q++) {
     int id;
     float d;
-    dslam_sc_decode_key(db->h_keys[q], &id, &d);
+    dslam_sc_decode_key(keys[q], &id, &d);
     res_idx[q] = id;
     if (res_diff) res_diff[q] = d;
   }
   return DSLAM_OK;
+}
+
+int dslam_sc_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs_dense, float ringkey_thres, int max_id, int *res_idx,
+                   float *res_diff) {
+  return sc_query_impl(db, nq, ringkeys, sigs_dense, nullptr, ringkey_thres, max_id, res_idx, res_diff);
+}
+int dslam_sc_query64(dslam_scdb *db, int nq, const float *ringkeys, const double *sigs_dense64, float ringkey_thres, int max_id, int *res_idx,
+                     float *res_diff) {
+  return sc_query_impl(db, nq, ringkeys, nullptr, sigs_dense64, ringkey_thres, max_id, res_idx, res_diff);
 }
 
 int dslam_sc_unique_id(unsigned char id128[128]) {
@@ -495,6 +798,63 @@ int dslam_sc_unique_id(unsigned char id128[128]) {
   const ncclResult_t r = api->GetUniqueId(&id);
   if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
   std::memcpy(id128, &id, 128);
+  return DSLAM_OK;
+}
+
+// NVLink mailboxes: every rank allocates one, exports it as a CUDA IPC handle, the handles travel through one ncclAllGather,
+// and every rank maps its peers' mailboxes (peer access enabled lazily by cudaIpcOpenMemHandle).  All ranks agree on the
+// outcome through one ncclAllReduce(min) of a success flag, so either all use the mailboxes or all use the NCCL exchange.
+static int sc_setup_mailboxes(dslam_scdb *db) {
+  NcclApi *api = nccl_api();
+  dslam_session *s = db->s;
+  const int world = db->world, rank = db->rank;
+  int ok = world <= 8 ? 1 : 0;
+  const char *mode = getenv("DSLAM_SC_EXCHANGE");
+  if (mode && !strcmp(mode, "nccl")) ok = 0;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc(&db->d_mail, sc_exchange_bytes()) != cudaSuccess) ok = 0;
+    if (ok && cudaMemsetAsync(db->d_mail, 0xff, sc_exchange_arrived_offset(), s->stream) != cudaSuccess) ok = 0;
+    if (ok && cudaMemsetAsync((char *)db->d_mail + sc_exchange_arrived_offset(), 0, 256, s->stream) != cudaSuccess) ok = 0;
+    if (ok && cudaStreamSynchronize(s->stream) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, db->d_mail) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+  }
+  // gather the handles (device buffers: NCCL moves device memory)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  unsigned char *d_h = nullptr;
+  std::vector<cudaIpcMemHandle_t> all((size_t)world);
+  DSLAM_CUDA(cudaMalloc((void **)&d_h, (size_t)64 * (world + 1)));
+  DSLAM_CUDA(cudaMemcpyAsync(d_h + (size_t)64 * world, &mine, 64, cudaMemcpyHostToDevice, s->stream));
+  ncclResult_t r = api->AllGather(d_h + (size_t)64 * world, d_h, 64, ncclChar, db->comm, s->stream);
+  if (r != ncclSuccess) { cudaFree(d_h); return nccl_fail(r, "ncclAllGather (mailbox handles)"); }
+  DSLAM_CUDA(cudaMemcpyAsync(all.data(), d_h, (size_t)64 * world, cudaMemcpyDeviceToHost, s->stream));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  if (ok) {
+    for (int p = 0; p < world && ok; p++) {
+      void *ptr = db->d_mail;
+      if (p != rank) {
+        ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+        db->peer_mail[p] = ptr;
+      }
+      db->xchg.keys[p] = reinterpret_cast<unsigned long long *>(ptr);
+      db->xchg.arrived[p] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ptr) + sc_exchange_arrived_offset());
+    }
+  }
+  // agreement: min over the ranks of the success flag
+  unsigned long long flag = ok ? 1ull : 0ull;
+  DSLAM_CUDA(cudaMemcpyAsync(d_h, &flag, 8, cudaMemcpyHostToDevice, s->stream));
+  r = api->AllReduce(d_h, d_h, 1, ncclUint64, ncclMin, db->comm, s->stream);
+  if (r != ncclSuccess) { cudaFree(d_h); return nccl_fail(r, "ncclAllReduce (mailbox agreement)"); }
+  DSLAM_CUDA(cudaMemcpyAsync(&flag, d_h, 8, cudaMemcpyDeviceToHost, s->stream));
+  DSLAM_CUDA(cudaStreamSynchronize(s->stream));
+  cudaFree(d_h);
+  db->p2p = flag == 1ull;
+  db->xchg.world = world;
+  db->xchg.rank = rank;
+  db->xseq = 0;
   return DSLAM_OK;
 }
 
@@ -513,6 +873,13 @@ int dslam_sc_comm_init(dslam_scdb *db, const unsigned char id128[128], int world
   db->world = world_size;
   db->rank = rank;
   db->qcap = 0;  // gather buffers depend on the world size
+  return sc_setup_mailboxes(db);
+}
+
+// 1 = the sharded query exchanges its keys through the NVLink mailboxes, 0 = through ncclAllReduce (or not sharded)
+int dslam_sc_exchange_mode(dslam_scdb *db, int *p2p_out) {
+  if (!db || !p2p_out) return fail(DSLAM_EINVAL, "null argument");
+  *p2p_out = db->comm && db->p2p ? 1 : 0;
   return DSLAM_OK;
 }
 

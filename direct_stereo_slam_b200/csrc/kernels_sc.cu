@@ -106,16 +106,20 @@ __global__ void __launch_bounds__(256) sc_ringkey_kernel(const float *__restrict
   __syncthreads();
   TopK t;
   t.init();
-  float row[64];
+  const bool vec4 = (dim & 3) == 0;
   for (int r = blockIdx.x * 256 + tid; r < n_rows; r += gridDim.x * 256) {
     const int id = ids[r];
     if (id >= max_id) continue;
     const float *kr = keys + (size_t)r * dim;
     float result = 0.f;
     int i = 0;
-    for (; i + 3 < dim; i += 4) {
+    for (; vec4 && i + 3 < dim; i += 4) {
       const float4 kv = __ldg(reinterpret_cast<const float4 *>(kr + i));
       const float d0 = qk[i] - kv.x, d1 = qk[i + 1] - kv.y, d2 = qk[i + 2] - kv.z, d3 = qk[i + 3] - kv.w;
+      result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    for (; i + 3 < dim; i += 4) {  // rows are only 16-B aligned when dim % 4 == 0: scalar loads otherwise, same arithmetic
+      const float d0 = qk[i] - __ldg(kr + i), d1 = qk[i + 1] - __ldg(kr + i + 1), d2 = qk[i + 2] - __ldg(kr + i + 2), d3 = qk[i + 3] - __ldg(kr + i + 3);
       result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
     for (; i < dim; i++) {
@@ -124,7 +128,6 @@ __global__ void __launch_bounds__(256) sc_ringkey_kernel(const float *__restrict
     }
     t.insert(make_key(result, id));
   }
-  (void)row;
   u64 out[kScTopK];
   warp_merge(t, out);
   if (lane == 0) {
@@ -163,13 +166,48 @@ __global__ void __launch_bounds__(32) sc_merge_kernel(const u64 *__restrict__ sc
   }
 }
 
+// ---- fused final merge of the scan kernels -----------------------------------------------------------------------
+// Every CTA has written its per-query list to scratch[q][cta][K]; one thread then takes a ticket (acq_rel: releases this
+// CTA's lists, ordered before it through the CTA barrier, and acquires those of the CTAs that came earlier).  The CTA that
+// draws the last ticket merges the gridDim.x lists of every query — a warp per query, the same TopK / warp_merge as the
+// per-CTA stage — so no second launch sits between the scan and the exact re-score (it was 11 us of a 1-CTA kernel).
+// Returns true in the threads of the last CTA.  `sync` is the CTA-wide barrier of the caller's thread set.
+template <typename SyncFn>
+__device__ __forceinline__ bool sc_take_ticket(unsigned *ticket, bool elected, int *s_flag, SyncFn sync) {
+  sync();  // the lists of this CTA are written
+  if (elected) {
+    unsigned t;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    *s_flag = (t == gridDim.x - 1);
+  }
+  sync();
+  return *s_flag != 0;
+}
+__device__ __forceinline__ void sc_merge_lists(const u64 *__restrict__ scratch, int nlists, int nqc, int warp, int nwarps, int lane,
+                                               u64 *__restrict__ out) {
+  for (int q = warp; q < nqc; q += nwarps) {
+    TopK t;
+    t.init();
+    const u64 *src = scratch + (size_t)q * nlists * kScTopK;
+    for (int i = lane; i < nlists * kScTopK; i += 32) t.insert(__ldcg(src + i));
+    u64 o[kScTopK];
+    warp_merge(t, o);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) out[(size_t)q * kScTopK + i] = o[i];
+    }
+  }
+}
+
 // ---- sector-cosine scan: persistent grid, 16 warps per CTA, warp streams rows, lane q owns query q ------------
 // dynamic smem: qs[nqc][n_cells] floats followed by qkeys[nqc][key_dim]
 __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__restrict__ sigs, const float *__restrict__ keys,
                                                               const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
                                                               const float *__restrict__ q_sigs, const float *__restrict__ q_keys, int nqc,
-                                                              float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch) {
+                                                              float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch,
+                                                              unsigned *__restrict__ ticket, u64 *__restrict__ out) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int s_last;
   float *qs = smem;
   float *qk = smem + (size_t)nqc * n_cells;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -245,8 +283,11 @@ __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__re
     }
     u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
 #pragma unroll
-    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+    for (int i = 0; i < kScTopK; i++) __stcg(dst + i, m.k[i]);
   }
+  if (!sc_take_ticket(ticket, tid == 0, &s_last, [] { __syncthreads(); })) return;
+  sc_merge_lists(scratch, gridDim.x, nqc, warp, kScanWarps, lane, out);
+  if (tid == 0) *ticket = 0;  // the next launch on this stream starts after this grid has drained
 }
 
 // ---- sector-cosine scan, batched flavour (query batches > 8): register-blocked tiles fed by TMA ----------------
@@ -343,8 +384,10 @@ __device__ __forceinline__ void sc_tile_stage(const float4 *__restrict__ A, cons
 __global__ void __launch_bounds__(kTileThreads, 1)
     sc_scan_tile_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_q, const float *__restrict__ keys,
                         const int *__restrict__ ids, int n_rows, int n_cells, int key_dim, const float *__restrict__ q_keys, int nqc,
-                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch) {
+                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch,
+                        unsigned *__restrict__ ticket, u64 *__restrict__ out) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_last;
   unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-B alignment
   float *sA = reinterpret_cast<float *>(base);
   float *sB = reinterpret_cast<float *>(base + (size_t)kTileStages * kStageABytes);
@@ -453,47 +496,94 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     }
     u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
 #pragma unroll
-    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+    for (int i = 0; i < kScTopK; i++) __stcg(dst + i, m.k[i]);
   }
+  // (the producer warp has returned: the consumers meet on their named barrier)
+  if (!sc_take_ticket(ticket, tid == 0, &s_last, [] { sc_consumer_sync(); })) return;
+  sc_merge_lists(scratch, gridDim.x, nqc, warp, kTileConsumers / 32, lane, out);
+  if (tid == 0) *ticket = 0;
 }
 
 // ---- exact re-score -------------------------------------------------------------------------------------------
 // search_sc's arithmetic (search_place.h:71-79) on dense descriptors: float cur_prod += double(q)*double(d) over the
-// cells where both are occupied, in ascending cell order; diff = (1 - cur_prod / sc_width) / 2.0.  The chain of
-// float roundings is inherently serial; a warp loads 32 cells at a time (coalesced), forms the exact double
-// products in parallel and walks only the non-zero ones in order (every lane carries the same running value).
-__device__ __forceinline__ float exact_sc_diff(const float *__restrict__ q, const float *__restrict__ d, int n_cells, int sc_width, int lane) {
+// cells where both are occupied, in ascending cell order; diff = (1 - cur_prod / sc_width) / 2.0.  The chain of float
+// roundings is inherently serial (F2F -> DADD -> F2F per term), so everything else is taken off it: a warp forms the
+// double products of 128 cells in parallel (coalesced loads, the next 128 cells already in flight), compacts the
+// non-zero ones in cell order into its shared-memory strip (ballot + popc, adding an exact zero is a no-op in the
+// reference's chain), and then every lane walks the strip with broadcast LDS.64 — no ballot / ffs / shuffle in the
+// dependent loop (that loop was 59 us per query with them).  T = float: fp32 signatures (the product of two floats is
+// exact in fp64); T = double: the reference's SigType values (ScanContext.h:24), product rounded to double as in C++.
+constexpr int kRescoreChunk = 128;
+template <typename T>
+__device__ __forceinline__ float exact_sc_diff(const T *__restrict__ q, const T *__restrict__ d, int n_cells, int sc_width, int lane,
+                                               double *__restrict__ strip /* [kRescoreChunk], this warp's */) {
+  constexpr int NJ = kRescoreChunk / 32;
   float cur = 0.f;
-  for (int base = 0; base < n_cells; base += 32) {
-    const int k = base + lane;
-    const float qv = k < n_cells ? q[k] : 0.f;
-    const float dv = k < n_cells ? __ldg(d + k) : 0.f;
-    const double p = __dmul_rn((double)qv, (double)dv);
-    unsigned m = __ballot_sync(0xffffffffu, qv != 0.f && dv != 0.f);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const double pl = __shfl_sync(0xffffffffu, p, l);
-      cur = __double2float_rn(__dadd_rn((double)cur, pl));
+  T qv[NJ], dv[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int k = 32 * j + lane;
+    qv[j] = k < n_cells ? q[k] : (T)0;
+    dv[j] = k < n_cells ? __ldg(d + k) : (T)0;
+  }
+  for (int base = 0; base < n_cells; base += kRescoreChunk) {
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const bool nz = qv[j] != (T)0 && dv[j] != (T)0;
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (nz) strip[cnt + __popc(m & ((1u << lane) - 1u))] = __dmul_rn((double)qv[j], (double)dv[j]);
+      cnt += __popc(m);
     }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {  // next chunk: in flight while the chain below runs
+      const int k = base + kRescoreChunk + 32 * j + lane;
+      qv[j] = k < n_cells ? q[k] : (T)0;
+      dv[j] = k < n_cells ? __ldg(d + k) : (T)0;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int i = 0; i < cnt; i++) cur = __double2float_rn(__dadd_rn((double)cur, strip[i]));
+    __syncwarp();
   }
   const float t = 1.0f - cur / (float)sc_width;
   return __double2float_rn((double)t / 2.0);
 }
 
-// one CTA per query, one warp per top-K entry: exact distance of each survivor, then the per-query best as a
-// packed (ordered dist bits << 32 | GLOBAL id) key — the value a multi-GPU min-reduction combines.
-__global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64 *__restrict__ topk, const float *__restrict__ sigs,
-                                                                       const int *__restrict__ ids, const float *__restrict__ q_sigs,
+// Cross-GPU exchange of the per-query best keys without a library collective: every rank holds, in its own HBM, a small
+// mailbox (kScXchgSlots slots x [keys[kScXchgMaxQ], arrived]) that all peers can reach over NVLink (CUDA IPC mappings).
+// A rank min-combines its keys into EVERY rank's mailbox (atom.sys.min.u64 — the packed (distance, id) keys make "min" the
+// argmin with ties to the lowest id), fences, and bumps every mailbox's arrival counter; the last CTA of the local grid
+// then waits until its own mailbox has heard from all `world` ranks and publishes the combined keys to the host.
+// Slot = query sequence number mod kScXchgSlots: a peer can run at most one query ahead of this rank (its next query
+// needs this rank's contribution), so a slot is long consumed and reset when it comes round again.
+constexpr int kScXchgSlots = 4;
+struct ScXchg {
+  int world, rank;
+  u64 *keys[8];       // keys[r]    : mailbox keys of rank r   [kScXchgSlots][kScXchgMaxQ]   (this rank's mapping)
+  unsigned *arrived[8];  // arrived[r]: arrival counters of rank r [kScXchgSlots]
+};
+
+// one CTA per query, one warp per top-K entry: exact distance of each survivor, the per-query best as a packed
+// (ordered dist bits << 32 | GLOBAL id) key, and — fused — the publication: straight to the host as self-validating
+// words (32 payload bits | query sequence number; the host spins on them, no D2H copy, no stream synchronise), after
+// the NVLink mailbox exchange above when the database is sharded.
+template <typename T>
+__global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64 *__restrict__ topk, const T *__restrict__ sigs,
+                                                                       const int *__restrict__ ids, const T *__restrict__ q_sigs,
                                                                        int n_cells, int sc_width, u64 *__restrict__ exact_keys,
-                                                                       u64 *__restrict__ best) {
+                                                                       u64 *__restrict__ best, u64 *__restrict__ host_words, unsigned seq,
+                                                                       const __grid_constant__ ScXchg X, int slot, int q0,
+                                                                       unsigned *__restrict__ ticket, unsigned long long timeout_ns) {
   __shared__ u64 sk[kScTopK];
+  __shared__ double strips[kScTopK][kRescoreChunk];
+  __shared__ int s_last;
   const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u64 key = topk[(size_t)q * kScTopK + warp];
   u64 out = kKeyMax;
   if (key != kKeyMax) {
     const int row = (int)(unsigned)(key & 0xffffffffull);
-    const float diff = exact_sc_diff(q_sigs + (size_t)q * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane);
+    const float diff = exact_sc_diff<T>(q_sigs + (size_t)q * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane, strips[warp]);
     out = make_key(diff, ids[row]);
   }
   if (lane == 0) {
@@ -501,24 +591,86 @@ __global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64
     if (exact_keys) exact_keys[(size_t)q * kScTopK + warp] = out;
   }
   __syncthreads();
+  if (threadIdx.x != 0 && X.world <= 1) return;
+  u64 b = kKeyMax;
   if (threadIdx.x == 0) {
-    u64 b = sk[0];
+    b = sk[0];
 #pragma unroll
     for (int i = 1; i < kScTopK; i++) b = sk[i] < b ? sk[i] : b;
     best[q] = b;
   }
+  if (X.world <= 1) {
+    if (host_words) {
+      host_words[2 * (size_t)(q0 + q)] = (b & 0xffffffff00000000ull) | seq;
+      host_words[2 * (size_t)(q0 + q) + 1] = (b << 32) | seq;
+    }
+    return;
+  }
+  // ---- sharded: NVLink mailbox exchange (slot = exchange sequence number mod kScXchgSlots, the same on every rank) ----
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < X.world; r++) {
+      u64 *dst = X.keys[r] + (size_t)slot * kScXchgMaxQ + q;
+      asm volatile("red.relaxed.sys.global.min.u64 [%0], %1;" ::"l"(dst), "l"(b) : "memory");
+    }
+    __threadfence_system();
+    unsigned t;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of this rank: all local contributions are out -> announce to every mailbox, wait for all ranks, publish
+  unsigned *mine = X.arrived[X.rank] + slot;
+  if (threadIdx.x == 0) {
+    *ticket = 0;
+    __threadfence_system();
+    for (int r = 0; r < X.world; r++) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(X.arrived[r] + slot) : "memory");
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    unsigned seen = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if (seen >= (unsigned)X.world) break;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) break;  // a peer never arrived: the host sees the error word instead of a hung GPU
+      __nanosleep(200);
+    }
+    s_last = seen >= (unsigned)X.world ? 1 : 2;
+  }
+  __syncthreads();
+  const bool ok = s_last == 1;
+  u64 *mykeys = X.keys[X.rank] + (size_t)slot * kScXchgMaxQ;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mykeys + i) : "memory");
+    if (!ok) v = kScXchgErrorKey;
+    best[i] = v;
+    if (host_words) {
+      host_words[2 * (size_t)(q0 + i)] = (v & 0xffffffff00000000ull) | seq;
+      host_words[2 * (size_t)(q0 + i) + 1] = (v << 32) | seq;
+    }
+    mykeys[i] = kKeyMax;  // reset for the query that reuses this slot (kScXchgSlots queries later)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *mine = 0;
+  }
 }
 
 // explicit (query, row) pairs: diff per pair (row < 0 -> skipped, diff = +inf)
+template <typename T>
 __global__ void __launch_bounds__(256) sc_rescore_pairs_kernel(const int *__restrict__ pair_q, const int *__restrict__ pair_row, int npairs,
-                                                               const float *__restrict__ sigs, const float *__restrict__ q_sigs, int n_cells,
+                                                               const T *__restrict__ sigs, const T *__restrict__ q_sigs, int n_cells,
                                                                int sc_width, float *__restrict__ diff_out) {
+  __shared__ double strips[8][kRescoreChunk];
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (p >= npairs) return;
   const int row = pair_row[p];
   float diff = __int_as_float(0x7f800000);
-  if (row >= 0) diff = exact_sc_diff(q_sigs + (size_t)pair_q[p] * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane);
+  if (row >= 0)
+    diff = exact_sc_diff<T>(q_sigs + (size_t)pair_q[p] * n_cells, sigs + (size_t)row * n_cells, n_cells, sc_width, lane, strips[threadIdx.x >> 5]);
   if (lane == 0) diff_out[p] = diff;
 }
 
@@ -631,25 +783,30 @@ __global__ void sc_fill_cells_kernel(u64 *cells, int n, double v) {
   if (i < n) cells[i] = order_double(v);
 }
 
-int g_num_sms = 0;
+// SM count of the CURRENT device (a process may hold sessions on several devices)
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return cached[dev];
 }
 
 }  // namespace
 
 constexpr int kRingGridX = 64;
 
+// per-CTA lists of one query chunk + (last 256 bytes) the tickets of the fused merges; the caller zeroes it once
 size_t sc_scratch_bytes(int nq) {
   const int lists = num_sms() > kRingGridX ? num_sms() : kRingGridX;
-  return (size_t)(nq > kQChunk ? nq : kQChunk) * lists * kScTopK * sizeof(u64);
+  return (size_t)(nq > kQChunk ? nq : kQChunk) * lists * kScTopK * sizeof(u64) + 256;
 }
+static size_t sc_ticket_offset_u64(int nq) { return (sc_scratch_bytes(nq) - 256) / sizeof(u64); }
 
 cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
                               unsigned long long *out, unsigned long long *scratch, cudaStream_t stream) {
@@ -692,14 +849,12 @@ void sc_set_scan_flavour(int f) { g_sc_scan_flavour = f; }
 
 static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                                         const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
-                                        int grid, cudaStream_t stream) {
+                                        unsigned *ticket, unsigned long long *out, int grid, cudaStream_t stream) {
   ScEncodeTiledFn enc = sc_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device and cheap: set on every launch (a process may drive several devices)
     cudaError_t e = cudaFuncSetAttribute(sc_scan_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   CUtensorMap map_db, map_q;
   const cuuint32_t estr[2] = {1, 1};
@@ -721,7 +876,7 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
   const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
   const int groups_per_cta = (n_groups + grid - 1) / grid;
   sc_scan_tile_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(map_db, map_q, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
-                                                                      max_id, sc_width, groups_per_cta, scratch);
+                                                                      max_id, sc_width, groups_per_cta, scratch, ticket, out);
   return cudaGetLastError();
 }
 
@@ -729,13 +884,11 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
                            const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *out,
                            unsigned long long *scratch, cudaStream_t stream) {
   if (n_cells % 4 != 0 || n_cells > 1280 || key_dim > 64) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  const size_t smem_max = (size_t)kQChunk * n_cells * 4 + kQChunk * key_dim * 4;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  {  // worst case of any descriptor shape this library accepts; per device and cheap, so set on every launch
+    cudaError_t e = cudaFuncSetAttribute(sc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQChunk * 1280 * 4 + kQChunk * 64 * 4);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
+  unsigned *ticket = reinterpret_cast<unsigned *>(scratch + sc_ticket_offset_u64(nq));
   const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
   for (int q0 = 0; q0 < nq; q0 += kQChunk) {
     const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
@@ -748,17 +901,20 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
     if (tiles) {
       const int n_groups = (n_rows + 63) / 64;
       if (grid > n_groups) grid = n_groups;
+      // every CTA of the grid must own at least one group (the ticket counts gridDim.x arrivals either way)
+      const int gpc = (n_groups + grid - 1) / grid;
+      grid = (n_groups + gpc - 1) / gpc;
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
-                                           ringkey_thres, max_id, sc_width, scratch, grid, stream);
+                                           ringkey_thres, max_id, sc_width, scratch, ticket, out + (size_t)q0 * kScTopK, grid, stream);
       if (e != cudaSuccess) return e;
     } else {
       size_t smem = (size_t)nqc * n_cells * 4 + (size_t)nqc * key_dim * 4;
       const size_t lists_bytes = (size_t)kScanWarps * kQChunk * kScTopK * sizeof(u64);
       if (smem < lists_bytes) smem = lists_bytes;
       sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
-                                                           q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch);
+                                                           q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch, ticket,
+                                                           out + (size_t)q0 * kScTopK);
     }
-    sc_merge_kernel<<<nqc, 32, 0, stream>>>(scratch, grid, out + (size_t)q0 * kScTopK);
   }
   return cudaGetLastError();
 }
@@ -784,17 +940,65 @@ cudaError_t launch_sc_bin_finalize(const double *pts, int n, const double mean[3
   return cudaGetLastError();
 }
 
-cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const float *sigs, const int *ids, const float *q_sigs, int nq, int n_cells,
-                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, cudaStream_t stream) {
+cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq, int n_cells,
+                                   int sc_width, unsigned long long *exact_keys, unsigned long long *best, unsigned long long *host_words,
+                                   unsigned seq, const ScExchange *xchg, unsigned xchg_seq, int q0, unsigned *ticket, cudaStream_t stream) {
   if (nq < 1) return cudaSuccess;
-  sc_rescore_topk_kernel<<<nq, 32 * kScTopK, 0, stream>>>(topk, sigs, ids, q_sigs, n_cells, sc_width, exact_keys, best);
+  const int slot = (int)(xchg_seq % kScXchgSlots);
+  ScXchg X;
+  std::memset(&X, 0, sizeof(X));
+  X.world = 1;
+  if (xchg && xchg->world > 1) {
+    if (xchg->world > 8 || nq > kScXchgMaxQ) return cudaErrorInvalidValue;
+    X.world = xchg->world;
+    X.rank = xchg->rank;
+    for (int r = 0; r < xchg->world; r++) {
+      X.keys[r] = xchg->keys[r];
+      X.arrived[r] = xchg->arrived[r];
+    }
+  }
+  const unsigned long long timeout_ns = 2000000000ull;
+  if (fp64)
+    sc_rescore_topk_kernel<double><<<nq, 32 * kScTopK, 0, stream>>>(topk, (const double *)sigs, ids, (const double *)q_sigs, n_cells, sc_width,
+                                                                    exact_keys, best, host_words, seq, X, slot, q0, ticket, timeout_ns);
+  else
+    sc_rescore_topk_kernel<float><<<nq, 32 * kScTopK, 0, stream>>>(topk, (const float *)sigs, ids, (const float *)q_sigs, n_cells, sc_width, exact_keys,
+                                                                   best, host_words, seq, X, slot, q0, ticket, timeout_ns);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const float *sigs, const float *q_sigs, int n_cells,
+cudaError_t launch_sc_rescore_pairs(const int *pair_q, const int *pair_row, int npairs, const void *sigs, int fp64, const void *q_sigs, int n_cells,
                                     int sc_width, float *diff_out, cudaStream_t stream) {
   if (npairs < 1) return cudaSuccess;
-  sc_rescore_pairs_kernel<<<(npairs + 7) / 8, 256, 0, stream>>>(pair_q, pair_row, npairs, sigs, q_sigs, n_cells, sc_width, diff_out);
+  if (fp64)
+    sc_rescore_pairs_kernel<double><<<(npairs + 7) / 8, 256, 0, stream>>>(pair_q, pair_row, npairs, (const double *)sigs, (const double *)q_sigs, n_cells,
+                                                                          sc_width, diff_out);
+  else
+    sc_rescore_pairs_kernel<float><<<(npairs + 7) / 8, 256, 0, stream>>>(pair_q, pair_row, npairs, (const float *)sigs, (const float *)q_sigs, n_cells,
+                                                                         sc_width, diff_out);
+  return cudaGetLastError();
+}
+
+size_t sc_exchange_arrived_offset() { return (size_t)kScXchgSlots * kScXchgMaxQ * sizeof(u64); }
+size_t sc_exchange_bytes() { return sc_exchange_arrived_offset() + 256; }
+
+// widen fp32 signatures to the fp64 side table (rows appended through the fp32 entry points of an fp64 database)
+__global__ void sc_widen_kernel(const float *__restrict__ src, double *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+__global__ void sc_narrow_kernel(const double *__restrict__ src, float *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+cudaError_t launch_sc_widen(const float *src, double *dst, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  sc_widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sc_narrow(const double *src, float *dst, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  sc_narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
   return cudaGetLastError();
 }
 

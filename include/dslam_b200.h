@@ -218,12 +218,27 @@ int dslam_pe_get_trace(dslam_pe *p, double *rows, int max_rows, int *rows_out);
  * sector*n_rings + ring, 0 = empty (ScanContext.cpp:119-141).  ids are insertion order; with world_size > 1
  * row i of the global DB lives on rank i % world_size. */
 int dslam_sc_create(dslam_session *s, int n_sectors, int n_rings, int capacity, dslam_scdb **out);
+/* flags: DSLAM_SC_FP64 keeps, next to the fp32 table the scan streams, the signature values as DOUBLES — the reference's
+ * SigType is vector<pair<int,double>> (ScanContext.h:24) and search_sc multiplies doubles (search_place.h:71-77) — and
+ * the exact re-score of the K survivors reads those, so res_diff equals the reference's on unrounded signatures
+ * (+9,600 B per row).  `capacity` is the initial allocation; the tables grow geometrically when it is exceeded. */
+#define DSLAM_SC_FP64 1
+int dslam_sc_create_ex(dslam_session *s, int n_sectors, int n_rings, int capacity, int flags, dslam_scdb **out);
 int dslam_sc_destroy(dslam_scdb *db);
 /* append n descriptors that belong to THIS shard; global_ids[n] strictly ascending (NULL = local running count) */
 int dslam_sc_add(dslam_scdb *db, int n, const float *ringkeys, const float *sigs_dense, const int *global_ids);
 /* append one descriptor in the reference's sparse form (SigType = vector<pair<int,double>>, ScanContext.h:24);
  * values are rounded to the database's fp32 storage format; global_id < 0 = previous id + 1 */
 int dslam_sc_add_sparse(dslam_scdb *db, const float *ringkey, const int *idx, const double *val, int nnz, int global_id);
+/* dslam_sc_add with double signatures (DSLAM_SC_FP64 databases): the doubles are stored as they are, the fp32 scan copy is
+ * derived from them on the device; dslam_sc_add_sparse keeps the doubles too on such a database */
+int dslam_sc_add64(dslam_scdb *db, int n, const float *ringkeys, const double *sigs_dense64, const int *global_ids);
+/* On-disk dump of the shard, ".scdb": 64-byte header {"SCDB", u32 version = 1, n_sectors, n_rings, rows,
+ * flags (bit 0: an fp64 table follows), 40 reserved bytes}, int32 ids[rows], fp32 ringkeys[rows][n_rings],
+ * fp32 sigs[rows][n_sectors*n_rings], then fp64 sigs64[rows][...] when flagged; little endian.  dslam_sc_load APPENDS the
+ * rows of a file to a database of the same geometry (ids must ascend past those present); *rows_out = rows read. */
+int dslam_sc_save(dslam_scdb *db, const char *path);
+int dslam_sc_load(dslam_scdb *db, const char *path, int *rows_out);
 /* ScanContext::generate on the device (src/loop_closure/loop_detection/ScanContext.cpp:19-142): PCA alignment of the
  * n x 3 fp64 cloud (the 3x3 eigen-decomposition runs on the host; eigenvectors are sign-normalised so that their largest
  * component is positive), polar max-height binning, ring key, per-sector L2 normalisation.  Outputs (any may be NULL):
@@ -241,13 +256,23 @@ int dslam_sc_search_ringkey(dslam_scdb *db, int nq, const float *ringkeys, int k
  * reference's arithmetic (float += double*double; (1 - prod/sc_width)/2; strict '>' running min from 1.1) */
 int dslam_sc_search_sc(dslam_scdb *db, int nq, const float *sigs_dense, const int *candidates, int n_cand, int *res_idx,
                        float *res_diff);
+/* the same with the query signatures as doubles (DSLAM_SC_FP64 databases): products are double * double rounded to double,
+ * exactly search_place.h:71-77 on the reference's SigType values */
+int dslam_sc_search_sc64(dslam_scdb *db, int nq, const double *sigs_dense64, const int *candidates, int n_cand, int *res_idx,
+                         float *res_diff);
 /* full sector-cosine scan of the whole (sharded) DB for a query batch: argmin id + distance per query among
  * ids < max_id, optionally gated by ring-key distance < ringkey_thres (pass a negative thres to disable the
  * gate).  The device scan keeps the top-K per query and re-scores those K in the reference's exact arithmetic
- * (float += double*double in cell order); with a communicator attached the per-rank winners are combined by
- * one NCCL all-reduce(min) of packed (dist,id) keys.  res_idx = -1 (res_diff = 1.1) when nothing qualifies. */
+ * (float += double*double in cell order); the re-score kernel publishes the result straight into mapped host memory.
+ * With a communicator attached (collective call: every rank passes the same batch) the per-rank winners are min-combined
+ * as packed (dist,id) keys in every rank's NVLink mailbox by that same kernel (system-scope atomics over CUDA IPC peer
+ * mappings; dslam_sc_exchange_mode reports 1), or — without peer access / with DSLAM_SC_EXCHANGE=nccl — by one NCCL
+ * all-reduce(min).  res_idx = -1 (res_diff = 1.1) when nothing qualifies. */
 int dslam_sc_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs_dense, float ringkey_thres, int max_id,
                    int *res_idx, float *res_diff);
+int dslam_sc_query64(dslam_scdb *db, int nq, const float *ringkeys, const double *sigs_dense64, float ringkey_thres, int max_id,
+                     int *res_idx, float *res_diff);
+int dslam_sc_exchange_mode(dslam_scdb *db, int *p2p_out);
 /* the same scan without the collective: the local shard's best per query as a packed key
  * (order-preserving bits of the exact distance << 32 | global id; all-ones = nothing qualified) — what the
  * all-reduce(min) combines; dslam_sc_decode_key unpacks one (id = -1, dist = 1.1 for the empty key). */

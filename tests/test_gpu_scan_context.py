@@ -297,3 +297,81 @@ def test_loop_closure_chain_malaga_config(session, oracle):
     print("revisits found: two-stage (FLANN-style k=3 ring-key gate) %d / %d, exhaustive scan %d / %d" % (found_two_stage, n_q, found_scan, n_q))
     assert found_scan >= int(0.8 * n_q)
     db.close()
+
+
+def test_fp64_database_matches_reference_on_unrounded_signatures(session, oracle, tmp_path):
+    """DSLAM_SC_FP64: the signatures keep the reference's double values (SigType = vector<pair<int, double>>, ScanContext.h:24),
+    the exact re-score multiplies doubles like search_place.h:71-77, so res_idx / res_diff equal the oracle — and, when
+    oracle/_ref is built, the reference's own search_sc compiled in place — on UNROUNDED inputs.  Also: capacity growth past the
+    initial allocation and the .scdb save / load round trip."""
+    rng = np.random.default_rng(19)
+    db = api.ScanContextDB(session, 64, fp64=True)  # grows: 260 rows appended below
+    ptr, idxs, vals, dense64, keys = [0], [], [], [], []
+    for r in range(260):
+        pts = rng.normal(0, 12, (2500, 3))
+        rk, si, sv, _ = oracle.sc_generate(pts)
+        db.add_sparse(rk, si, sv)
+        idxs.append(si)
+        vals.append(sv)
+        ptr.append(ptr[-1] + len(si))
+        d = np.zeros(1200, np.float64)
+        d[si] = sv
+        dense64.append(d)
+        keys.append(rk)
+    assert len(db) == 260
+    idxs, vals, dense64 = np.concatenate(idxs), np.concatenate(vals), np.stack(dense64)
+    ref = None
+    try:
+        import oracle as orc
+        ref = orc.ReferencePieces() if orc.ReferencePieces.available() else None
+    except Exception:
+        ref = None
+    for q in range(12):
+        cands = rng.choice(260, 3, replace=False).astype(np.int32)
+        qd = dense64[rng.integers(0, 260)] * (1.0 + rng.normal(0, 1e-3, 1200))  # doubles that are NOT fp32-representable
+        qd[rng.integers(0, 1200, 50)] = 0
+        qi = np.nonzero(qd)[0].astype(np.int32)
+        i_o, d_o = oracle.search_sc(qi, qd[qi], ptr, idxs, vals, cands)
+        i_g, d_g = db.search_sc64(qd, cands)
+        assert i_g[0] == i_o and d_g[0] == np.float32(d_o)
+        if ref is not None:
+            i_r, d_r = ref.search_sc(qi, qd[qi], ptr, idxs, vals, cands)
+            assert i_g[0] == i_r and d_g[0] == np.float32(d_r)
+        # full scan: fp32 ranking, fp64 exact re-score of the survivors == brute force over all rows in the reference's arithmetic
+        i_all, d_all = oracle.search_sc(qi, qd[qi], ptr, idxs, vals, np.arange(260, dtype=np.int32))
+        i_q, d_q = db.query64(qd)
+        assert i_q[0] == i_all and d_q[0] == np.float32(d_all)
+    # save / load round trip (fp64 table included)
+    path = tmp_path / "shard.scdb"
+    db.save(path)
+    db2 = api.ScanContextDB(session, 16, fp64=True)
+    assert db2.load(path) == 260 and len(db2) == 260
+    qd = dense64[7] * (1.0 + rng.normal(0, 1e-3, 1200))
+    assert db2.query64(qd)[0][0] == db.query64(qd)[0][0] == 7
+    assert np.array_equal(db2.query64(qd)[1].view(np.uint32), db.query64(qd)[1].view(np.uint32))
+    raw = np.fromfile(path, np.uint8)
+    assert raw[:4].tobytes() == b"SCDB" and len(raw) == 64 + 260 * (4 + 20 * 4 + 1200 * 4 + 1200 * 8)
+    # an fp32 database reads the same file (ignores the fp64 table) and finds the same row
+    db3 = api.ScanContextDB(session, 16)
+    assert db3.load(path) == 260
+    assert db3.query(qd.astype(np.float32))[0][0] == 7
+    for d in (db, db2, db3):
+        d.close()
+
+
+def test_ringkey_width_not_multiple_of_four(session, oracle):
+    """A 60x10 descriptor: ring-key rows are only 8-byte aligned — the kNN kernel must not use 16-byte loads there."""
+    rng = np.random.default_rng(4)
+    db = api.ScanContextDB(session, 128, n_sectors=60, n_rings=10)
+    key = rng.uniform(0, 1, (100, 10)).astype(np.float32)
+    sig = rng.normal(0, 1, (100, 600)).astype(np.float32)
+    db.add(key, sig)
+    qk = key[:5] + rng.normal(0, 0.01, (5, 10)).astype(np.float32)
+    cand, dist = db.search_ringkey(qk, k=3, thres=0.5)
+    for q in range(5):
+        c_o, d_o = oracle.search_ringkey(qk[q], key, k=3, thres=0.5)
+        assert np.array_equal(cand[q, :len(c_o)], c_o)
+        assert np.array_equal(dist[q, :len(c_o)].view(np.uint32), d_o.view(np.uint32))
+    idx, _ = db.query(sig[:4])
+    assert np.array_equal(idx, [0, 1, 2, 3])
+    db.close()

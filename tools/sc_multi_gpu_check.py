@@ -28,7 +28,13 @@ db.add(key[rows], sig[rows], global_ids=rows)
 ident = [api.ScanContextDB.unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ident, src=0)
 db.attach_comm(ident[0], world, rank)
+mode = db.exchange_mode()
 idx, diff = db.query(qs)
+for _ in range(6):  # the mailbox slots come round: repeated collective queries must keep giving the same answer
+    idx2, diff2 = db.query(qs)
+    assert np.array_equal(idx2, idx) and np.array_equal(diff2.view(np.uint32), diff.view(np.uint32)), "repeated sharded query differs"
+i1, d1 = db.query(qs[:1])
+assert i1[0] == idx[0] and d1[0] == diff[0]
 cand, cdist = db.search_ringkey(qk, k=3, thres=0.1)
 ok = True
 if rank == 0:
@@ -53,7 +59,7 @@ for _ in range(30):
 t = torch.tensor([float(np.median(lat)), db.last_scan_ms()], dtype=torch.float64, device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("world %d rows %d: parity %s, query(32) latency %.3f ms, scan kernel %.3f ms" % (world, n, "OK" if ok else "FAILED", t[0].item(), t[1].item()))
+    print("world %d rows %d exchange %s: parity %s, query(32) latency %.3f ms, scan kernel %.3f ms" % (world, n, mode, "OK" if ok else "FAILED", t[0].item(), t[1].item()))
 dist.barrier()
 db.close()
 dist.destroy_process_group()
