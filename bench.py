@@ -215,16 +215,18 @@ class GpuStreams:
         the PREVIOUS step) run concurrently — and (e2e) the host mirrors start draining on the frames' copy streams."""
         P = self._plans(k)
         left = P["left"]
+        mirrors = e2e is True  # e2e == "pose_only": host images in, poses / scales out, no pyramid mirrors
         if e2e:
-            for f in left:
-                f.wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
+            if mirrors:
+                for f in left:
+                    f.wait_host()  # the mirror this frame object produced two steps ago must have landed before it is reused
             P["left_fb"].upload()
             if P["right_fb"]:
                 P["right_fb"].upload()
-        P["left_fb"].build(stage_host=3 if e2e else 0, overlap=True)
+        P["left_fb"].build(stage_host=3 if mirrors else 0, overlap=True)
         if P["right_fb"]:
             P["right_fb"].build(overlap=True)
-        if e2e:
+        if mirrors:
             for i in range(self.n):
                 if self.is_kf(i, k):
                     left[i].download(wait=False)
@@ -263,7 +265,7 @@ class GpuStreams:
 def timed_steps(streams, session, steps, warmup, e2e, dist_barrier):
     for k in range(warmup):
         streams.step(k, e2e)
-    if e2e:
+    if e2e is True:
         streams.drain()
     session.sync()
     dist_barrier()
@@ -272,7 +274,7 @@ def timed_steps(streams, session, steps, warmup, e2e, dist_barrier):
     t0 = time.perf_counter()
     for k in range(steps):
         streams.step(warmup + k, e2e)
-    if e2e:
+    if e2e is True:
         streams.drain()
     session.mark(1)
     session.sync()
@@ -690,6 +692,34 @@ def parity_check(api, session, case):
                             "ok_equal": bool(ok == r0[0])}}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: keep this rank's host threads (LM groups, copy threads) and the pinned arenas they first touch on the CPUs
+    that are local to its GPU (sysfs local_cpulist of the GPU's PCI function), when that is a proper subset of the CPUs the
+    process may use.  Returns what was done, for the JSON line."""
+    info = {"numa_node": None, "local_cpus": None, "bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("0000"):
+            bdf = bdf[4:]  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        base = "/sys/bus/pci/devices/" + bdf
+        info["numa_node"] = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        info["local_cpus"] = len(local)
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            info["bound"] = True
+    except Exception as e:  # sysfs layout differs / container hides it: run unbound, say so
+        info["error"] = str(e)[:100]
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -740,6 +770,7 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    binding = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     session = api.Session(local_rank)
     cases = make_cases(args.cases, seed0=1000 + 16 * rank)
     streams = GpuStreams(api, session, cases, args.streams, kf_every=args.keyframe_every)
@@ -754,6 +785,8 @@ def main():
     host_times = session.host_times()
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------------------
     ms_e2e, _ = timed_steps(streams, session, args.steps, warmup, True, barrier)
+    # ---- the path's own end-to-end cost: host images in, poses / scales out, no host mirrors of the pyramid ------------------
+    ms_e2e_pose, _ = timed_steps(streams, session, args.steps, warmup, "pose_only", barrier)
     clocks = sampler.stop() if rank == 0 else None
     # ---- roofline: per-launch CUDA-event timing of the fused pose kernel over the same steps -----------------------------------
     session.profile(True)
@@ -803,9 +836,9 @@ def main():
     if dist is not None:
         import torch
 
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_e2e_pose], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_pose = float(t[0]), float(t[1]), float(t[2])
         tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(tl)
         launches = int(tl[0])
@@ -830,7 +863,12 @@ def main():
                            "multi_gpu": "replicas only (tracking does not shard); scan_context is the sharded piece",
                            "timing": "max(CUDA events on the session stream, host clock) over the K steps, max over ranks"},
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes() * world,
-                        "d2h_bytes_per_step": streams.d2h_bytes() * world},
+                        "d2h_bytes_per_step": streams.d2h_bytes() * world,
+                        "note": "contract complete: every frame's level-0 dI (and on keyframes all levels + absSquaredGrad) is mirrored into the "
+                                "reference's host layouts for the untouched DSO code that reads it; PCIe-bound (see e2e_pose_only and DESIGN.md 10)"},
+                "e2e_pose_only": {"value": frames / (ms_e2e_pose * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": streams.h2d_bytes() * world,
+                                  "d2h_bytes_per_step": args.streams * world * (7 * 8 + 2 * 8 + 5 * 8 + 4),
+                                  "note": "host images in, poses / affine / residuals / scales out; no host mirror of the pyramid"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "eval_kernel (fused calcRes*+calcGSSSE* of all pose / scale items of an LM round)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1], "peak_source": peak_src,
@@ -862,6 +900,7 @@ def main():
                                                    "event times do not add up to the step)"},
                              "sweep": sweep3},
                 "clocks": clocks,
+                "host": {"cpus": len(os.sched_getaffinity(0)), "ranks": world, "numa_binding": binding},
                 "host_ms_per_step": {k: (v / (args.steps + warmup) if k != "launches" else v) for k, v in host_times.items()},
                 "lm": {"evals_per_frame": float(np.sum([c["evals"] for c in counters])) / (args.streams * (2 * warmup + 2 * args.steps + min(args.steps, 5))),
                        "note": "fused residual+Jacobian evaluations (pose + scale LM rounds) per stereo frame"}}

@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdslam_b200.so")
+# DSLAM_LIB=<path> loads another build of the same library (A/B runs of kernel variants, tools/build_variants.sh)
+LIB_PATH = os.environ.get("DSLAM_LIB") or os.path.join(_HERE, "libdslam_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 c_f = C.POINTER(C.c_float)

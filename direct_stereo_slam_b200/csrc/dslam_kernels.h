@@ -141,11 +141,13 @@ constexpr int kScTopK = 8;
 // (float_bits(dist) << 32 | global_id) keys sorted ascending; out[nq][kScTopK], unused = ~0ull
 cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
                               unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
-// sector-cosine scan: per query top-kScTopK packed (approximate dist, LOCAL ROW) keys over rows with id < max_id and
-// (thres < 0 or ring dist < thres); ids must ascend with the row so that ties still resolve to the lowest id
+// sector-cosine scan: per query and CTA the top-kScTopK packed (approximate dist, LOCAL ROW) keys over rows with id < max_id
+// and (thres < 0 or ring dist < thres), written to scratch as lists[q][sc_list_stride()][K] (*nlists_out lists are valid per
+// query); the re-score kernel merges them.  ids must ascend with the row so that ties still resolve to the lowest id.
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim,
                            const float *q_sigs, const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width,
-                           unsigned long long *out, unsigned long long *scratch, cudaStream_t stream);
+                           unsigned long long *scratch, int *nlists_out, cudaStream_t stream);
+int sc_list_stride();
 size_t sc_scratch_bytes(int nq);
 // scan kernel selection: 0 = by batch size (default; DSLAM_SC_SCAN=stream|tile overrides), 1 = streaming, 2 = tiled
 void sc_set_scan_flavour(int flavour);
@@ -168,7 +170,7 @@ size_t sc_exchange_arrived_offset();
 // exact re-score of the scan's survivors in search_sc's arithmetic -> per-query best packed (dist, GLOBAL id) key, published
 // to host_words (mapped pinned, 2 self-validating words per query: high / low 32 key bits | seq) — after the mailbox
 // exchange when xchg->world > 1.  fp64: sigs / q_sigs are double tables (the reference's SigType values).
-cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq, int n_cells,
+cudaError_t launch_sc_rescore_topk(const unsigned long long *lists, int nlists, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq, int n_cells,
                                    int sc_width, unsigned long long *exact_keys, unsigned long long *best, unsigned long long *host_words,
                                    unsigned seq, const ScExchange *xchg, unsigned xchg_seq, int q0, unsigned *ticket, cudaStream_t stream);
 // exact distances of explicit (query, local row) pairs; row < 0 = skip (+inf)

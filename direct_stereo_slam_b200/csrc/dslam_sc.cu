@@ -160,7 +160,6 @@ int ensure_query_buffers(dslam_scdb *db, int nq) {
     cudaFree(db->d_scratch);
     db->d_scratch = nullptr;
     DSLAM_CUDA(cudaMalloc((void **)&db->d_scratch, sb));
-    DSLAM_CUDA(cudaMemsetAsync(db->d_scratch, 0, sb, db->s->stream));  // the tickets of the fused merges live in its tail
     db->scratch_bytes = sb;
   }
   const size_t hk = (size_t)std::max(32, nq) * kScTopK * world;
@@ -274,8 +273,9 @@ int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs
   if (rc != DSLAM_OK) return rc;
   dslam_session *s = db->s;
   DSLAM_CUDA(cudaEventRecord(db->ev0, s->stream));
+  int nlists = 0;
   DSLAM_CUDA(launch_sc_scan(db->d_sigs, db->d_keys, db->d_ids, db->n, db->n_cells, db->n_rings, db->d_qsigs, db->d_qkeys, nq, ringkey_thres,
-                            max_id, (float)db->n_sectors, db->d_topk, db->d_scratch, s->stream));
+                            max_id, (float)db->n_sectors, db->d_scratch, &nlists, s->stream));
   DSLAM_CUDA(cudaEventRecord(db->ev1, s->stream));
   db->have_scan_time = true;
   s->launches += (nq + 31) / 32;
@@ -284,7 +284,7 @@ int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs
   if (seq_out) *seq_out = seq;
   const void *tab = db->fp64 ? (const void *)db->d_sigs64 : (const void *)db->d_sigs;
   const void *qtab = db->fp64 ? (const void *)db->d_qsigs64 : (const void *)db->d_qsigs;
-  DSLAM_CUDA(launch_sc_rescore_topk(db->d_topk, tab, db->fp64 ? 1 : 0, db->d_ids, qtab, nq, db->n_cells, db->n_sectors, db->d_exact, db->d_best,
+  DSLAM_CUDA(launch_sc_rescore_topk(db->d_scratch, nlists, tab, db->fp64 ? 1 : 0, db->d_ids, qtab, nq, db->n_cells, db->n_sectors, db->d_exact, db->d_best,
                                     pub == kToDevice ? nullptr : db->d_words, seq, pub == kExchange ? &db->xchg : nullptr,
                                     pub == kExchange ? db->xseq++ : 0u, 0, db->d_ticket, s->stream));
   s->launches++;
@@ -503,7 +503,8 @@ int dslam_sc_generate(dslam_scdb *db, const double *pts_xyz, int n, double lidar
     for (int i = 0; i < 16; i++) tfm_pca_rig[i] = (i % 5 == 0) ? 1.0 : 0.0;
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) tfm_pca_rig[r * 4 + c] = v9[3 * r + c];
-    for (int r = 0; r < 3; r++) tfm_pca_rig[r * 4 + 3] = -(tfm_pca_rig[r * 4] * mom[0] + tfm_pca_rig[r * 4 + 1] * mom[1] + tfm_pca_rig[r * 4 + 2] * mom[2]);
+    for (int r = 0; r < 3; r++)  // Eigen's coefficient-based 3-term product: e0 + (e1 + e2), negation inside the coefficients
+      tfm_pca_rig[r * 4 + 3] = (-tfm_pca_rig[r * 4]) * mom[0] + ((-tfm_pca_rig[r * 4 + 1]) * mom[1] + (-tfm_pca_rig[r * 4 + 2]) * mom[2]);
   }
   DSLAM_CUDA(launch_sc_bin_finalize(db->d_pts, n, mom, v9, lidar_range, db->n_sectors, db->n_rings, db->d_cells, db->d_gen_key, db->d_gen_sig,
                                     db->d_gen_sig64, s->stream));

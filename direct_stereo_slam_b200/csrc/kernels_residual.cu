@@ -9,25 +9,31 @@
 //          TrackerAndScaler::calcGSSSEScale                                         :966-1005
 //          ScaleAccumulator::updateSSE_oneed src/scale_optimization/ScaleAccumulator.h:60-77
 //          getInterpolatedElement33        deps:dso/src/util/globalFuncs.h:75-89
+//   (PoseEstimator::calcRes / calcGSSSE, src/loop_closure/pose_estimation/PoseEstimator.cpp:84-296, is the pose flavour
+//    with 3-D point records.)
 //
-// Numerics contract (checked by tests/test_parity_gpu.py against oracle/dslam_oracle.cpp):
+// Numerics contract (checked by tests/test_gpu_tracker.py, test_gpu_full_size.py, test_gpu_golden.py against
+// oracle/dslam_oracle.cpp):
 //   * this translation unit is compiled with -fmad=false and every per-point expression is written in the
 //     reference's operation order, so warp, bilinear weights, residual, Huber weight, energy term and the
 //     Jacobian row are bit-identical to the fp32 CPU arithmetic;
-//   * the weighted outer product is accumulated as acc += (double)(J_r*w) * (double)J_c with an explicit
-//     DFMA — the product of two fp32 values is exact in fp64, so the only rounding is the fp64 add.  The
-//     reference's 4-lane / 3-tier fp32 SSE accumulation is strictly noisier; the oracle's "fp64" mode is this
-//     arithmetic, its "sse" mode is the reference's, and their distance is reported as the noise floor.
+//   * the weighted outer product is accumulated as acc += (double)(J_r*w) * (double)J_c — the product of two fp32 values
+//     is exact in fp64, so the only rounding is the fp64 add.  The reference's 4-lane / 3-tier fp32 SSE accumulation is
+//     strictly noisier; the oracle's "fp64" mode is this arithmetic, its "sse" mode is the reference's, and their
+//     distance is reported as the noise floor;
 //   * reduction order is fixed (thread-sequential, warp reduce-scatter tree, warps in order, CTAs in order),
 //     so results are bit-reproducible run to run for a given launch geometry.
 //
-// Data movement: one 16-B template record + four 16-B texel taps per point (gather through L1/L2; the
-// whole pyramid of a frame is L2-resident after the pyramid kernels wrote it).  Each thread keeps its
-// partial normal equations in registers; a warp folds 48 fp64 values with a reduce-scatter butterfly
-// (48+... = 48 double shuffles instead of 240), warps meet in shared memory, and each CTA publishes one
-// partial record; the last CTA of an item (ticket atomic) sums the partials in CTA order and writes the
-// result record directly into mapped pinned host memory as self-validating words (payload | sequence number) the
-// host spins on — no memcpy, no stream synchronise and no system-scope fence on the LM critical path.
+// Data movement: one 16-B template record + four 16-B texel taps per point — a data-dependent gather through L1/L2 (the
+// warp target is only known after the projection, so the taps cannot be a TMA tile; a cp.async-staged software pipeline
+// of the taps was built and measured in round 2: 15-35 % SLOWER, the kernel is not bound by the latency of one gather
+// but sits at 40-50 % of three units at once — L1 data-pipe wavefronts, the XU pipe (fp32<->fp64 conversions, IEEE
+// divisions) and instruction issue; profiles/r02_eval_kernel.md).  Each thread keeps its partial sums in registers; a
+// warp's 8x8 block goes through the FP64 tensor cores; a warp folds the remaining fp64 values with a reduce-scatter
+// butterfly, warps meet in shared memory, and each CTA publishes one partial record; the last CTA of an item (ticket
+// atomic) sums the partials in CTA order and writes the result record directly into mapped pinned host memory as
+// self-validating words (payload | sequence number) the host spins on — no memcpy, no stream synchronise and no
+// system-scope fence on the LM critical path.
 
 #include "dslam_kernels.h"
 
@@ -120,13 +126,71 @@ struct BatchT {
   EvalItem item[CAP];
 };
 
-// Per-point work of one item with per-thread fp64 accumulators.  Used for SCALE items (MODE 1: calcResScale +
-// calcGSSSEScale); pose items take the DMMA path of eval_pose_mma below (the MODE 0 branches here are the same arithmetic
-// in per-thread FMA form and are kept as the readable statement of what the MMA path computes).
-// acc layout: pose  [0..44] upper triangle of [J0..J7 r]^T w [J0..J7 r], [45] E, [46] shiftT, [47] shiftRT
-//             scale [0] JwJ, [1] Jwr, [2] rwr, [3] E, [4] shiftT, [5] shiftRT
-template <int MODE, int NV>
-__device__ __forceinline__ void eval_points(const EvalItem &it, int bx, double (&acc)[NV], int &nE, int &nSat, int &nInl) {
+enum { kPose = 0, kScale = 1, kPose3d = 2 };
+
+
+// Flow indicators (:754-784 / :1070-1100 / PoseEstimator.cpp:191-226): every 32nd record of level 0, whether or not it
+// projects into the image.  A separate dense pass — inside the main loop one lane per warp would drag the whole warp through
+// ~200 extra instructions per point.  Adds 2 x sumSquaredShiftT terms to accT and 2 x sumSquaredShiftRT terms to accRT.
+template <int KIND>
+__device__ __forceinline__ void flow_pass(const EvalItem &it, int bx, double &accT, double &accRT) {
+  const float4 *__restrict__ pts = it.pts;
+  const float fxl = it.fx, fyl = it.fy, cxl = it.cx, cyl = it.cy;
+  const int nflow = (it.n + 31) >> 5;
+  for (int kf = bx * kEvalThreads + threadIdx.x; kf < nflow; kf += it.ppt_stride) {
+    const float4 p = __ldg(pts + 32 * kf);
+    float sT1, sT2, sRT1, sRT2;
+    if (KIND == kPose3d) {
+      // same four probes, but on the raw (x, y) of the 3-D point with z replaced by 1 and measured against the projection
+      // (Ku0, Kv0) of the untransformed point
+      const float x = p.x, y = p.y, z = p.z;
+      const float Ku0 = fxl * (x / z) + cxl, Kv0 = fyl * (y / z) + cyl;
+      const float pt0 = dot3_xyz(it.M[0], it.M[1], it.M[2], x, y, z) + it.t[0];
+      const float pt1 = dot3_xyz(it.M[3], it.M[4], it.M[5], x, y, z) + it.t[1];
+      const float pt2 = dot3_xyz(it.M[6], it.M[7], it.M[8], x, y, z) + it.t[2];
+      const float Ku = fxl * (pt0 / pt2) + cxl, Kv = fyl * (pt1 / pt2) + cyl;
+      const float ptTz = 1.0f + it.t[2], ptT2z = 1.0f - it.t[2];
+      const float pt3z = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) - it.t[2];
+      const float KuT = fxl * ((x + it.t[0]) / ptTz) + cxl, KvT = fyl * ((y + it.t[1]) / ptTz) + cyl;
+      const float KuT2 = fxl * ((x - it.t[0]) / ptT2z) + cxl, KvT2 = fyl * ((y - it.t[1]) / ptT2z) + cyl;
+      const float Ku3 = fxl * ((dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) - it.t[0]) / pt3z) + cxl;
+      const float Kv3 = fyl * ((dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) - it.t[1]) / pt3z) + cyl;
+      sT1 = (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0);
+      sT2 = (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
+      sRT1 = (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0);
+      sRT2 = (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
+    } else {
+      const float x = p.x, y = p.y, id = p.z;
+      const float s = KIND == kScale ? it.p0 : 1.0f;  // (multiplying by the literal 1 is exact)
+      const float kx0 = dot3_xy1(s * it.Ki[0], s * it.Ki[1], s * it.Ki[2], x, y);
+      const float kx1 = dot3_xy1(s * it.Ki[3], s * it.Ki[4], s * it.Ki[5], x, y);
+      const float kx2 = dot3_xy1(s * it.Ki[6], s * it.Ki[7], s * it.Ki[8], x, y);
+      const float mx0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y);
+      const float mx1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y);
+      const float mx2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y);
+      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
+      // the point itself (pt = M*(x,y,1) + t*id), as in the main loop
+      const float ptz = mx2 + tT2;
+      const float Ku = fxl * ((mx0 + tT0) / ptz) + cxl, Kv = fyl * ((mx1 + tT1) / ptz) + cyl;
+      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
+      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
+      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
+      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
+      sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+    }
+    accT += (double)sT1;
+    accT += (double)sT2;
+    accRT += (double)sRT1;
+    accRT += (double)sRT2;
+  }
+}
+
+// Scale items: calcResScale + calcGSSSEScale with per-thread fp64 FMAs.
+// acc layout: [0] JwJ, [1] Jwr, [2] rwr, [3] E, [4] shiftT, [5] shiftRT
+__device__ __forceinline__ void eval_scale_points(const EvalItem &it, int bx, double (&acc)[kScaleVals], int &nE, int &nSat, int &nInl) {
   const int tid = threadIdx.x;
   const float4 *__restrict__ tex = it.tex;
   const float4 *__restrict__ pts = it.pts;
@@ -134,7 +198,6 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, int bx, double (
   const float fxl = it.fx, fyl = it.fy, cxl = it.cx, cyl = it.cy;
   const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
   const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
-  constexpr int iE = MODE == 0 ? 45 : 3, iT = MODE == 0 ? 46 : 4, iRT = MODE == 0 ? 47 : 5;
 
   int i = bx * kEvalThreads + tid;
   float4 p_next = i < n ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -142,19 +205,11 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, int bx, double (
     const float4 p = p_next;
     if (i + stride < n) p_next = __ldg(pts + i + stride);  // the next record is in flight while this point is processed
     const float x = p.x, y = p.y, id = p.z, refColor = p.w;
-    float pt0, pt1, pt2, rx0 = 0.f, rx1 = 0.f, rx2 = 0.f;
-    if (MODE == 0) {
-      // :747  pt = RKi * (x,y,1) + t*id
-      pt0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) + it.t[0] * id;
-      pt1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) + it.t[1] * id;
-      pt2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) + it.t[2] * id;
-    } else {
-      // :1061  pt = (scale*M) * (x,y,1) + t*id ; :1068  rx = M*(x,y,1) / id
-      const float s = it.p0;
-      pt0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y) + it.t[0] * id;
-      pt1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y) + it.t[1] * id;
-      pt2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y) + it.t[2] * id;
-    }
+    // :1061  pt = (scale*M) * (x,y,1) + t*id
+    const float s = it.p0;
+    const float pt0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y) + it.t[0] * id;
+    const float pt1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y) + it.t[1] * id;
+    const float pt2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y) + it.t[2] * id;
     const float u = pt0 / pt2;
     const float v = pt1 / pt2;
     const float Ku = fxl * u + cxl;
@@ -164,103 +219,34 @@ __device__ __forceinline__ void eval_points(const EvalItem &it, int bx, double (
     if (!(Ku > 2 && Kv > 2 && Ku < wlm3 && Kv < hlm3 && new_idepth > 0)) continue;
     const float3 hit = interp33(tex, Ku, Kv, wl);
     if (!isfinite(hit.x)) continue;
-    const float residual = MODE == 0 ? hit.x - (it.p0 * refColor + it.p1) : hit.x - refColor;
+    const float residual = hit.x - refColor;  // :1109 (no affine)
     const float absr = fabsf(residual);
     const float hw = absr < kHuberTH ? 1.0f : kHuberTH / absr;
     nE++;
     if (absr > cutoff) {
-      acc[iE] += (double)maxEnergy;
+      acc[3] += (double)maxEnergy;
       nSat++;
       continue;
     }
-    acc[iE] += (double)(hw * residual * residual * (2 - hw));
+    acc[3] += (double)(hw * residual * residual * (2 - hw));
     nInl++;
-
-    if (MODE == 0) {
-      // calcGSSSEPose :658-678, lane arithmetic of the SSE code
-      const float dx = hit.y * fxl, dy = hit.z * fyl;
-      float J[9];
-      J[0] = new_idepth * dx;
-      J[1] = new_idepth * dy;
-      J[2] = 0.0f - (new_idepth * ((u * dx) + (v * dy)));
-      J[3] = 0.0f - (((u * v) * dx) + (dy * (1.0f + (v * v))));
-      J[4] = ((u * v) * dy) + (dx * (1.0f + (u * u)));
-      J[5] = (u * dy) - (v * dx);
-      J[6] = it.p0 * (it.p2 - refColor);
-      J[7] = -1.0f;
-      J[8] = residual;
-      double Jd[9];
-#pragma unroll
-      for (int c = 0; c < 9; c++) Jd[c] = (double)J[c];
-      int e = 0;
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        const double Jw = (double)(J[r] * hw);
-#pragma unroll
-        for (int c = r; c < 9; c++, e++) acc[e] = fma(Jw, Jd[c], acc[e]);
-      }
-    } else {
-      // calcGSSSEScale :983-997 (rx = M*(x,y,1) / id, :1068)
-      rx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) / id;
-      rx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) / id;
-      rx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) / id;
-      const float tx = it.t[0], ty = it.t[1], tz = it.t[2];
-      const float dxfx = hit.y * fxl, dyfy = hit.z * fyl;
-      const float deno_sqrt = (it.p0 * rx2) + tz;
-      const float deno = 1.0f / (deno_sqrt * deno_sqrt);
-      const float xno = (rx0 * tz) - (rx2 * tx);
-      const float yno = (rx1 * tz) - (rx2 * ty);
-      const float J = (dxfx * (deno * xno)) + (dyfy * (deno * yno));
-      const double Jw = (double)(J * hw), rw = (double)(residual * hw);
-      acc[0] = fma(Jw, (double)J, acc[0]);
-      acc[1] = fma(Jw, (double)residual, acc[1]);
-      acc[2] = fma(rw, (double)residual, acc[2]);
-    }
+    // calcGSSSEScale :983-997 (rx = M*(x,y,1) / id, :1068)
+    const float rx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) / id;
+    const float rx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) / id;
+    const float rx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) / id;
+    const float tx = it.t[0], ty = it.t[1], tz = it.t[2];
+    const float dxfx = hit.y * fxl, dyfy = hit.z * fyl;
+    const float deno_sqrt = (it.p0 * rx2) + tz;
+    const float deno = 1.0f / (deno_sqrt * deno_sqrt);
+    const float xno = (rx0 * tz) - (rx2 * tx);
+    const float yno = (rx1 * tz) - (rx2 * ty);
+    const float J = (dxfx * (deno * xno)) + (dyfy * (deno * yno));
+    const double Jw = (double)(J * hw), rw = (double)(residual * hw);
+    acc[0] = fma(Jw, (double)J, acc[0]);
+    acc[1] = fma(Jw, (double)residual, acc[1]);
+    acc[2] = fma(rw, (double)residual, acc[2]);
   }
-
-  // Flow indicators (:754-784 / :1070-1100): every 32nd template point of level 0, whether or not it projects into
-  // the image.  Done as a separate dense pass — inside the main loop one lane per warp would drag the whole warp
-  // through ~200 extra instructions per point.
-  if (it.flags & 1) {
-    const int nflow = (n + 31) >> 5;
-    for (int k = bx * kEvalThreads + tid; k < nflow; k += stride) {
-      const float4 p = __ldg(pts + 32 * k);
-      const float x = p.x, y = p.y, id = p.z;
-      const float s = MODE == 0 ? 1.0f : it.p0;
-      float kx0, kx1, kx2, mx0, mx1, mx2;
-      if (MODE == 0) {
-        kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
-        kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
-        kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
-        mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
-        mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
-        mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
-      } else {
-        kx0 = dot3_xy1(s * it.Ki[0], s * it.Ki[1], s * it.Ki[2], x, y);
-        kx1 = dot3_xy1(s * it.Ki[3], s * it.Ki[4], s * it.Ki[5], x, y);
-        kx2 = dot3_xy1(s * it.Ki[6], s * it.Ki[7], s * it.Ki[8], x, y);
-        mx0 = dot3_xy1(s * it.M[0], s * it.M[1], s * it.M[2], x, y);
-        mx1 = dot3_xy1(s * it.M[3], s * it.M[4], s * it.M[5], x, y);
-        mx2 = dot3_xy1(s * it.M[6], s * it.M[7], s * it.M[8], x, y);
-      }
-      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
-      // the point itself (pt = M*(x,y,1) + t*id), as in the main loop
-      const float ptz = mx2 + tT2;
-      const float Ku = fxl * ((mx0 + tT0) / ptz) + cxl, Kv = fyl * ((mx1 + tT1) / ptz) + cyl;
-      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
-      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
-      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
-      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
-      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-      acc[iT] += (double)sT1;
-      acc[iT] += (double)sT2;
-      acc[iRT] += (double)sRT1;
-      acc[iRT] += (double)sRT2;
-    }
-  }
+  if (it.flags & 1) flow_pass<kScale>(it, bx, acc[4], acc[5]);
 }
 
 // D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor cores (DMMA).  Fragments: A[row = lane/4][col = lane%4],
@@ -275,11 +261,14 @@ __device__ __forceinline__ int tri9(int g, int n) { return 9 * g - (g * (g - 1))
 // Pose items: calcResPose + calcGSSSEPose with the 8x8 block H = sum_p (J_p w_p) J_p^T accumulated by DMMA.
 // A warp takes 32 template points per iteration; every lane warps / samples its point and forms its Jacobian row in the
 // reference's fp32 arithmetic, the rows go through shared memory (the transposition the MMA fragments need: lane (g, k)
-// of MMA m reads element g of point 4m + k) and eight m8n8k4 DMMAs add the 32 outer products to the warp's 8x8
+// of MMA m reads element g of point 4m + k; the two 16-B halves of a row are swapped for points 4..7 mod 8, which makes the
+// row stores bank-conflict free as well as the fragment loads — unswizzled, the stores were 2-way conflicted and cost 13 %
+// of the L1 data-pipe wavefronts) and eight m8n8k4 DMMAs add the 32 outer products to the warp's 8x8
 // accumulator — 2 registers per lane instead of 72 per thread, no warp reduction for H at all.  Products of fp32 values
 // are exact in fp64, so the result differs from the per-thread FMA form only in the order of the fp64 additions.
 // b = sum J w r, sum w r^2, E and the flow sums stay per lane (12 doubles) and are folded by a 16-wide reduce-scatter.
 // Results land in sred_w[48] (this warp's slot, pre-zeroed) in the oracle's acc layout.
+template <int KIND>  // kPose: template records (u, v, idepth, color); kPose3d: 3-D point records (PoseEstimator)
 __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double *sred_w, float *sJ, float *sJw, int &nE, int &nSat, int &nInl) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 *__restrict__ tex = it.tex;
@@ -289,7 +278,8 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double
   const float cutoff = it.cutoff, maxEnergy = it.maxEnergy;
   const float wlm3 = (float)(wl - 3), hlm3 = (float)(hl - 3);
   const int g = lane >> 2, k = lane & 3;
-  const bool point3d = (it.flags & 4) != 0;  // PoseEstimator flavour: records are 3-D points of the matched keyframe
+  constexpr bool point3d = KIND == kPose3d;  // PoseEstimator flavour: records are 3-D points of the matched keyframe
+  const int h0 = (lane >> 2) & 1;  // staging swizzle: rows 4..7 (mod 8) keep their 16-B halves swapped
 
   double c0 = 0.0, c1 = 0.0;  // H(g, 2k), H(g, 2k+1)
   double ext[16];             // [0..7] b, [8] sum w r^2, [9] E, [10] shiftT, [11] shiftRT
@@ -353,78 +343,25 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double
         }
       }
     }
-    // rows -> shared memory (conflict-free: 32 B per lane, contiguous), then the fragment gathers (bank = 8k + g)
+    // rows -> shared memory (32 B per lane, halves swizzled: every quarter-warp of the STS.128 covers all 32 banks), then
+    // the fragment gathers (bank = 8k + (g ^ swizzle): all 32 distinct)
     float4 *dJ = reinterpret_cast<float4 *>(sJ + lane * 8), *dW = reinterpret_cast<float4 *>(sJw + lane * 8);
-    dJ[0] = make_float4(J[0], J[1], J[2], J[3]);
-    dJ[1] = make_float4(J[4], J[5], J[6], J[7]);
-    dW[0] = make_float4(Jw[0], Jw[1], Jw[2], Jw[3]);
-    dW[1] = make_float4(Jw[4], Jw[5], Jw[6], Jw[7]);
+    dJ[h0] = make_float4(J[0], J[1], J[2], J[3]);
+    dJ[h0 ^ 1] = make_float4(J[4], J[5], J[6], J[7]);
+    dW[h0] = make_float4(Jw[0], Jw[1], Jw[2], Jw[3]);
+    dW[h0 ^ 1] = make_float4(Jw[4], Jw[5], Jw[6], Jw[7]);
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-      const double a = (double)sJw[(4 * m + k) * 8 + g];
-      const double b = (double)sJ[(4 * m + k) * 8 + g];
+      const int e = (4 * m + k) * 8 + (g ^ ((m & 1) << 2));
+      const double a = (double)sJw[e];
+      const double b = (double)sJ[e];
       dmma_8x8x4(c0, c1, a, b);
     }
     __syncwarp();
   }
 
-  // Flow indicators (:754-784): every 32nd template point of level 0, whether or not it projects into the image.
-  if ((it.flags & 1) && point3d) {
-    // PoseEstimator.cpp:191-226: same four probes, but on the raw (x, y) of the 3-D point with z replaced by 1 and
-    // measured against the projection (Ku0, Kv0) of the untransformed point.
-    const int nflow = (n + 31) >> 5;
-    for (int kf = bx * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
-      const float4 p = __ldg(pts + 32 * kf);
-      const float x = p.x, y = p.y, z = p.z;
-      const float Ku0 = fxl * (x / z) + cxl, Kv0 = fyl * (y / z) + cyl;
-      const float pt0 = dot3_xyz(it.M[0], it.M[1], it.M[2], x, y, z) + it.t[0];
-      const float pt1 = dot3_xyz(it.M[3], it.M[4], it.M[5], x, y, z) + it.t[1];
-      const float pt2 = dot3_xyz(it.M[6], it.M[7], it.M[8], x, y, z) + it.t[2];
-      const float Ku = fxl * (pt0 / pt2) + cxl, Kv = fyl * (pt1 / pt2) + cyl;
-      const float ptTz = 1.0f + it.t[2], ptT2z = 1.0f - it.t[2];
-      const float pt3z = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y) - it.t[2];
-      const float KuT = fxl * ((x + it.t[0]) / ptTz) + cxl, KvT = fyl * ((y + it.t[1]) / ptTz) + cyl;
-      const float KuT2 = fxl * ((x - it.t[0]) / ptT2z) + cxl, KvT2 = fyl * ((y - it.t[1]) / ptT2z) + cyl;
-      const float Ku3 = fxl * ((dot3_xy1(it.M[0], it.M[1], it.M[2], x, y) - it.t[0]) / pt3z) + cxl;
-      const float Kv3 = fyl * ((dot3_xy1(it.M[3], it.M[4], it.M[5], x, y) - it.t[1]) / pt3z) + cyl;
-      const float sT1 = (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0);
-      const float sT2 = (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
-      const float sRT1 = (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0);
-      const float sRT2 = (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
-      ext[10] += (double)sT1;
-      ext[10] += (double)sT2;
-      ext[11] += (double)sRT1;
-      ext[11] += (double)sRT2;
-    }
-  } else if (it.flags & 1) {
-    const int nflow = (n + 31) >> 5;
-    for (int kf = bx * kEvalThreads + threadIdx.x; kf < nflow; kf += stride) {
-      const float4 p = __ldg(pts + 32 * kf);
-      const float x = p.x, y = p.y, id = p.z;
-      const float kx0 = dot3_xy1(it.Ki[0], it.Ki[1], it.Ki[2], x, y);
-      const float kx1 = dot3_xy1(it.Ki[3], it.Ki[4], it.Ki[5], x, y);
-      const float kx2 = dot3_xy1(it.Ki[6], it.Ki[7], it.Ki[8], x, y);
-      const float mx0 = dot3_xy1(it.M[0], it.M[1], it.M[2], x, y);
-      const float mx1 = dot3_xy1(it.M[3], it.M[4], it.M[5], x, y);
-      const float mx2 = dot3_xy1(it.M[6], it.M[7], it.M[8], x, y);
-      const float tT0 = it.t[0] * id, tT1 = it.t[1] * id, tT2 = it.t[2] * id;
-      const float ptz = mx2 + tT2;
-      const float Ku = fxl * ((mx0 + tT0) / ptz) + cxl, Kv = fyl * ((mx1 + tT1) / ptz) + cyl;
-      const float ptT2z = kx2 + tT2, ptT2nz = kx2 - tT2, pt3z = mx2 - tT2;
-      const float KuT = fxl * ((kx0 + tT0) / ptT2z) + cxl, KvT = fyl * ((kx1 + tT1) / ptT2z) + cyl;
-      const float KuT2 = fxl * ((kx0 - tT0) / ptT2nz) + cxl, KvT2 = fyl * ((kx1 - tT1) / ptT2nz) + cyl;
-      const float Ku3 = fxl * ((mx0 - tT0) / pt3z) + cxl, Kv3 = fyl * ((mx1 - tT1) / pt3z) + cyl;
-      const float sT1 = (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-      const float sT2 = (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-      const float sRT1 = (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-      const float sRT2 = (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-      ext[10] += (double)sT1;
-      ext[10] += (double)sT2;
-      ext[11] += (double)sRT1;
-      ext[11] += (double)sRT2;
-    }
-  }
+  if (it.flags & 1) flow_pass<KIND>(it, bx, ext[10], ext[11]);
 
   // warp results -> this warp's slot of the CTA reduction buffer (oracle layout: upper triangle, E, shiftT, shiftRT)
   if (g <= 2 * k) sred_w[tri9(g, 2 * k)] = c0;
@@ -442,8 +379,11 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double
 // tracker and the scale optimiser of a stereo frame advance in the same launch).  The grid is flat: the CTAs of item 0,
 // then those of item 1, ... (EvalItem::cta_begin); a CTA finds its item by bisection over the <= 128 prefix entries in
 // constant memory, so items of very different sizes share a launch without idle CTAs.
+#ifndef DSLAM_EVAL_MIN_CTAS
+#define DSLAM_EVAL_MIN_CTAS 5
+#endif
 template <int MODE, int CAP>
-__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
+__global__ void __launch_bounds__(kEvalThreads, DSLAM_EVAL_MIN_CTAS) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
                                                            EvalResult *__restrict__ results, unsigned seq, int nitems) {
   constexpr int NV = MODE == 1 ? kScaleVals : kPoseVals;
   constexpr int NW = kEvalThreads / 32;
@@ -472,12 +412,15 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const __grid_constan
   int nE = 0, nSat = 0, nInl = 0;
   const bool scale_item = MODE == 1 || (MODE == 2 && (it.flags & 2));
   if (!scale_item) {
-    if (MODE != 1) eval_pose_mma(it, bx, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
+    if (MODE != 1) {
+      if (it.flags & 4) eval_pose_mma<kPose3d>(it, bx, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
+      else eval_pose_mma<kPose>(it, bx, sred[warp], sJ[MODE == 1 ? 0 : warp], sJw[MODE == 1 ? 0 : warp], nE, nSat, nInl);
+    }
   } else {
     double acc[kScaleVals];
 #pragma unroll
     for (int i = 0; i < kScaleVals; i++) acc[i] = 0.0;
-    eval_points<1, kScaleVals>(it, bx, acc, nE, nSat, nInl);
+    eval_scale_points(it, bx, acc, nE, nSat, nInl);
     WarpRS<kScaleVals>::run(acc, lane);
     if (WarpRS<kScaleVals>::writer(lane)) sred[warp][WarpRS<kScaleVals>::base(lane)] = acc[0];
   }

@@ -166,48 +166,14 @@ __global__ void __launch_bounds__(32) sc_merge_kernel(const u64 *__restrict__ sc
   }
 }
 
-// ---- fused final merge of the scan kernels -----------------------------------------------------------------------
-// Every CTA has written its per-query list to scratch[q][cta][K]; one thread then takes a ticket (acq_rel: releases this
-// CTA's lists, ordered before it through the CTA barrier, and acquires those of the CTAs that came earlier).  The CTA that
-// draws the last ticket merges the gridDim.x lists of every query — a warp per query, the same TopK / warp_merge as the
-// per-CTA stage — so no second launch sits between the scan and the exact re-score (it was 11 us of a 1-CTA kernel).
-// Returns true in the threads of the last CTA.  `sync` is the CTA-wide barrier of the caller's thread set.
-template <typename SyncFn>
-__device__ __forceinline__ bool sc_take_ticket(unsigned *ticket, bool elected, int *s_flag, SyncFn sync) {
-  sync();  // the lists of this CTA are written
-  if (elected) {
-    unsigned t;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
-    *s_flag = (t == gridDim.x - 1);
-  }
-  sync();
-  return *s_flag != 0;
-}
-__device__ __forceinline__ void sc_merge_lists(const u64 *__restrict__ scratch, int nlists, int nqc, int warp, int nwarps, int lane,
-                                               u64 *__restrict__ out) {
-  for (int q = warp; q < nqc; q += nwarps) {
-    TopK t;
-    t.init();
-    const u64 *src = scratch + (size_t)q * nlists * kScTopK;
-    for (int i = lane; i < nlists * kScTopK; i += 32) t.insert(__ldcg(src + i));
-    u64 o[kScTopK];
-    warp_merge(t, o);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < kScTopK; i++) out[(size_t)q * kScTopK + i] = o[i];
-    }
-  }
-}
-
 // ---- sector-cosine scan: persistent grid, 16 warps per CTA, warp streams rows, lane q owns query q ------------
 // dynamic smem: qs[nqc][n_cells] floats followed by qkeys[nqc][key_dim]
 __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__restrict__ sigs, const float *__restrict__ keys,
                                                               const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
                                                               const float *__restrict__ q_sigs, const float *__restrict__ q_keys, int nqc,
                                                               float ringkey_thres, int max_id, float sc_width, u64 *__restrict__ scratch,
-                                                              unsigned *__restrict__ ticket, u64 *__restrict__ out) {
+                                                              int list_stride) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ int s_last;
   float *qs = smem;
   float *qk = smem + (size_t)nqc * n_cells;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,13 +247,10 @@ __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__re
 #pragma unroll
       for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + tid) * kScTopK + i]);
     }
-    u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
+    u64 *dst = scratch + ((size_t)tid * list_stride + blockIdx.x) * kScTopK;  // lists[q][cta][K]: merged by the re-score kernel
 #pragma unroll
-    for (int i = 0; i < kScTopK; i++) __stcg(dst + i, m.k[i]);
+    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
   }
-  if (!sc_take_ticket(ticket, tid == 0, &s_last, [] { __syncthreads(); })) return;
-  sc_merge_lists(scratch, gridDim.x, nqc, warp, kScanWarps, lane, out);
-  if (tid == 0) *ticket = 0;  // the next launch on this stream starts after this grid has drained
 }
 
 // ---- sector-cosine scan, batched flavour (query batches > 8): register-blocked tiles fed by TMA ----------------
@@ -384,10 +347,8 @@ __device__ __forceinline__ void sc_tile_stage(const float4 *__restrict__ A, cons
 __global__ void __launch_bounds__(kTileThreads, 1)
     sc_scan_tile_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_q, const float *__restrict__ keys,
                         const int *__restrict__ ids, int n_rows, int n_cells, int key_dim, const float *__restrict__ q_keys, int nqc,
-                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch,
-                        unsigned *__restrict__ ticket, u64 *__restrict__ out) {
+                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch, int list_stride) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ int s_last;
   unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-B alignment
   float *sA = reinterpret_cast<float *>(base);
   float *sB = reinterpret_cast<float *>(base + (size_t)kTileStages * kStageABytes);
@@ -494,14 +455,10 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 #pragma unroll
       for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + tid) * kScTopK + i]);
     }
-    u64 *dst = scratch + ((size_t)tid * gridDim.x + blockIdx.x) * kScTopK;
+    u64 *dst = scratch + ((size_t)tid * list_stride + blockIdx.x) * kScTopK;
 #pragma unroll
-    for (int i = 0; i < kScTopK; i++) __stcg(dst + i, m.k[i]);
+    for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
   }
-  // (the producer warp has returned: the consumers meet on their named barrier)
-  if (!sc_take_ticket(ticket, tid == 0, &s_last, [] { sc_consumer_sync(); })) return;
-  sc_merge_lists(scratch, gridDim.x, nqc, warp, kTileConsumers / 32, lane, out);
-  if (tid == 0) *ticket = 0;
 }
 
 // ---- exact re-score -------------------------------------------------------------------------------------------
@@ -569,17 +526,49 @@ struct ScXchg {
 // words (32 payload bits | query sequence number; the host spins on them, no D2H copy, no stream synchronise), after
 // the NVLink mailbox exchange above when the database is sharded.
 template <typename T>
-__global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64 *__restrict__ topk, const T *__restrict__ sigs,
+__global__ void __launch_bounds__(32 * kScTopK) sc_rescore_topk_kernel(const u64 *__restrict__ lists, int nlists, int list_stride,
+                                                                       const T *__restrict__ sigs,
                                                                        const int *__restrict__ ids, const T *__restrict__ q_sigs,
                                                                        int n_cells, int sc_width, u64 *__restrict__ exact_keys,
                                                                        u64 *__restrict__ best, u64 *__restrict__ host_words, unsigned seq,
                                                                        const __grid_constant__ ScXchg X, int slot, int q0,
                                                                        unsigned *__restrict__ ticket, unsigned long long timeout_ns) {
   __shared__ u64 sk[kScTopK];
+  __shared__ u64 swl[kScTopK][kScTopK];
   __shared__ double strips[kScTopK][kRescoreChunk];
   __shared__ int s_last;
   const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u64 key = topk[(size_t)q * kScTopK + warp];
+  // merge of the scan's per-CTA lists of this query (every query has its own CTA here, so the merge is as parallel as the
+  // batch is wide; a merge kernel of its own cost 11 us, a merge in the scan's last CTA serialised the queries)
+  {
+    TopK t;
+    t.init();
+    const u64 *src = lists + (size_t)q * list_stride * kScTopK;
+    for (int i = threadIdx.x; i < nlists * kScTopK; i += 32 * kScTopK) t.insert(__ldcg(src + i));
+    u64 o[kScTopK];
+    warp_merge(t, o);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) swl[warp][i] = o[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      TopK m;
+      m.init();
+      if (lane < kScTopK) {
+#pragma unroll
+        for (int i = 0; i < kScTopK; i++) m.insert(swl[lane][i]);
+      }
+      warp_merge(m, o);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kScTopK; i++) sk[i] = o[i];
+      }
+    }
+    __syncthreads();
+  }
+  const u64 key = sk[warp];
+  __syncthreads();  // sk is reused for the exact keys below
   u64 out = kKeyMax;
   if (key != kKeyMax) {
     const int row = (int)(unsigned)(key & 0xffffffffull);
@@ -801,12 +790,9 @@ int num_sms() {
 
 constexpr int kRingGridX = 64;
 
-// per-CTA lists of one query chunk + (last 256 bytes) the tickets of the fused merges; the caller zeroes it once
-size_t sc_scratch_bytes(int nq) {
-  const int lists = num_sms() > kRingGridX ? num_sms() : kRingGridX;
-  return (size_t)(nq > kQChunk ? nq : kQChunk) * lists * kScTopK * sizeof(u64) + 256;
-}
-static size_t sc_ticket_offset_u64(int nq) { return (sc_scratch_bytes(nq) - 256) / sizeof(u64); }
+// per-CTA top-K lists of every query of a batch: lists[q][sc_list_stride()][K]
+int sc_list_stride() { return num_sms() > kRingGridX ? num_sms() : kRingGridX; }
+size_t sc_scratch_bytes(int nq) { return (size_t)(nq > kQChunk ? nq : kQChunk) * sc_list_stride() * kScTopK * sizeof(u64); }
 
 cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
                               unsigned long long *out, unsigned long long *scratch, cudaStream_t stream) {
@@ -849,7 +835,7 @@ void sc_set_scan_flavour(int f) { g_sc_scan_flavour = f; }
 
 static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                                         const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
-                                        unsigned *ticket, unsigned long long *out, int grid, cudaStream_t stream) {
+                                        int list_stride, int grid, cudaStream_t stream) {
   ScEncodeTiledFn enc = sc_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
   {  // per device and cheap: set on every launch (a process may drive several devices)
@@ -876,44 +862,48 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
   const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
   const int groups_per_cta = (n_groups + grid - 1) / grid;
   sc_scan_tile_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(map_db, map_q, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
-                                                                      max_id, sc_width, groups_per_cta, scratch, ticket, out);
+                                                                      max_id, sc_width, groups_per_cta, scratch, list_stride);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
-                           const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *out,
-                           unsigned long long *scratch, cudaStream_t stream) {
+                           const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch, int *nlists_out,
+                           cudaStream_t stream) {
   if (n_cells % 4 != 0 || n_cells > 1280 || key_dim > 64) return cudaErrorInvalidValue;
   {  // worst case of any descriptor shape this library accepts; per device and cheap, so set on every launch
     cudaError_t e = cudaFuncSetAttribute(sc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQChunk * 1280 * 4 + kQChunk * 64 * 4);
     if (e != cudaSuccess) return e;
   }
-  unsigned *ticket = reinterpret_cast<unsigned *>(scratch + sc_ticket_offset_u64(nq));
+  const int stride = sc_list_stride();
   const int n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  // one grid size for all chunks of the batch (the re-score kernel merges `grid` lists per query)
+  const int flavour = sc_scan_flavour();
+  const int nq_first = nq < kQChunk ? nq : kQChunk;
+  // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
+  // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
+  // (a shard smaller than one 64-row TMA box always takes the streaming kernel)
+  const bool tiles = n_rows >= 64 && (flavour == 2 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
+  int grid = num_sms();
+  if (tiles) {
+    const int n_groups = (n_rows + 63) / 64;
+    if (grid > n_groups) grid = n_groups;
+    const int gpc = (n_groups + grid - 1) / grid;
+    grid = (n_groups + gpc - 1) / gpc;  // no CTA without a group
+  }
+  if (nlists_out) *nlists_out = grid;
   for (int q0 = 0; q0 < nq; q0 += kQChunk) {
     const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
-    // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
-    // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
-    const int flavour = sc_scan_flavour();
-    // (a shard smaller than one 64-row TMA box always takes the streaming kernel)
-    const bool tiles = n_rows >= 64 && (flavour == 2 || (flavour == 0 && nqc > 8 && n_tiles * 2 >= num_sms()));
-    int grid = num_sms();
+    unsigned long long *lists = scratch + (size_t)q0 * stride * kScTopK;
     if (tiles) {
-      const int n_groups = (n_rows + 63) / 64;
-      if (grid > n_groups) grid = n_groups;
-      // every CTA of the grid must own at least one group (the ticket counts gridDim.x arrivals either way)
-      const int gpc = (n_groups + grid - 1) / grid;
-      grid = (n_groups + gpc - 1) / gpc;
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
-                                           ringkey_thres, max_id, sc_width, scratch, ticket, out + (size_t)q0 * kScTopK, grid, stream);
+                                           ringkey_thres, max_id, sc_width, lists, stride, grid, stream);
       if (e != cudaSuccess) return e;
     } else {
       size_t smem = (size_t)nqc * n_cells * 4 + (size_t)nqc * key_dim * 4;
       const size_t lists_bytes = (size_t)kScanWarps * kQChunk * kScTopK * sizeof(u64);
       if (smem < lists_bytes) smem = lists_bytes;
       sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
-                                                           q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, scratch, ticket,
-                                                           out + (size_t)q0 * kScTopK);
+                                                           q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, lists, stride);
     }
   }
   return cudaGetLastError();
@@ -940,7 +930,8 @@ cudaError_t launch_sc_bin_finalize(const double *pts, int n, const double mean[3
   return cudaGetLastError();
 }
 
-cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq, int n_cells,
+cudaError_t launch_sc_rescore_topk(const unsigned long long *lists, int nlists, const void *sigs, int fp64, const int *ids, const void *q_sigs, int nq,
+                                   int n_cells,
                                    int sc_width, unsigned long long *exact_keys, unsigned long long *best, unsigned long long *host_words,
                                    unsigned seq, const ScExchange *xchg, unsigned xchg_seq, int q0, unsigned *ticket, cudaStream_t stream) {
   if (nq < 1) return cudaSuccess;
@@ -959,10 +950,10 @@ cudaError_t launch_sc_rescore_topk(const unsigned long long *topk, const void *s
   }
   const unsigned long long timeout_ns = 2000000000ull;
   if (fp64)
-    sc_rescore_topk_kernel<double><<<nq, 32 * kScTopK, 0, stream>>>(topk, (const double *)sigs, ids, (const double *)q_sigs, n_cells, sc_width,
+    sc_rescore_topk_kernel<double><<<nq, 32 * kScTopK, 0, stream>>>(lists, nlists, sc_list_stride(), (const double *)sigs, ids, (const double *)q_sigs, n_cells, sc_width,
                                                                     exact_keys, best, host_words, seq, X, slot, q0, ticket, timeout_ns);
   else
-    sc_rescore_topk_kernel<float><<<nq, 32 * kScTopK, 0, stream>>>(topk, (const float *)sigs, ids, (const float *)q_sigs, n_cells, sc_width, exact_keys,
+    sc_rescore_topk_kernel<float><<<nq, 32 * kScTopK, 0, stream>>>(lists, nlists, sc_list_stride(), (const float *)sigs, ids, (const float *)q_sigs, n_cells, sc_width, exact_keys,
                                                                    best, host_words, seq, X, slot, q0, ticket, timeout_ns);
   return cudaGetLastError();
 }

@@ -15,10 +15,21 @@
 //   FrameHessian : `Eigen::Vector3f* dIp[PYR_LEVELS]`, `float* absSquaredGrad[PYR_LEVELS]`, `float ab_exposure`,
 //                  `AffLight aff_g2l()`, `shell->id`
 //   CalibHessian : `fxl() fyl() cxl() cyl()`, `float* B` (256-entry inverse response, HessianBlocks.h:329-330)
+//
+// Threading contract.  A dslam_session (and everything created from it) is used by ONE host thread at a time.  The reference
+// runs two threads that touch this path: the tracking thread (FrontEnd: makeImages, trackNewCoarse, optimizeScale,
+// setCoarseTrackingRef) and the LoopHandler thread (ScanContext::generate, search_ringkey, search_sc, PoseEstimator::estimate).
+// Give each thread its OWN Session and its own FramePyramids; objects of different sessions share nothing.  The loop thread's
+// PoseEstimator never keeps device twins of frames: estimate() rebuilds the pyramid of `cur_frame->fh` from its host mirror
+// (fh->dIp[0], which that thread owns) and releases the twin before it returns, so a FrameHessian address that is reused after
+// `delete cur_frame->fh` can never hit a stale device pyramid.  On the tracking thread call FramePyramids::release(fh) from
+// FrameHessian::~FrameHessian (or wherever the front end deletes a frame) — that is the only hook needed there.
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "dslam_b200.h"
@@ -81,6 +92,23 @@ class FramePyramids {
     check(dslam_frame_build_batch(1, &f, B, 1 | 2 | 4), "dslam_frame_build_batch");
     check(dslam_frame_download(f, dIp, ag), "dslam_frame_download");
   }
+  // `fh->makeImages(color, HCalib)` with the reference's own allocation behaviour (HessianBlocks.cpp:131-136): dIp[l] and
+  // absSquaredGrad[l] are new[]-ed here, dI = dIp[0], and FrameHessian::~FrameHessian delete[]s them as it always did.  The
+  // mirrors are complete when this returns (pageable memory: the copy is staged by the driver; allocate the arrays with
+  // dslam_host_alloc and use the overload above to get true DMA + overlap).
+  template <class CalibHessian>
+  void makeImages(FrameHessian *fh, const float *color, CalibHessian *HCalib) {
+    typedef typename std::remove_pointer<typename std::decay<decltype(fh->dIp[0])>::type>::type Texel;  // Eigen::Vector3f
+    static_assert(sizeof(Texel) == 3 * sizeof(float), "dIp texels must be 3 packed floats");
+    for (int l = 0; l < levels_; l++) {
+      const size_t n = (size_t)(w_ >> l) * (h_ >> l);
+      fh->dIp[l] = new Texel[n];
+      fh->absSquaredGrad[l] = new float[n];
+    }
+    fh->dI = fh->dIp[0];
+    makeImages(fh, color, HCalib, HCalib != nullptr);  // gamma weights whenever a calibration is passed (setting_gammaWeightsPixelSelect == 1)
+    wait_host(fh);
+  }
   void wait_host(FrameHessian *fh) { check(dslam_frame_wait_host(at(fh)), "dslam_frame_wait_host"); }
   // call from FrameHessian::~FrameHessian / FrameHessian::release
   void release(FrameHessian *fh) {
@@ -94,16 +122,15 @@ class FramePyramids {
     if (it == live_.end()) throw std::runtime_error("FrameHessian has no device pyramid (makeImages not called)");
     return it->second;
   }
-  // Device pyramid of a frame whose twin may already have been released (a keyframe the LoopHandler thread kept after the
-  // front end marginalised it): rebuilt from the intensity channel of the host mirror fh->dIp[0] when it is gone.
-  dslam_frame *ensure(FrameHessian *fh) {
-    auto it = live_.find(fh);
-    if (it != live_.end()) return it->second;
+  // Device pyramid of a frame this object has no (trustworthy) twin of — a keyframe the LoopHandler thread kept after the front
+  // end released it, seen from the loop thread's own FramePyramids: ALWAYS rebuilt from the intensity channel of the host
+  // mirror fh->dIp[0] (never a cached twin: the address of a deleted FrameHessian may have been reused).  Pair with release().
+  dslam_frame *rebuild(FrameHessian *fh) {
     dslam_frame *f = acquire(fh);
-    std::vector<float> color((size_t)w_ * h_);
+    color_.resize((size_t)w_ * h_);
     const float *src = reinterpret_cast<const float *>(fh->dIp[0]);
-    for (size_t i = 0; i < color.size(); i++) color[i] = src[3 * i];
-    check(dslam_frame_make_images(f, color.data(), nullptr, nullptr, nullptr), "dslam_frame_make_images");
+    for (size_t i = 0; i < color_.size(); i++) color_[i] = src[3 * i];
+    check(dslam_frame_make_images(f, color_.data(), nullptr, nullptr, nullptr), "dslam_frame_make_images");
     return f;
   }
 
@@ -125,6 +152,7 @@ class FramePyramids {
   int w_, h_, levels_;
   std::unordered_map<FrameHessian *, dslam_frame *> live_;
   std::vector<dslam_frame *> free_;
+  std::vector<float> color_;
 };
 
 // Flat export of the active points that makeCoarseDepthL0 iterates over (TrackerAndScaler.cpp:149-166): the maintainer
@@ -215,6 +243,36 @@ class TrackerAndScaler {
     }
   }
 
+  // The whole hypothesis loop of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:192-247) in one call: `tries` in the reference's
+  // order, `aff_last_2_l` the start affine of every try, `last_coarse_rmse` / `reTrackThreshold` of the break test (:244-246).
+  // Outputs exactly what the sequential loop leaves behind: lastF_2_fh, aff_g2l, achievedRes, flowVecs (via lastFlowIndicators
+  // semantics: returned in flowVecs), haveOneGood; returns tryIterations.  The hypotheses are evaluated speculatively in
+  // lock-step batches (1, then 4, then the rest) and the acceptance rule is replayed in order (dslam_track_new_coarse).
+  template <class SE3Vector>
+  int trackNewCoarse(FrameHessian *fh, const SE3Vector &tries, const AffLight &aff_last_2_l, int coarsestLvl, const Vec5 &last_coarse_rmse,
+                     double reTrackThreshold, SE3 &lastF_2_fh, AffLight &aff_g2l, Vec5 &achievedRes, Vec3 &flowVecs, bool &haveOneGood) {
+    const int n = (int)tries.size();
+    std::vector<double> p(7 * (size_t)n);
+    for (int k = 0; k < n; k++) {
+      SE3 t = tries[k];
+      for (int i = 0; i < 7; i++) p[7 * (size_t)k + i] = t.data()[i];
+    }
+    const double aff0[2] = {aff_last_2_l.a, aff_last_2_l.b};
+    double last[5], pose[7], aff[2], ach[5], flow[3];
+    for (int i = 0; i < 5; i++) last[i] = last_coarse_rmse[i];
+    int good = 0, ntry = 0;
+    check(dslam_track_new_coarse(c_, frames_.at(fh), fh->ab_exposure, n, p.data(), aff0, coarsestLvl, last, reTrackThreshold, pose, aff, ach, flow, &good,
+                                 &ntry),
+          "dslam_track_new_coarse");
+    for (int i = 0; i < 7; i++) lastF_2_fh.data()[i] = pose[i];
+    aff_g2l.a = aff[0];
+    aff_g2l.b = aff[1];
+    for (int i = 0; i < 5; i++) achievedRes[i] = ach[i];
+    for (int i = 0; i < 3; i++) flowVecs[i] = flow[i];
+    haveOneGood = good != 0;
+    return ntry;
+  }
+
   // float optimizeScale(FrameHessian* fh1, float& scale, int coarsestLvl)  (:854-964)
   float optimizeScale(FrameHessian *fh1, float &scale, int coarsestLvl) {
     float rmse = 0;
@@ -248,6 +306,7 @@ class TrackerAndScaler {
 template <class FrameHessian>
 class PoseEstimator {
  public:
+  // `s` and `frames` are the LOOP THREAD's own Session / FramePyramids (not the tracking thread's)
   PoseEstimator(Session &s, FramePyramids<FrameHessian> &frames, int w, int h, int levels) : frames_(frames), levels_(levels) {
     check(dslam_pe_create(s.get(), w, h, levels, &p_), "dslam_pe_create");
   }
@@ -270,8 +329,10 @@ class PoseEstimator {
     for (int r = 0; r < 4; r++)
       for (int c = 0; c < 4; c++) T[r * 4 + c] = ref_to_new(r, c);
     int ok = 0;
-    check(dslam_pe_estimate(p_, frames_.ensure(new_fh), new_fh->ab_exposure, new_cam.data(), coarsest_lvl, T, &pose_error, &inlier_percent, &ok),
-          "dslam_pe_estimate");
+    dslam_frame *twin = frames_.rebuild(new_fh);  // from the host mirror; see the threading contract at the top of this header
+    const int rc = dslam_pe_estimate(p_, twin, new_fh->ab_exposure, new_cam.data(), coarsest_lvl, T, &pose_error, &inlier_percent, &ok);
+    frames_.release(new_fh);
+    check(rc, "dslam_pe_estimate");
     for (int r = 0; r < 4; r++)
       for (int c = 0; c < 4; c++) ref_to_new(r, c) = T[r * 4 + c];
     return ok != 0;
@@ -292,8 +353,10 @@ class LoopDatabase {
   static constexpr int kLoopMargin = 100;   // LOOP_MARGIN  search_place.h:22
   static constexpr int kFlannNN = 3;        // FLANN_NN     :21
   static constexpr float kRingkeyThres() { return 0.1f; }  // RINGKEY_THRES :23
-  LoopDatabase(Session &s, int capacity, int n_sectors = 60, int n_rings = 20) : n_rings_(n_rings), n_cells_(n_sectors * n_rings) {
-    check(dslam_sc_create(s.get(), n_sectors, n_rings, capacity, &db_), "dslam_sc_create");
+  // capacity = initial allocation (the tables grow like the reference's index does); fp64 keeps the double signature values
+  LoopDatabase(Session &s, int capacity, int n_sectors = 60, int n_rings = 20, bool fp64 = false)
+      : n_rings_(n_rings), n_cells_(n_sectors * n_rings), fp64_(fp64) {
+    check(dslam_sc_create_ex(s.get(), n_sectors, n_rings, capacity, fp64 ? DSLAM_SC_FP64 : 0, &db_), "dslam_sc_create_ex");
   }
   ~LoopDatabase() { dslam_sc_destroy(db_); }
   // One LoopHandler::run iteration (src/loop_closure/LoopHandler.cpp:236-264): the new keyframe's descriptor is appended
@@ -323,11 +386,86 @@ class LoopDatabase {
     check(dslam_sc_search_sc(db_, 1, dense.data(), cand, kFlannNN, &res_idx, &res_diff), "dslam_sc_search_sc");
     return res_idx;
   }
+  // ---- the three calls of LoopHandler::run one by one (src/loop_closure/LoopHandler.cpp:239-259) ---------------------------
+  // ScanContext::generate (ScanContext.cpp:78-142) on the device; the descriptor is appended to the database under
+  // id = number of descriptors so far (device to device) and returned in the reference's forms: ringkey[n_rings] floats, sparse
+  // signature (SigType), tfm_pca_rig.  Vector3d: operator()(i); Matrix4d: operator()(r, c).
+  template <class Vector3d, class SigType, class Matrix4d>
+  void generate(const std::vector<Vector3d> &pts_spherical, float *ringkey, SigType &signature, double lidar_range, Matrix4d &tfm_pca_rig) {
+    xyz_.resize(3 * pts_spherical.size());
+    for (size_t i = 0; i < pts_spherical.size(); i++)
+      for (int k = 0; k < 3; k++) xyz_[3 * i + k] = pts_spherical[i](k);
+    sig64_.resize((size_t)n_cells_);
+    double T[16];
+    check(dslam_sc_generate(db_, xyz_.data(), (int)pts_spherical.size(), lidar_range, ringkey, nullptr, sig64_.data(), T, 1, count_), "dslam_sc_generate");
+    count_++;
+    signature.clear();
+    for (int i = 0; i < n_cells_; i++)
+      if (sig64_[(size_t)i] != 0.0) signature.push_back({i, sig64_[(size_t)i]});
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) tfm_pca_rig(r, c) = T[r * 4 + c];
+  }
+  // search_ringkey (search_place.h:25-57) for the descriptor appended LAST (by generate / addAndSearch): exact 3-NN among the
+  // ids older than LOOP_MARGIN keyframes (the reference's delay queue), kept when dist < RINGKEY_THRES.  Differences from the
+  // FLANN call it replaces: exact instead of a randomised kd-tree with 128 checks, and the three neighbours are always real rows
+  // (FLANN's three may include the uninitialised dummy row 0 the reference's index starts with, which it then discards).
+  void search_ringkey(const float *ringkey, std::vector<int> &candidates) {
+    const int max_id = (count_ - 1) - kLoopMargin;
+    if (max_id < kFlannNN) return;  // "ringkeys->size() > FLANN_NN" with the dummy row (:28)
+    int cand[kFlannNN];
+    float dist[kFlannNN];
+    check(dslam_sc_search_ringkey(db_, 1, ringkey, kFlannNN, kRingkeyThres(), max_id, cand, dist), "dslam_sc_search_ringkey");
+    for (int i = 0; i < kFlannNN; i++)
+      if (cand[i] >= 0) candidates.emplace_back(cand[i]);
+  }
+  // search_sc (search_place.h:59-85): the candidates' signatures are the database rows (the reference reads
+  // loop_frames[candidate]->signature); float += double * double in cell order, strict '>' running minimum from 1.1.
+  // On a database created with fp64 = true the doubles of `signature` are used unrounded.
+  template <class SigType>
+  void search_sc(const SigType &signature, const std::vector<int> &candidates, int /*sc_width*/, int &res_idx, float &res_diff) {
+    if (fp64_) {
+      sig64_.assign((size_t)n_cells_, 0.0);
+      for (size_t i = 0; i < signature.size(); i++) sig64_[(size_t)signature[i].first] = signature[i].second;
+      check(dslam_sc_search_sc64(db_, 1, sig64_.data(), candidates.data(), (int)candidates.size(), &res_idx, &res_diff), "dslam_sc_search_sc64");
+    } else {
+      dense_.assign((size_t)n_cells_, 0.f);
+      for (size_t i = 0; i < signature.size(); i++) dense_[(size_t)signature[i].first] = (float)signature[i].second;
+      check(dslam_sc_search_sc(db_, 1, dense_.data(), candidates.data(), (int)candidates.size(), &res_idx, &res_diff), "dslam_sc_search_sc");
+    }
+  }
+  // exhaustive alternative to the two-stage search: sector-cosine scan of every row older than LOOP_MARGIN keyframes
+  // (dslam_sc_query; sharded over the GPUs of the box when a communicator is attached)
+  template <class SigType>
+  int query(const SigType &signature, float &res_diff) {
+    dense_.assign((size_t)n_cells_, 0.f);
+    for (size_t i = 0; i < signature.size(); i++) dense_[(size_t)signature[i].first] = (float)signature[i].second;
+    int res_idx = -1;
+    check(dslam_sc_query(db_, 1, nullptr, dense_.data(), -1.0f, (count_ - 1) - kLoopMargin, &res_idx, &res_diff), "dslam_sc_query");
+    return res_idx;
+  }
+  int size() const { return count_; }
   dslam_scdb *handle() const { return db_; }
 
  private:
   dslam_scdb *db_ = nullptr;
   int n_rings_, n_cells_, count_ = 0;
+  bool fp64_ = false;
+  std::vector<double> xyz_, sig64_;
+  std::vector<float> dense_;
 };
+
+// The reference's free functions by their own names and argument order (search_place.h:25-27, 59-63), with the FLANN index /
+// the loop-frame vector replaced by the LoopDatabase that holds the descriptors:
+//   search_ringkey(ringkey, ringkeys_, candidates)                      ->  search_ringkey(ringkey, &loop_db, candidates)
+//   search_sc(signature, loop_frames_, candidates, width, idx, diff)    ->  search_sc(signature, loop_db, candidates, width, idx, diff)
+// FlannMatrix: `operator[](row)` -> float* (flann::Matrix<float>).
+template <class FlannMatrix>
+inline void search_ringkey(const FlannMatrix &ringkey, LoopDatabase *ringkeys, std::vector<int> &candidates) {
+  ringkeys->search_ringkey(ringkey[0], candidates);
+}
+template <class SigType>
+inline void search_sc(SigType &signature, LoopDatabase &loop_frames, const std::vector<int> &candidates, int sc_width, int &res_idx, float &res_diff) {
+  loop_frames.search_sc(signature, candidates, sc_width, res_idx, res_diff);
+}
 
 }  // namespace dslam_b200

@@ -629,6 +629,32 @@ def reference_make_images(img, levels, B256=None, path=None):
     return dIp, ag
 
 
+class ReferenceScanContext:
+    """oracle/_ref/libdslam_ref_sc.so: the reference's own ScanContext.cpp (align_points_PCA + ScanContext::generate) compiled
+    in place against oracle/shim_sc (its SelfAdjointEigenSolver is oracle/jacobi_eig3.h, the solver the oracle uses too)."""
+
+    PATH = os.path.join(_HERE, "_ref", "libdslam_ref_sc.so")
+
+    @staticmethod
+    def available():
+        return os.path.exists(ReferenceScanContext.PATH)
+
+    def __init__(self):
+        self.L = C.CDLL(self.PATH)
+        self.L.refsc_generate.restype = C.c_int
+        self.L.refsc_generate.argtypes = [c_d, C.c_int, C.c_double, C.c_int, C.c_int, c_f, c_i, c_d, c_d]
+
+    def generate(self, pts, lidar_range=40.0, num_s=60, num_r=20):
+        """-> (ringkey [num_r] float32, sig_idx int32 ascending, sig_val float64, tfm_pca_rig 4x4)"""
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        rk = np.empty(num_r, np.float32)
+        idx = np.empty(num_s * num_r, np.int32)
+        val = np.empty(num_s * num_r, np.float64)
+        tfm = np.empty(16, np.float64)
+        n = self.L.refsc_generate(_dp(pts), len(pts), lidar_range, num_s, num_r, _fp(rk), _ip(idx), _dp(val), _dp(tfm))
+        return rk, idx[:n].copy(), val[:n].copy(), tfm.reshape(4, 4)
+
+
 class OraclePoseEstimator:
     """dso::PoseEstimator restated (src/loop_closure/pose_estimation/PoseEstimator.cpp)."""
 

@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """Compile the pieces of the REFERENCE that build from their own few source files, in place, into oracle/_ref/.
 
-What builds here (g++ only; the reference's cmake / catkin build is not run and cannot be — no Eigen, Boost, OpenCV,
-FLANN, PCL, ROS in this image):
-  * deps:dso/src/OptimizationBackend/MatrixAccumulators.h  (Accumulator9; lives inside /root/reference/dependencies.zip and is
-    extracted to a temporary directory outside the repository for the duration of the compile)
-  * src/scale_optimization/ScaleAccumulator.h
-  * src/loop_closure/loop_detection/search_place.h
-against the shims in oracle/shim (Eigen/Core, util/NumType.h) and oracle/ref_driver.cpp.  Output: oracle/_ref/libdslam_ref.so
-(git-ignored; travels to the GPU box with the snapshot).  No reference source is copied into the repository.
-The warp / residual / LM code (TrackerAndScaler.cpp) needs real Eigen + Sophus + DSO and is NOT buildable: those
-functions stay "parity unpinned" (see oracle/dslam_oracle.cpp header).
+What builds here (plain g++; the reference's cmake / catkin build is not run and cannot be — no Eigen, Boost, OpenCV, FLANN,
+PCL, ROS in this image), every piece against stand-ins for the absent third-party headers (oracle/shim, oracle/shim_sc):
+  * libdslam_ref.so            deps:dso/src/OptimizationBackend/MatrixAccumulators.h (Accumulator9), src/scale_optimization/
+                               ScaleAccumulator.h, src/loop_closure/loop_detection/search_place.h            (ref_driver.cpp)
+  * libdslam_ref_tracker.so    src/scale_optimization/TrackerAndScaler.cpp :1-336 and :451-1172 (constructor, makeK,
+    libdslam_ref_tracker_opt   makeCoarseDepthL0, trackNewestCoarse, calcResPose, calcGSSSEPose, optimizeScale, calcResScale,
+                               calcGSSSEScale) + FrameHessian::makeImages (deps:dso HessianBlocks.cpp:128-191); the _opt build
+                               (-O3 -march=x86-64-v3) is the timed CPU baseline of bench.py               (ref_driver_tracker.cpp)
+  * libdslam_ref_pe.so         src/loop_closure/pose_estimation/PoseEstimator.cpp, whole file                (ref_driver_pe.cpp)
+  * libdslam_ref_sc.so         src/loop_closure/loop_detection/ScanContext.cpp, whole file                   (ref_driver_sc.cpp)
+Files that live inside /root/reference/dependencies.zip are extracted to a temporary directory outside the repository for the
+duration of the compile.  Outputs go to oracle/_ref/ only (git-ignored; they travel to the GPU box with the snapshot).  No
+reference source is copied into the repository.
 """
 import os
 import subprocess
@@ -68,6 +71,23 @@ def main():
                os.path.join(HERE, "ref_driver_pe.cpp"), "-o", os.path.join(OUT, "libdslam_ref_pe.so")]
         subprocess.run(cmd, check=True)
         print("built", os.path.join(OUT, "libdslam_ref_pe.so"))
+        # ---- the C++ adapter instantiated with the reference's types, next to the reference's own tracker (adapter_vs_reference) ----
+        repo = os.path.dirname(HERE)
+        libdir = os.path.join(repo, "direct_stereo_slam_b200")
+        if os.path.exists(os.path.join(libdir, "libdslam_b200.so")):
+            cmd = ["g++", "-O2", "-std=c++14", "-msse2", "-ffp-contract=off", "-w",
+                   "-I", os.path.join(HERE, "shim"), "-I", tmp, "-I", os.path.join(tmp, "dso", "src"),
+                   "-I", os.path.join(REF, "src"), "-I", os.path.join(REF, "src", "scale_optimization"), "-I", os.path.join(repo, "include"),
+                   os.path.join(HERE, "adapter_vs_reference.cpp"), "-L", libdir, "-ldslam_b200",
+                   "-Wl,-rpath,$ORIGIN/../../direct_stereo_slam_b200", "-o", os.path.join(OUT, "adapter_vs_reference")]
+            subprocess.run(cmd, check=True)
+            print("built", os.path.join(OUT, "adapter_vs_reference"))
+        # ---- ScanContext.cpp as a whole (descriptor generation) against oracle/shim_sc ----------------------
+        cmd = ["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-w",
+               "-I", os.path.join(HERE, "shim_sc"), "-I", os.path.join(REF, "src"),
+               os.path.join(HERE, "ref_driver_sc.cpp"), "-o", os.path.join(OUT, "libdslam_ref_sc.so")]
+        subprocess.run(cmd, check=True)
+        print("built", os.path.join(OUT, "libdslam_ref_sc.so"))
     return 0
 
 

@@ -3,59 +3,23 @@
 // TEST INFRASTRUCTURE ONLY (same rules as dslam_oracle.cpp).
 //
 // Follows src/loop_closure/loop_detection/ScanContext.cpp:19-66 (align_points_PCA) and :78-142 (generate).
-// PARITY STATUS: parity unpinned.  The reference uses Eigen::SelfAdjointEigenSolver<MatrixXd> (:42-46), whose
-// eigenvector SIGNS are an artefact of its tridiagonal-QR iteration; Eigen is absent from this image.  Here the
-// 3x3 symmetric eigenproblem is solved by cyclic Jacobi, eigenvalues ascending (as Eigen orders them), and each
-// eigenvector is sign-normalised so that its largest-magnitude component is positive.  Everything after the
-// eigenvectors (polar binning, max-height, ring key, per-sector L2 normalisation) is restated op for op.
+// PARITY STATUS: pinned bit for bit against the reference's own ScanContext.cpp compiled in place (oracle/ref_build.py ->
+// oracle/_ref/libdslam_ref_sc.so, tests/test_oracle_ref_sc.py) GIVEN THE SAME 3x3 EIGEN-SOLVER: the reference calls
+// Eigen::SelfAdjointEigenSolver<MatrixXd> (:42-46), Eigen is absent from this image, so both sides use oracle/jacobi_eig3.h
+// (cyclic Jacobi, eigenvalues ascending as Eigen orders them, eigenvector sign fixed so that the largest-magnitude component
+// is positive).  What stays unpinned is exactly that stand-in: Eigen's tridiagonal-QR returns the same vectors up to sign and
+// ~1e-16, and its blocked GEMM sums `pts_mat^T * pts_mat` in another order.  Everything after the eigenvectors (rotation,
+// polar binning, max-height, ring key, per-sector L2 normalisation) is the reference's own source text on both sides.
 
 #include <cmath>
 #include <cstring>
 #include <vector>
 #include <algorithm>
 
+#include "jacobi_eig3.h"
+
 namespace {
-
-void jacobi_eig3(const double Ain[9], double evals[3], double evecs[9] /* columns = eigenvectors, row-major 3x3 */) {
-  double A[9]; std::memcpy(A, Ain, sizeof(A));
-  double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  for (int sweep = 0; sweep < 64; sweep++) {
-    const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
-    if (off < 1e-300) break;
-    for (int p = 0; p < 2; p++)
-      for (int q = p + 1; q < 3; q++) {
-        const double apq = A[p * 3 + q];
-        if (std::fabs(apq) < 1e-300) continue;
-        const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; k++) {  // A <- A * J
-          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
-          A[k * 3 + p] = c * akp - s * akq; A[k * 3 + q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 3; k++) {  // A <- J^T * A
-          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
-          A[p * 3 + k] = c * apk - s * aqk; A[q * 3 + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 3; k++) {
-          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
-          V[k * 3 + p] = c * vkp - s * vkq; V[k * 3 + q] = s * vkp + c * vkq;
-        }
-      }
-  }
-  int order[3] = {0, 1, 2};
-  std::sort(order, order + 3, [&](int a, int b) { return A[a * 3 + a] < A[b * 3 + b]; });
-  for (int j = 0; j < 3; j++) {
-    const int src = order[j];
-    evals[j] = A[src * 3 + src];
-    double v[3] = {V[0 * 3 + src], V[1 * 3 + src], V[2 * 3 + src]};
-    const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    int big = 0; for (int k = 1; k < 3; k++) if (std::fabs(v[k]) > std::fabs(v[big])) big = k;
-    const double sgn = (v[big] < 0 ? -1.0 : 1.0) / nrm;
-    for (int k = 0; k < 3; k++) evecs[k * 3 + j] = v[k] * sgn;
-  }
-}
-
+inline void jacobi_eig3(const double A[9], double evals[3], double evecs[9]) { dslam_jacobi_eig3(A, evals, evecs); }
 }  // namespace
 
 extern "C" {
@@ -80,7 +44,10 @@ int orc_sc_generate(const double *pts, int n, double lidar_range, int num_s, int
     for (int j = 0; j < 3; j++) al[3 * i + j] = pm[3 * i] * ev[0 * 3 + j] + pm[3 * i + 1] * ev[1 * 3 + j] + pm[3 * i + 2] * ev[2 * 3 + j];
   for (int i = 0; i < 16; i++) tfm_pca_rig[i] = (i % 5 == 0) ? 1.0 : 0.0;
   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) tfm_pca_rig[r * 4 + c] = ev[c * 3 + r];  // rows = v_r^T
-  for (int r = 0; r < 3; r++) tfm_pca_rig[r * 4 + 3] = -(tfm_pca_rig[r * 4] * mx + tfm_pca_rig[r * 4 + 1] * my + tfm_pca_rig[r * 4 + 2] * mz);
+  // t = -R * mean  (:62-64): a fixed-size 3x3 * 3x1 product is coefficient based in Eigen 3.3 and its 3-term sum is reduced as
+  // e0 + (e1 + e2) (Redux.h redux_novec_unroller); the negation lives inside every coefficient
+  for (int r = 0; r < 3; r++)
+    tfm_pca_rig[r * 4 + 3] = (-tfm_pca_rig[r * 4]) * mx + ((-tfm_pca_rig[r * 4 + 1]) * my + (-tfm_pca_rig[r * 4 + 2]) * mz);
 
   // generate :78-142
   for (int i = 0; i < num_r; i++) ringkey[i] = 0.0;

@@ -16,13 +16,19 @@ struct SE3 {  // Sophus::SE3d::data(): quaternion (x,y,z,w) + translation
 };
 struct Vec5 { double v[5]; double &operator[](int i) { return v[i]; } const double &operator[](int i) const { return v[i]; } };
 struct Vec3 { double v[3]; double &operator[](int i) { return v[i]; } };
-struct Vec3d { double v[3]; double operator[](int i) const { return v[i]; } };
+struct Vec3d { double v[3]; double operator[](int i) const { return v[i]; } double operator()(int i) const { return v[i]; } };
+struct FlannMatrix {  // flann::Matrix<float>
+  float *data; size_t rows, cols;
+  float *operator[](size_t r) const { return data + r * cols; }
+};
+typedef std::vector<std::pair<int, double>> SigType;
 struct Mat44 {  // Eigen::Matrix4d (column-major storage, (row, col) access)
   double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   double &operator()(int r, int c) { return m[c * 4 + r]; }
 };
 struct FrameShell { int id = 0; };
 struct FrameHessian {
+  Vector3f *dI = nullptr;
   Vector3f *dIp[6] = {nullptr};
   float *absSquaredGrad[6] = {nullptr};
   float ab_exposure = 1.f;
@@ -110,6 +116,62 @@ int main() {
   // a 2 px shift of a plane at 10 m with f = 200 is a translation of -0.1 m (the scene moved +x, so the camera moved -x)
   std::printf("adapter_mock: ok=%d tx=%.4f (expect about -0.1) rmse0=%.3f scale=%.3f (expect about 1) scale_rmse=%.3f pc_n0=%d\n", (int)ok,
               pose.data()[4], last[0], scale, rmse, tracker.pc_n()[0]);
-  const bool pass = ok && std::fabs(pose.data()[4] + 0.1) < 0.01 && std::fabs(scale - 1.f) < 0.05f && std::fabs(ref_to_new(0, 3) + 0.1) < 0.01;
+  bool pass = ok && std::fabs(pose.data()[4] + 0.1) < 0.01 && std::fabs(scale - 1.f) < 0.05f && std::fabs(ref_to_new(0, 3) + 0.1) < 0.01;
+
+  // makeImages with the reference's allocation behaviour (new[] inside, dI = dIp[0]) + the hypothesis loop in one call
+  {
+    mock::FrameHessian fa;
+    mock::FrameShell sa;
+    fa.shell = &sa;
+    render(2.f, img);
+    frames.makeImages(&fa, img.data(), &calib);
+    pass = pass && fa.dI == fa.dIp[0] && fa.dIp[0][5 * w + 7].v[0] == img[5 * w + 7];
+    std::vector<mock::SE3> tries(3);
+    tries[0].d[4] = 0.5;  // a bad start, then the identity twice
+    mock::SE3 best;
+    mock::AffLight aff0, aff_best;
+    mock::Vec5 last_rmse, achieved;
+    for (int i = 0; i < 5; i++) last_rmse[i] = 100.0;
+    mock::Vec3 flowv;
+    bool have = false;
+    const int ntried = tracker.trackNewCoarse(&fa, tries, aff0, levels - 1, last_rmse, 1.5, best, aff_best, achieved, flowv, have);
+    std::printf("adapter_mock: trackNewCoarse tried %d of 3, haveOneGood=%d tx=%.4f\n", ntried, (int)have, best.data()[4]);
+    pass = pass && have && ntried >= 1 && std::fabs(best.data()[4] + 0.1) < 0.02;
+    frames.release(&fa);
+    for (int l = 0; l < levels; l++) { delete[] fa.dIp[l]; delete[] fa.absSquaredGrad[l]; }
+  }
+  // the loop-closure calls one by one, by the reference's names and argument order (LoopHandler.cpp:239-259)
+  {
+    dslam_b200::Session loop_session(0);  // the LoopHandler thread owns its session
+    dslam_b200::LoopDatabase db(loop_session, 8, 60, 20, true);  // grows; keeps the double signature values
+    unsigned rs = 12345u;
+    auto rnd = [&]() { rs = rs * 1664525u + 1013904223u; return (double)(rs >> 8) / 16777216.0 - 0.5; };
+    std::vector<std::vector<mock::Vec3d>> clouds(130);
+    int found = -2;
+    float diff = 9.f;
+    for (int k = 0; k < 130; k++) {
+      for (int i = 0; i < 1500; i++) clouds[k].push_back(mock::Vec3d{{60.0 * rnd() * (1 + 0.3 * (k % 7)), 40.0 * rnd(), 6.0 * rnd() * (1 + 0.2 * (k % 5))}});
+      if (k == 129) clouds[k] = clouds[10];  // a revisit of keyframe 10, 119 keyframes later (> LOOP_MARGIN)
+      float ringkey[20];
+      mock::SigType signature;
+      mock::Mat44 tfm;
+      db.generate(clouds[k], ringkey, signature, 40.0, tfm);
+      mock::FlannMatrix rk{ringkey, 1, 20};
+      std::vector<int> candidates;
+      dslam_b200::search_ringkey(rk, &db, candidates);
+      if (k == 129 && !candidates.empty()) {
+        int idx = -1;
+        dslam_b200::search_sc(signature, db, candidates, 60, idx, diff);
+        found = idx;
+        float qdiff = 9.f;
+        const int qidx = db.query(signature, qdiff);
+        pass = pass && qidx == 10;
+      } else if (k < 103) {
+        pass = pass && candidates.empty();  // nothing is old enough yet
+      }
+    }
+    std::printf("adapter_mock: loop search found keyframe %d (expect 10) diff %.5f, database rows %d\n", found, diff, db.size());
+    pass = pass && found == 10 && diff < 1e-5f && db.size() == 130;
+  }
   return pass ? 0 : 1;
 }

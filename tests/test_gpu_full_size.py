@@ -83,3 +83,75 @@ def test_lock_step_batch_full_size(full):
     assert ok[0] == ok1 and rel_err(poses[0], pose1) < 1e-9 and np.allclose(affs[0], aff1, rtol=1e-8, atol=1e-10)
     assert scales[0] == np.float32(s1) and rmse[0] == np.float32(rmse1)
     f2.close()
+
+
+# The north star asks for "per-iteration pose delta within 1e-5 rel of the reference".  The reference's own arithmetic (oracle
+# mode 0: 4 SSE lanes x 3 tiers of fp32 sums, bit-identical to the compiled TrackerAndScaler.cpp) and the fp64-accumulating
+# arithmetic the GPU shares with oracle mode 1 (the sanctioned target, BASELINE.md 4: agreement 1e-5, measured ~1e-10) differ
+# by the reference's own fp32 summation noise.  That floor is asserted here — not only printed — so that a regression in
+# either direction shows up: increments of a few 1e-3 relative on the near-converged iterations, poses 1e-5.
+NOISE_INC_WORST = 2e-2   # worst per-iteration increment, relative, where the accept / reject sequences coincide
+NOISE_INC_MEDIAN = 2e-3
+NOISE_POSE = 1e-5        # final pose, relative
+
+
+def test_distance_to_the_reference_faithful_trace_is_asserted(full):
+    oc, gc = full
+    init = perturbed_pose(oc.o, oc.case["pose7_true"], np.random.default_rng(1), trans=0.02, rot=0.004)
+    ok_s, pose_s, aff_s, last_s, _ = oc.trk.track_newest_coarse(0, init, (0, 0), oc.levels - 1)  # mode 0 = the reference's arithmetic
+    ts = oc.trk.trace()
+    ok_g, pose_g, aff_g, last_g = gc.trk.trackNewestCoarse(gc.f_new, init, (0, 0), oc.levels - 1)
+    tg = gc.trk.trace()
+    assert ok_g == ok_s
+    errs, same = [], 0
+    for rg, rs in zip(tg, ts):
+        if not np.array_equal(rg[:3], rs[:3]):  # level / iteration / accept: from the first difference on the paths are different problems
+            break
+        same += 1
+        if rs[1] >= 0:
+            errs.append(rel_err(rg[7:15], rs[7:15]))
+    assert same >= 0.8 * len(ts), "accept / reject sequences diverge early: %d of %d rows" % (same, len(ts))
+    assert max(errs) < NOISE_INC_WORST and np.median(errs) < NOISE_INC_MEDIAN, (max(errs), np.median(errs))
+    assert rel_err(pose_g, pose_s) < NOISE_POSE and np.allclose(aff_g, aff_s, rtol=1e-4, atol=1e-4)
+    assert np.allclose(last_g, last_s, rtol=1e-4, equal_nan=True)
+    print("noise floor vs the reference-faithful trace: rows %d/%d, increments worst %.2e median %.2e, pose %.2e" % (
+        same, len(ts), max(errs), float(np.median(errs)), rel_err(pose_g, pose_s)))
+
+
+def test_hypothesis_loop_83_tries_full_size(full):
+    """f-4 at full size with the 83 initialisations of FrontEnd::trackNewCoarse (src/FrontEnd.cpp:147-180): (a) the normal case —
+    the constant-motion guess wins and nothing else is evaluated; (b) a bad motion model — wrong guesses first, so the loop walks
+    the rotation retries; both equal the sequential loop on the oracle."""
+    from direct_stereo_slam_b200 import synthetic as syn
+
+    oc, gc = full
+    c = oc.case
+    good = syn.pose7(*syn.se3_exp_mat(c["xi_true"] * 0.9))
+    dbl = syn.pose7(*syn.se3_exp_mat(c["xi_true"] * 1.8))
+    half = syn.pose7(*syn.se3_exp_mat(c["xi_true"] * 0.45))
+    tries = syn.frontend_pose_tries(good, dbl, half, IDENT7)
+    assert len(tries) == 83
+    last = np.full(5, 100.0)
+    ref = oc.trk.track_new_coarse(1, tries, (0.0, 0.0), oc.levels - 1, last)
+    got = gc.trk.trackNewCoarse(gc.f_new, tries, (0.0, 0.0), oc.levels - 1, last)
+    assert got["tryIterations"] == ref["tryIterations"] == 1 and got["haveOneGood"]
+    assert rel_err(got["pose"], ref["pose"]) < 1e-8 and np.allclose(got["achievedRes"], ref["achievedRes"], rtol=1e-6, equal_nan=True)
+    # (b) a threshold no try can meet (last_coarse_rmse far below what the scene allows): the loop never breaks, all 83
+    # hypotheses are evaluated (the speculative stages 1, 4, "the rest") and the replay applies the level-abort test of every
+    # try against the evolving achievedRes exactly like the sequential loop
+    last_b = np.full(5, ref["achievedRes"][0] / 1.6)
+    ref_b = oc.trk.track_new_coarse(1, tries, (0.0, 0.0), oc.levels - 1, last_b)
+    got_b = gc.trk.trackNewCoarse(gc.f_new, tries, (0.0, 0.0), oc.levels - 1, last_b)
+    assert got_b["tryIterations"] == ref_b["tryIterations"] == 83 and got_b["haveOneGood"] == ref_b["haveOneGood"], (got_b, ref_b)
+    assert rel_err(got_b["pose"], ref_b["pose"]) < 1e-8 and np.allclose(got_b["aff"], ref_b["aff"], rtol=1e-7, atol=1e-9)
+    assert np.allclose(got_b["achievedRes"], ref_b["achievedRes"], rtol=1e-6, equal_nan=True)
+    assert np.allclose(got_b["flow"], ref_b["flow"], rtol=1e-8)
+    # (c) a wrong motion model first (the constant-motion slot 12 degrees off), the usable guess only in the zero-motion slot
+    bad = oc.o.se3_mul(oc.o.se3_exp([0.0, 0, 0, 0.0, 0.21, 0.0]), good)
+    tries_c = syn.frontend_pose_tries(bad, oc.o.se3_mul(bad, bad), bad, good)
+    last_c = np.full(5, ref["achievedRes"][0] / 1.4)
+    ref_c = oc.trk.track_new_coarse(1, tries_c, (0.0, 0.0), oc.levels - 1, last_c)
+    got_c = gc.trk.trackNewCoarse(gc.f_new, tries_c, (0.0, 0.0), oc.levels - 1, last_c)
+    assert got_c["tryIterations"] == ref_c["tryIterations"] > 1 and got_c["haveOneGood"] == ref_c["haveOneGood"], (got_c, ref_c)
+    assert rel_err(got_c["pose"], ref_c["pose"]) < 1e-8 and np.allclose(got_c["achievedRes"], ref_c["achievedRes"], rtol=1e-6, equal_nan=True)
+    print("83-try loop: normal case 1 try; unreachable threshold %d tries; wrong motion model %d tries" % (got_b["tryIterations"], got_c["tryIterations"]))
