@@ -10,6 +10,7 @@
 //
 // There is no CPU fallback in this file: without a CUDA device every entry point fails with DSLAM_ENODEVICE.
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <new>
@@ -575,6 +576,108 @@ struct ScaleLM {
   }
 };
 
+// ---- resident evaluation server, host side -------------------------------------------------------------------------------
+int server_ensure_buffers(dslam_session *s) {
+  if (s->srv_doors) return DSLAM_OK;
+  DSLAM_CUDA(cudaHostAlloc((void **)&s->srv_doors, sizeof(ServerDoor) * kSrvLanes, cudaHostAllocMapped));
+  std::memset(s->srv_doors, 0, sizeof(ServerDoor) * kSrvLanes);
+  DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->srv_doors_dev, s->srv_doors, 0));
+  DSLAM_CUDA(cudaHostAlloc((void **)&s->srv_items, sizeof(EvalItem) * kSrvLanes * kMaxItemsPerLaunch, cudaHostAllocMapped));
+  DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->srv_items_alias, s->srv_items, 0));
+  DSLAM_CUDA(cudaHostAlloc((void **)&s->srv_units, sizeof(unsigned) * kSrvLanes * kSrvMaxUnits, cudaHostAllocMapped));
+  DSLAM_CUDA(cudaHostGetDevicePointer((void **)&s->srv_units_alias, s->srv_units, 0));
+  DSLAM_CUDA(cudaMalloc((void **)&s->srv_queue, sizeof(unsigned long long) * kSrvQueueSlots));
+  DSLAM_CUDA(cudaMemsetAsync(s->srv_queue, 0, sizeof(unsigned long long) * kSrvQueueSlots, s->stream));
+  DSLAM_CUDA(cudaMalloc((void **)&s->srv_qctl, 256));
+  DSLAM_CUDA(cudaMalloc((void **)&s->srv_lane_seq, sizeof(unsigned) * kSrvLanes));
+  DSLAM_CUDA(cudaMalloc((void **)&s->srv_items_dev, sizeof(EvalItem) * kSrvLanes * kMaxItemsPerLaunch));
+  return DSLAM_OK;
+}
+
+struct ServerLaneHost {  // where lane `id` of a lock step keeps its scratch and its slice of the result ring
+  EvalScratch scratch;
+  int slot0;
+};
+
+// Launch the server on the session stream (behind everything queued there: pyramids, template uploads).
+int server_start(dslam_session *s, int nlanes, const ServerLaneHost *lanes) {
+  int rc = server_ensure_buffers(s);
+  if (rc != DSLAM_OK) return rc;
+  ServerParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.nlanes = nlanes;
+  P.gen = ++s->srv_gen;
+  if ((P.gen & 0xffu) == 0) P.gen = ++s->srv_gen;  // the low byte tags queue slots; zero is what an untouched slot holds
+  P.doors = s->srv_doors_dev;
+  for (int l = 0; l < nlanes; l++) {
+    P.lane[l].partials = lanes[l].scratch.partials;
+    P.lane[l].counters = lanes[l].scratch.counters;
+    P.lane[l].results = s->results_dev + lanes[l].slot0;
+    P.lane[l].items_host = s->srv_items_alias + (size_t)l * kMaxItemsPerLaunch;
+    P.lane[l].units_host = s->srv_units_alias + (size_t)l * kSrvMaxUnits;
+  }
+  for (int l = 0; l < kSrvLanes; l++) P.last_round[l] = s->srv_round[l];
+  P.queue = s->srv_queue;
+  P.qctl = s->srv_qctl;
+  P.items_dev = s->srv_items_dev;
+  P.lane_seq = s->srv_lane_seq;
+  P.idle_ns = 2ull * 1000 * 1000 * 1000;   // no doorbell for 2 s: the host is gone
+  P.life_ns = 30ull * 1000 * 1000 * 1000;  // hard cap on the life of one server (an LM call times out on the host after timeout_s = 20 s)
+  DSLAM_CUDA(cudaMemsetAsync(s->srv_qctl, 0, 256, s->stream));
+  DSLAM_CUDA(cudaMemsetAsync(s->srv_queue, 0, sizeof(unsigned long long) * kSrvQueueSlots, s->stream));  // no stale units, whatever their tag
+  DSLAM_CUDA(launch_eval_server(P, s->num_sms * s->srv_ctas_per_sm, s->stream));
+  s->launches++;
+  return DSLAM_OK;
+}
+
+// One LM round of a lane: items + work units into the lane's mapped buffers, then the doorbell.
+int server_post(dslam_session *s, int lane, std::vector<EvalItem> &items, unsigned seq, int lanes_in_flight) {
+  const int n = (int)items.size();
+  if (n < 1 || n > kMaxItemsPerLaunch) return fail(DSLAM_EINVAL, "server round with %d items", n);
+  int total = assign_blocks(items.data(), n, s->num_sms, lanes_in_flight);
+  if (total > kSrvMaxUnits) {  // shrink proportionally: a lane round is at most kSrvMaxUnits work units
+    int t2 = 0;
+    for (int i = 0; i < n; i++) {
+      int per = (int)((long)items[i].nblocks * kSrvMaxUnits / total);
+      items[i].nblocks = per < 1 ? 1 : per;
+      t2 += items[i].nblocks;
+    }
+    while (t2 > kSrvMaxUnits) {  // rounding up of the small items: take the excess from the largest ones
+      int big = 0;
+      for (int i = 1; i < n; i++)
+        if (items[i].nblocks > items[big].nblocks) big = i;
+      items[big].nblocks--;
+      t2--;
+    }
+    total = 0;
+    for (int i = 0; i < n; i++) {
+      items[i].ppt_stride = items[i].nblocks * kEvalThreads;
+      items[i].cta_begin = total;
+      total += items[i].nblocks;
+    }
+  }
+  EvalItem *dst = s->srv_items + (size_t)lane * kMaxItemsPerLaunch;
+  std::memcpy(dst, items.data(), sizeof(EvalItem) * (size_t)n);
+  unsigned *u = s->srv_units + (size_t)lane * kSrvMaxUnits;
+  int k = 0;
+  for (int i = 0; i < n; i++)
+    for (int b = 0; b < items[i].nblocks; b++) u[k++] = ((unsigned)i << 16) | (unsigned)b;
+  ServerDoor *d = s->srv_doors + lane;
+  d->n_items = (unsigned)n;
+  d->n_units = (unsigned)total;
+  d->seq = seq;
+  const unsigned r = ++s->srv_round[lane];
+  std::atomic_thread_fence(std::memory_order_release);
+  reinterpret_cast<std::atomic<unsigned> *>(&d->round)->store(r, std::memory_order_release);
+  s->srv_rounds++;
+  return DSLAM_OK;
+}
+
+void server_stop(dslam_session *s) {
+  std::atomic_thread_fence(std::memory_order_release);
+  reinterpret_cast<std::atomic<unsigned> *>(&s->srv_doors[0].stop)->store(s->srv_gen, std::memory_order_release);
+}
+
 // All machines (pose and scale alike) advance one evaluation per round.  The machines are dealt into groups that run
 // concurrently: each group has its own host thread, CUDA stream, scratch and result slots and loops
 // "prepare -> launch (one kernel for the whole group) -> wait -> consume" until its machines are done.  Every machine
@@ -633,6 +736,28 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
     for (int g = 0; g < ngroups; g++)
       if (two_lanes(g)) DSLAM_CUDA(cudaStreamWaitEvent(s->lm_stream2[g], s->lm_fork, 0));
   }
+  // Resident server: one kernel for the whole call; every lane (group x half) rings its doorbell per round.  Not used while
+  // per-launch profiling is on (there are no launches to time) or when a lane could exceed one parameter block of items.
+  bool use_server = s->srv_enabled && !s->prof_on;
+  for (int g = 0; g < ngroups && use_server; g++) use_server = (int)grp[g].members.size() <= (two_lanes(g) ? 2 : 1) * kMaxItemsPerLaunch;
+  if (use_server) {
+    ServerLaneHost lanes[kSrvLanes];
+    for (int g = 0; g < ngroups; g++) {
+      lanes[2 * g] = ServerLaneHost{s->lm_scratch[g], g * slots_per_group};
+      lanes[2 * g + 1] = ServerLaneHost{s->lm_scratch2[g], g * slots_per_group + slots_per_half};
+    }
+    // the side streams' earlier kernels (previous launch-path calls) must have drained before the server reuses their scratch
+    for (int g = 1; g < ngroups; g++) {
+      DSLAM_CUDA(cudaEventRecord(s->lm_done[g], s->lm_stream[g]));
+      DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done[g], 0));
+    }
+    for (int g = 0; g < ngroups; g++) {
+      DSLAM_CUDA(cudaEventRecord(s->lm_done2[g], s->lm_stream2[g]));
+      DSLAM_CUDA(cudaStreamWaitEvent(s->stream, s->lm_done2[g], 0));
+    }
+    const int rc = server_start(s, 2 * ngroups, lanes);
+    if (rc != DSLAM_OK) return rc;
+  }
   auto now_ns = []() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto drive = [&](int g) {
     Group &gr = grp[g];
@@ -676,7 +801,12 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
       t_prep += t1 - t0;
       L.inflight = false;
       if (L.items.empty()) return;
-      gr.rc = launch_items(s, L.items, L.slot0, L.stream, L.scratch, &L.seq, &gr.launches, total_lanes);
+      if (use_server) {
+        L.seq = ++s->seq;
+        gr.rc = server_post(s, 2 * g + (int)(&L - lane), L.items, L.seq, total_lanes);
+      } else {
+        gr.rc = launch_items(s, L.items, L.slot0, L.stream, L.scratch, &L.seq, &gr.launches, total_lanes);
+      }
       t_launch += now_ns() - t1;
       rounds++;
       L.inflight = gr.rc == DSLAM_OK;
@@ -728,6 +858,7 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
     std::unique_lock<std::mutex> lock(w->m);
     w->cv.wait(lock, [&] { return w->done; });
   }
+  if (use_server) server_stop(s);
   int rc = DSLAM_OK;
   for (int g = 0; g < ngroups; g++) {
     if (counters) {
@@ -857,6 +988,11 @@ int dslam_session_create(int device, dslam_session **out) {
     const int v = atoi(e);
     if (v >= 1 && v <= dslam_session::kLmGroups) s->lm_groups = v;
   }
+  if (const char *e = getenv("DSLAM_LM_SERVER")) s->srv_enabled = atoi(e) != 0;
+  if (const char *e = getenv("DSLAM_LM_SERVER_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 5) s->srv_ctas_per_sm = v;
+  }
   DSLAM_CUDA(cudaEventCreateWithFlags(&s->lm_fork, cudaEventDisableTiming));
   {  // LM rounds are latency-critical, the overlapped pyramid builds are not: highest / lowest stream priority
     DSLAM_CUDA(cudaStreamCreateWithPriority(&s->pyr_stream, cudaStreamNonBlocking, prio_lo));
@@ -930,6 +1066,10 @@ int dslam_session_destroy(dslam_session *s) {
   if (s->pyr_in) cudaEventDestroy(s->pyr_in);
   for (int k = 0; k < dslam_session::kPyrEvents; k++)
     if (s->pyr_ev[k]) cudaEventDestroy(s->pyr_ev[k]);
+  if (s->srv_doors) cudaFreeHost(s->srv_doors);
+  if (s->srv_items) cudaFreeHost(s->srv_items);
+  if (s->srv_units) cudaFreeHost(s->srv_units);
+  cudaFree(s->srv_queue); cudaFree(s->srv_qctl); cudaFree(s->srv_lane_seq); cudaFree(s->srv_items_dev);
   cudaFree(s->upload_arena);
   cudaFree(s->scratch.partials);
   cudaFree(s->scratch.counters);
@@ -1664,14 +1804,20 @@ int dslam_lm_batch(int n_pose, dslam_ctx *const *pose_ctxs, dslam_frame *const *
   std::vector<ScaleLM> scale((size_t)n_scale);
   for (int i = 0; i < n_pose; i++) pose_ctxs[i]->trace.clear();
   for (int i = 0; i < n_scale; i++) scale_ctxs[i]->trace.clear();
-  for (int i = 0; i < n_pose; i++)
+  // the machines of a batch run on several host threads: a tracker object that appears more than once (hypotheses of one
+  // frame passed as separate jobs) records the trace of its FIRST job only — one writer per trace vector
+  std::vector<const dslam_ctx *> traced;
+  for (int i = 0; i < n_pose; i++) {
+    const bool first = std::find(traced.begin(), traced.end(), pose_ctxs[i]) == traced.end();
+    if (first) traced.push_back(pose_ctxs[i]);
     pose[i].begin(pose_ctxs[i], pose_frames[i], new_exposure ? new_exposure[i] : 1.0f, pose7_io + 7 * i, aff_io + 2 * i, coarsestLvl, minResForAbort,
-                  &pose_ctxs[i]->trace);
+                  first ? &pose_ctxs[i]->trace : nullptr);
+  }
   for (int i = 0; i < n_scale; i++) {
     // a tracker object that also tracks in this batch keeps the pose trace; its scale trace is not recorded
-    bool also_pose = false;
-    for (int j = 0; j < n_pose; j++) also_pose |= pose_ctxs[j] == scale_ctxs[i];
-    scale[i].begin(scale_ctxs[i], scale_frames[i], scales_io[i], scale_coarsestLvl, also_pose ? nullptr : &scale_ctxs[i]->trace);
+    const bool first = std::find(traced.begin(), traced.end(), scale_ctxs[i]) == traced.end();
+    if (first) traced.push_back(scale_ctxs[i]);
+    scale[i].begin(scale_ctxs[i], scale_frames[i], scales_io[i], scale_coarsestLvl, first ? &scale_ctxs[i]->trace : nullptr);
   }
   dslam_ctx *counters = n_pose > 0 ? pose_ctxs[0] : scale_ctxs[0];
   const int rc = run_lock_step(s, pose, scale, counters);

@@ -85,6 +85,25 @@ struct dslam_session {
     bool has_job = false, done = false, quit = false;
   };
   Worker *workers[kLmGroups] = {};  // [0] unused (the caller's thread)
+  // Resident evaluation server (kernels_residual.cu: eval_server_kernel): for the duration of a lock-step LM call one kernel
+  // stays on the GPU; the lanes ring doorbells in mapped pinned memory instead of launching a kernel per LM round.
+  // OFF by default (DSLAM_LM_SERVER=1 turns it on): measured on B200 / PCIe Gen5 the doorbell protocol costs more than the
+  // launch it replaces — the SMs must poll host memory (>= 2 dependent PCIe read round trips of ~1.5 us per round: doorbell,
+  // then items + units) while cudaLaunchKernel is a posted write plus one front-end fetch: S = 1 tracking 0.585 ms vs 0.498 ms,
+  // 512 streams 76-83 k vs 95 k frames/s (profiles/r02_resident_server.md).  Results are bit-identical either way
+  // (tests/test_gpu_batch.py); the launch path is also used while per-launch profiling is on.
+  bool srv_enabled = false;
+  int srv_ctas_per_sm = 3;                     // resident worker CTAs per SM (DSLAM_LM_SERVER_CTAS); the rest of the SM stays free for the pyramid stream
+  dslam::ServerDoor *srv_doors = nullptr;      // pinned mapped [kSrvLanes]
+  dslam::ServerDoor *srv_doors_dev = nullptr;  // device alias
+  dslam::EvalItem *srv_items = nullptr, *srv_items_alias = nullptr;    // pinned mapped [kSrvLanes][kMaxItemsPerLaunch] + device alias
+  unsigned *srv_units = nullptr, *srv_units_alias = nullptr;            // pinned mapped [kSrvLanes][kSrvMaxUnits] + device alias
+  unsigned long long *srv_queue = nullptr;     // device
+  unsigned *srv_qctl = nullptr, *srv_lane_seq = nullptr;
+  dslam::EvalItem *srv_items_dev = nullptr;
+  unsigned srv_round[dslam::kSrvLanes] = {};   // last doorbell value written per lane
+  unsigned srv_gen = 0;
+  std::atomic<long long> srv_rounds{0};        // LM rounds served through doorbells (diagnostics)
   std::mutex prof_mutex;
   // host-side time split of the lock-step driver (ns, summed over the group threads)
   std::atomic<long long> t_prep_ns{0}, t_launch_ns{0}, t_wait_ns{0}, n_rounds{0};

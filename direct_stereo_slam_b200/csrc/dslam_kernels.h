@@ -58,6 +58,39 @@ struct EvalScratch {
   int *counters;      // [kMaxItemsPerLaunch][4]: nE, nSat, nInl, ticket
 };
 
+// ---- resident evaluation server (kernels_residual.cu: eval_server_kernel) -----------------------------------------------------
+constexpr int kSrvLanes = 32;              // doorbells: one per LM lane (group x half)
+constexpr unsigned kSrvQueueSlots = 16384;  // work-unit queue in HBM (a lane round is <= 512 units, <= kSrvLanes rounds in flight)
+constexpr int kSrvMaxUnits = 512;          // CTA-sized work units per lane round
+// doorbell of one lane in mapped pinned memory (its own 128-byte line).  The host fills items_host / units_host of the lane
+// and n_items / n_units / seq, then stores `round` (release).  doors[0].stop = generation number asks the server to leave.
+struct alignas(128) ServerDoor {
+  unsigned round, n_items, n_units, seq;
+  unsigned stop;
+  unsigned pad[27];
+};
+static_assert(sizeof(ServerDoor) == 128, "ServerDoor layout");
+struct ServerLane {
+  double *partials;                // reduction scratch of the lane (EvalScratch)
+  int *counters;
+  EvalResult *results;             // device alias of the lane's slice of the mapped result ring
+  const EvalItem *items_host;      // mapped pinned: items of the lane's current round
+  const unsigned *units_host;      // mapped pinned: (item << 16 | CTA index) per work unit
+};
+struct ServerParams {
+  int nlanes;
+  unsigned gen;                    // generation of this server (tags queue slots; doors[0].stop == gen stops it)
+  const volatile ServerDoor *doors;  // mapped pinned
+  ServerLane lane[kSrvLanes];
+  unsigned last_round[kSrvLanes];  // doorbell values at launch
+  unsigned long long *queue;       // [kSrvQueueSlots]
+  unsigned *qctl;                  // [0] next ticket, [1] next free index (zeroed before every launch)
+  EvalItem *items_dev;             // [kSrvLanes][kMaxItemsPerLaunch]
+  unsigned *lane_seq;              // [kSrvLanes]
+  unsigned long long idle_ns, life_ns;
+};
+cudaError_t launch_eval_server(const ServerParams &P, int workers, cudaStream_t stream);
+
 // mode 0 = pose (8-DoF), 1 = scale (1-DoF). results_dev = device alias of the mapped EvalResult array.
 cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream);

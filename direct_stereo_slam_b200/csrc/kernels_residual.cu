@@ -379,26 +379,14 @@ __device__ __forceinline__ void eval_pose_mma(const EvalItem &it, int bx, double
 // tracker and the scale optimiser of a stereo frame advance in the same launch).  The grid is flat: the CTAs of item 0,
 // then those of item 1, ... (EvalItem::cta_begin); a CTA finds its item by bisection over the <= 128 prefix entries in
 // constant memory, so items of very different sizes share a launch without idle CTAs.
-#ifndef DSLAM_EVAL_MIN_CTAS
-#define DSLAM_EVAL_MIN_CTAS 5
-#endif
-template <int MODE, int CAP>
-__global__ void __launch_bounds__(kEvalThreads, DSLAM_EVAL_MIN_CTAS) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
-                                                           EvalResult *__restrict__ results, unsigned seq, int nitems) {
+// The work of ONE CTA on ONE item (item slot iy of its launch / lane round, CTA bx of the item's it.nblocks): walk the CTA's
+// share of the records, reduce to one partial record, take the item's ticket and — in the CTA that draws the last one — sum
+// the partials in CTA order and publish the result record to the host.  Shared by the launch kernel below (items in
+// kernel-parameter space) and the resident server kernel (items in shared memory).
+template <int MODE>
+__device__ __forceinline__ void eval_cta(const EvalItem &it, int iy, int bx, EvalScratch scratch, EvalResult *__restrict__ results, unsigned seq) {
   constexpr int NV = MODE == 1 ? kScaleVals : kPoseVals;
   constexpr int NW = kEvalThreads / 32;
-  int iy = 0;
-  if (CAP > 1) {  // last item whose cta_begin <= blockIdx.x
-    int lo = 0, hi = nitems - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (batch.item[mid].cta_begin <= (int)blockIdx.x) lo = mid;
-      else hi = mid - 1;
-    }
-    iy = lo;
-  }
-  const EvalItem &it = batch.item[iy];
-  const int bx = (int)blockIdx.x - it.cta_begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   DBG_MIN(0);
@@ -503,7 +491,201 @@ __global__ void __launch_bounds__(kEvalThreads, DSLAM_EVAL_MIN_CTAS) eval_kernel
     __stcg(cnt + k, 0);
   }
   DBG_MAX(3);
-  if (tid == 67) __stcg(cnt + 3, 0);  // ticket: the next launch on this stream starts after this grid has drained
+  if (tid == 67) __stcg(cnt + 3, 0);  // ticket: the next evaluation of this slot starts after this item's result was consumed
+}
+
+#ifndef DSLAM_EVAL_MIN_CTAS
+#define DSLAM_EVAL_MIN_CTAS 5
+#endif
+template <int MODE, int CAP>
+__global__ void __launch_bounds__(kEvalThreads, DSLAM_EVAL_MIN_CTAS) eval_kernel(const __grid_constant__ BatchT<CAP> batch, EvalScratch scratch,
+                                                           EvalResult *__restrict__ results, unsigned seq, int nitems) {
+  int iy = 0;
+  if (CAP > 1) {  // last item whose cta_begin <= blockIdx.x
+    int lo = 0, hi = nitems - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (batch.item[mid].cta_begin <= (int)blockIdx.x) lo = mid;
+      else hi = mid - 1;
+    }
+    iy = lo;
+  }
+  const EvalItem &it = batch.item[iy];
+  eval_cta<MODE>(it, iy, (int)blockIdx.x - it.cta_begin, scratch, results, seq);
+}
+
+// ---- resident evaluation server -------------------------------------------------------------------------------------
+// One kernel that stays on the GPU for the duration of a lock-step LM call and takes the launch out of every LM round:
+//   * the host threads ("lanes") write the items of their next round and a list of CTA-sized work units (item, CTA index)
+//     into mapped pinned memory and ring their doorbell (a round counter in a 128-byte line of their own);
+//   * CTA 0 is the DISPATCHER: one warp polls all doorbells at once (one PCIe read per lane, issued together), then the CTA
+//     pulls the rung lanes' items into HBM and their units into a bounded multi-producer / multi-consumer queue in HBM
+//     (a slot = one 64-bit word: generation | lap tag | lane | item | CTA index, so publishing a unit is one store);
+//   * every other CTA is a WORKER: it draws a ticket, waits for that queue slot to carry its tag, copies the unit's item into
+//     shared memory and runs eval_cta — the very code of the launch kernel — publishing results exactly as launches do.
+// Nothing here can hang the GPU: the dispatcher leaves when the host says stop, when no doorbell rang for idle_ns, or after
+// life_ns; it then poisons the queue so that every worker leaves too, and a worker that waits longer than life_ns leaves by
+// itself.  The 8x8 solve stays on the host (north star); the doorbell replaces cudaLaunchKernel, whose cost under eight
+// contending host threads (16-19 us) was a fifth of an LM round.
+constexpr unsigned kSrvPoison = 0xffu;
+__device__ __forceinline__ unsigned ld_volatile_u32(const volatile unsigned *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long srv_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long srv_slot_word(unsigned gen, unsigned idx, unsigned lane, unsigned item, unsigned bx) {
+  const unsigned long long tag = ((unsigned long long)(gen & 0xffu) << 16) | ((idx / kSrvQueueSlots + 1u) & 0xffffu);
+  return (tag << 40) | ((unsigned long long)(lane & 0xffu) << 32) | ((unsigned long long)(item & 0xffu) << 24) | ((unsigned long long)(bx & 0xffffu) << 8);
+}
+
+__global__ void __launch_bounds__(kEvalThreads, DSLAM_EVAL_MIN_CTAS) eval_server_kernel(const __grid_constant__ ServerParams P) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long t0 = srv_now();
+  if (blockIdx.x == 0) {
+    // ---------------- dispatcher ----------------
+    __shared__ unsigned s_round[kSrvLanes], s_seen[kSrvLanes], s_mask, s_hdr[4], s_base;
+    __shared__ int s_stop;
+    if (tid < kSrvLanes) s_seen[tid] = P.last_round[tid];
+    __syncthreads();
+    unsigned long long t_act = t0;  // (lane 0 of warp 0 keeps the clock: every decision below is taken by one thread and read by all)
+    for (;;) {
+      if (warp == 0) {
+        unsigned r = 0;
+        bool rung = false;
+        if (lane < P.nlanes) {
+          r = ld_volatile_u32(&P.doors[lane].round);
+          rung = r != s_seen[lane];
+          s_round[lane] = r;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, rung);
+        if (lane == 0) {
+          const unsigned long long now = srv_now();
+          if (mask) t_act = now;
+          s_mask = mask;
+          s_stop = mask == 0 && (ld_volatile_u32(&P.doors[0].stop) == P.gen || now - t_act > P.idle_ns || now - t0 > P.life_ns);
+        }
+      }
+      __syncthreads();
+      unsigned mask = s_mask;
+      const bool leave = s_stop != 0;
+      __syncthreads();  // s_mask / s_stop are rewritten by the next poll
+      if (leave) break;
+      if (mask == 0) continue;
+      while (mask) {
+        const int L = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (tid == 0) {
+          const uint4 h = ld_volatile_v4((const void *)&P.doors[L]);  // round, n_items, n_units, seq
+          s_hdr[0] = h.y;
+          s_hdr[1] = h.z;
+          s_hdr[2] = h.w;
+          s_base = atomicAdd(P.qctl + 1, h.z);
+          P.lane_seq[L] = h.w;
+        }
+        __syncthreads();
+        const int n_items = (int)s_hdr[0], n_units = (int)s_hdr[1];
+        const unsigned base = s_base;
+        // items: host -> HBM (all loads of a thread are issued before its stores: one PCIe round trip, not one per record)
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.lane[L].items_host);
+        uint4 *dst = reinterpret_cast<uint4 *>(P.items_dev + (size_t)L * kMaxItemsPerLaunch);
+        constexpr int IT4 = (int)(sizeof(EvalItem) / 16);
+        for (int k0 = 0; k0 < n_items * IT4; k0 += kEvalThreads * 8) {
+          uint4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int k = k0 + j * kEvalThreads + tid;
+            if (k < n_items * IT4) v[j] = ld_volatile_v4(src + k);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int k = k0 + j * kEvalThreads + tid;
+            if (k < n_items * IT4) dst[k] = v[j];
+          }
+        }
+        unsigned u[4];
+        const unsigned *usrc = P.lane[L].units_host;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // <= 512 units per round and lane
+          const int k = j * kEvalThreads + tid;
+          u[j] = k < n_units ? ld_volatile_u32(usrc + k) : 0u;
+        }
+        __threadfence();   // items and lane_seq before the units that point at them
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int k = j * kEvalThreads + tid;
+          if (k < n_units) {
+            const unsigned idx = base + (unsigned)k;
+            st_release_u64(P.queue + idx % kSrvQueueSlots, srv_slot_word(P.gen, idx, (unsigned)L, u[j] >> 16, u[j] & 0xffffu));
+          }
+        }
+        if (tid == 0) s_seen[L] = s_round[L];
+        __syncthreads();
+      }
+    }
+    // leave: poison every worker
+    if (tid == 0) s_base = atomicAdd(P.qctl + 1, gridDim.x - 1);
+    __syncthreads();
+    for (unsigned k = tid; k < gridDim.x - 1; k += kEvalThreads) {
+      const unsigned idx = s_base + k;
+      st_release_u64(P.queue + idx % kSrvQueueSlots, srv_slot_word(P.gen, idx, kSrvPoison, kSrvPoison, 0));
+    }
+    return;
+  }
+  // ---------------- worker ----------------
+  __shared__ unsigned long long s_desc;
+  __shared__ unsigned s_seq;
+  __shared__ __align__(16) unsigned char s_item[sizeof(EvalItem)];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned idx = atomicAdd(P.qctl + 0, 1u);
+      const unsigned long long want = (((unsigned long long)(P.gen & 0xffu) << 16) | ((idx / kSrvQueueSlots + 1u) & 0xffffu));
+      const unsigned long long *slot = P.queue + idx % kSrvQueueSlots;
+      unsigned long long d;
+      unsigned spins = 0;
+      for (;;) {
+        d = ld_acquire_u64(slot);
+        if ((d >> 40) == want) break;
+        if ((++spins & 63u) == 0 && srv_now() - t0 > P.life_ns) {  // the dispatcher is gone or the host never came back
+          d = srv_slot_word(P.gen, idx, kSrvPoison, kSrvPoison, 0);
+          break;
+        }
+        __nanosleep(100);
+      }
+      s_desc = d;
+    }
+    __syncthreads();
+    const unsigned long long d = s_desc;
+    const unsigned L = (unsigned)(d >> 32) & 0xffu, item = (unsigned)(d >> 24) & 0xffu, bx = (unsigned)(d >> 8) & 0xffffu;
+    if (L == kSrvPoison) return;
+    constexpr int IT4 = (int)(sizeof(EvalItem) / 16);
+    if (tid < IT4) reinterpret_cast<uint4 *>(s_item)[tid] = __ldcg(reinterpret_cast<const uint4 *>(P.items_dev + (size_t)L * kMaxItemsPerLaunch + item) + tid);
+    if (tid == 32) s_seq = __ldcg(P.lane_seq + L);
+    __syncthreads();
+    EvalScratch sc;
+    sc.partials = P.lane[L].partials;
+    sc.counters = P.lane[L].counters;
+    eval_cta<2>(*reinterpret_cast<const EvalItem *>(s_item), (int)item, (int)bx, sc, P.lane[L].results, s_seq);
+  }
 }
 
 template <int MODE, int CAP>
@@ -542,6 +724,12 @@ cudaError_t debug_times(unsigned long long *out8, int reset) {
   return e;
 }
 #endif
+
+cudaError_t launch_eval_server(const ServerParams &P, int workers, cudaStream_t stream) {
+  if (workers < 1 || P.nlanes < 1 || P.nlanes > kSrvLanes) return cudaErrorInvalidValue;
+  eval_server_kernel<<<workers + 1, kEvalThreads, 0, stream>>>(P);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_eval(int mode, const EvalBatch &batch, int nitems, int total_ctas, EvalScratch scratch, EvalResult *results_dev,
                         unsigned seq, cudaStream_t stream) {

@@ -83,3 +83,35 @@ def test_lm_batch_equals_separate_calls(session, oracle):
         assert abs(scales[k] - s_o) <= 1e-6 * abs(s_o)
     for g in gcs:
         g.close()
+
+
+def test_resident_server_equals_launch_per_round(oracle, monkeypatch):
+    """The resident evaluation server (doorbells instead of a kernel launch per LM round) and the launch-per-round path run the
+    same eval_cta code on the same work split: identical traces, poses, scales — bit for bit — for one stream and for a batch
+    of streams with pose and scale machines in one lock step."""
+    from helpers import GpuCase, OracleCase
+
+    results = {}
+    oc = OracleCase(oracle, "tiny", 3, scale_error=1.4)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DSLAM_LM_SERVER", mode)
+        s = api.Session(0)
+        gc = GpuCase(s, oc, template="device")
+        l0 = s.launch_count()
+        ok, pose, aff, last = gc.trk.trackNewestCoarse(gc.f_new, IDENT7, (0, 0), oc.levels - 1)
+        single_launches = s.launch_count() - l0
+        tr = gc.trk.trace()
+        rmse, sc = gc.trk.optimizeScale(gc.f_right, 1.0, oc.levels - 1)
+        n = 24
+        poses = np.tile(IDENT7, (n, 1))
+        poses[:, 4:] += np.random.default_rng(0).normal(0, 0.01, (n, 3))
+        out = api.lm_batch([gc.trk] * n, [gc.f_new] * n, poses, np.zeros((n, 2)), oc.levels - 1, [gc.trk] * 3, [gc.f_right] * 3, [0.8, 1.0, 1.3])
+        results[mode] = (ok, pose, aff, last, tr, rmse, sc, out, single_launches)
+        gc.close()
+        s.close()
+    a, b = results["1"], results["0"]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3], equal_nan=True)
+    assert np.array_equal(a[4], b[4]) and a[5] == b[5] and a[6] == b[6]
+    for x, y in zip(a[7], b[7]):
+        assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True)
+    assert a[8] == 1 and b[8] > 10, "server: one launch per LM call; launch path: one per round (%d / %d)" % (a[8], b[8])
