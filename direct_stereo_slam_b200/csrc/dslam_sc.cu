@@ -89,7 +89,7 @@ struct dslam_scdb {
   std::unordered_map<int, int> row_of;   // global id -> local row
   // query-side buffers (grown on demand)
   int qcap = 0;
-  float *d_qsigs = nullptr, *d_qkeys = nullptr;
+  float *d_qsigs = nullptr, *d_qkeys = nullptr, *d_qsplit = nullptr;  // d_qsplit: hi / lo halves of the batch for the tensor-core scan
   double *d_qsigs64 = nullptr;
   u64 *d_topk = nullptr, *d_exact = nullptr, *d_best = nullptr, *d_gather = nullptr, *d_scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -131,9 +131,9 @@ int ensure_query_buffers(dslam_scdb *db, int nq) {
   const int world = db->world;
   if (nq > db->qcap) {
     cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_qsigs64); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best);
-    cudaFree(db->d_gather);
+    cudaFree(db->d_gather); cudaFree(db->d_qsplit);
     if (db->h_words) cudaFreeHost(db->h_words);
-    db->d_qsigs = db->d_qkeys = nullptr;
+    db->d_qsigs = db->d_qkeys = db->d_qsplit = nullptr;
     db->d_qsigs64 = nullptr;
     db->d_topk = db->d_exact = db->d_best = db->d_gather = nullptr;
     db->h_words = db->d_words = nullptr;
@@ -141,6 +141,7 @@ int ensure_query_buffers(dslam_scdb *db, int nq) {
     const int cap = std::max(32, nq);
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs, (size_t)cap * db->n_cells * sizeof(float)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qkeys, (size_t)cap * db->n_rings * sizeof(float)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_qsplit, (size_t)2 * cap * db->n_cells * sizeof(float)));
     if (db->fp64) DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs64, (size_t)cap * db->n_cells * sizeof(double)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_topk, (size_t)cap * kScTopK * sizeof(u64)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_exact, (size_t)cap * kScTopK * sizeof(u64)));
@@ -275,7 +276,7 @@ int local_query(dslam_scdb *db, int nq, const float *ringkeys, const float *sigs
   DSLAM_CUDA(cudaEventRecord(db->ev0, s->stream));
   int nlists = 0;
   DSLAM_CUDA(launch_sc_scan(db->d_sigs, db->d_keys, db->d_ids, db->n, db->n_cells, db->n_rings, db->d_qsigs, db->d_qkeys, nq, ringkey_thres,
-                            max_id, (float)db->n_sectors, db->d_scratch, &nlists, s->stream));
+                            max_id, (float)db->n_sectors, db->d_scratch, &nlists, db->d_qsplit, s->stream));
   DSLAM_CUDA(cudaEventRecord(db->ev1, s->stream));
   db->have_scan_time = true;
   s->launches += (nq + 31) / 32;
@@ -364,7 +365,7 @@ int dslam_sc_destroy(dslam_scdb *db) {
   cudaFree(db->d_mail);
   cudaFree(db->d_sigs); cudaFree(db->d_keys); cudaFree(db->d_ids); cudaFree(db->d_sigs64);
   cudaFree(db->d_qsigs); cudaFree(db->d_qkeys); cudaFree(db->d_qsigs64); cudaFree(db->d_topk); cudaFree(db->d_exact); cudaFree(db->d_best);
-  cudaFree(db->d_gather); cudaFree(db->d_ticket);
+  cudaFree(db->d_gather); cudaFree(db->d_ticket); cudaFree(db->d_qsplit);
   cudaFree(db->d_pts); cudaFree(db->d_mom); cudaFree(db->d_gen_sig64); cudaFree(db->d_cells); cudaFree(db->d_gen_sig); cudaFree(db->d_gen_key);
   cudaFree(db->d_scratch); cudaFree(db->d_pair_q); cudaFree(db->d_pair_row); cudaFree(db->d_pair_diff);
   if (db->h_keys) cudaFreeHost(db->h_keys);
@@ -893,7 +894,7 @@ int dslam_sc_last_scan_ms(dslam_scdb *db, float *ms) {
 }
 
 int dslam_sc_set_scan_kernel(int flavour) {
-  if (flavour < 0 || flavour > 2) return fail(DSLAM_EINVAL, "scan kernel flavour must be 0 (auto), 1 (stream) or 2 (tile)");
+  if (flavour < 0 || flavour > 3) return fail(DSLAM_EINVAL, "scan kernel flavour must be 0 (auto), 1 (stream), 2 (tile) or 3 (tcgen05)");
   sc_set_scan_flavour(flavour);
   return DSLAM_OK;
 }

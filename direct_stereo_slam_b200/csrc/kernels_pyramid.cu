@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ F
   __shared__ __align__(128) float box[2][kBoxStride];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ TileInfo info[2];
+  // host-layout staging of one tile (Vector3f AoS: 12 B per pixel, 768 B per 64-pixel row): collected here and written out as
+  // 16-B vectors — three scalar stores per pixel at a 12-B stride cost three times the store instructions
+  __shared__ __align__(16) float sh3[kGradTileH][3 * kGradTileW];
   const int tid = threadIdx.x;
   const PyramidGeom &G = B.G;
   const int tiles_per_frame = G.tile_begin[G.levels];
@@ -178,6 +181,9 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ F
     mbar_wait(&bar[stage], (it >> 1) & 1);
     const TileInfo ti = info[stage];
     const float *__restrict__ bx = box[stage];
+    // 16-B stores need 16-B aligned rows: 12 * w bytes per row, i.e. w % 4 == 0 (levels 0-2 of every shipped calibration, 98 % of
+    // the bytes), and a full-width tile; other tiles keep the scalar stores
+    const bool vec3 = ti.hd != nullptr && (ti.w & 3) == 0 && ti.x0 + kGradTileW <= ti.w && (reinterpret_cast<size_t>(ti.hd) & 15) == 0;
 #pragma unroll
     for (int k = 0; k < kGradTileH / 4; k++) {
       const int lx = tid % kGradTileW, ly = tid / kGradTileW + 4 * k;
@@ -205,14 +211,27 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ F
       }
       const size_t idx = (size_t)y * ti.w + x;
       __stcs(ti.tex + idx, make_float4(c, dx, dy, ag));
-      if (ti.hd != nullptr) {
+      if (vec3) {
+        sh3[ly][3 * lx + 0] = c;
+        sh3[ly][3 * lx + 1] = dx;
+        sh3[ly][3 * lx + 2] = dy;
+      } else if (ti.hd != nullptr) {
         ti.hd[3 * idx + 0] = c;
         ti.hd[3 * idx + 1] = dx;
         ti.hd[3 * idx + 2] = dy;
       }
       if (ti.ha != nullptr) ti.ha[idx] = ag;
     }
-    __syncthreads();  // everyone is done with box[stage] / info[stage]: thread 0 may refill them in the next iteration
+    if (vec3) {
+      __syncthreads();
+      constexpr int kRowVec = 3 * kGradTileW / 4;  // 48 x 16 B per tile row
+      for (int v = tid; v < kGradTileH * kRowVec; v += 256) {
+        const int ly = v / kRowVec, c4 = v - ly * kRowVec;
+        const int y = ti.y0 + ly;
+        if (y < ti.h) *reinterpret_cast<float4 *>(ti.hd + 3 * ((size_t)y * ti.w + ti.x0) + 4 * c4) = *reinterpret_cast<const float4 *>(&sh3[ly][4 * c4]);
+      }
+    }
+    __syncthreads();  // everyone is done with box[stage] / info[stage] / sh3: thread 0 may refill them in the next iteration
   }
 }
 

@@ -312,12 +312,16 @@ __device__ __forceinline__ void sc_tma_load_2d(void *dst, const CUtensorMap *map
 }
 __device__ __forceinline__ void sc_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); }
 
-// Work split: the database is cut into groups of 64 rows; CTA c owns the contiguous run of groups [c * gpc, (c+1) * gpc) and
-// walks it in tiles of up to 4 groups, so all CTAs carry the same load to within one group (a 256-row tile granularity
-// would leave 12 % of the machine idle at 100k rows / 148 SMs).  A partial last tile loads and multiplies only its groups.
-constexpr int kGroupRows = 64;
-constexpr int kGroupsPerTile = kTileRows / kGroupRows;
-constexpr int kGroupBytes = kGroupRows * kTileK * 4;  // 8 KB per TMA box
+// Work split: the database is cut into HALF-GROUPS of 32 rows (one TMA box, one consumer warp's rows); CTA c owns the
+// contiguous run of half-groups [c * hpc, (c+1) * hpc) and walks it in tiles of up to 8 half-groups (256 rows), so all CTAs
+// carry the same load to within 32 rows: a 100k-row database fills 148 CTAs to 99 %, a 12.5k-row shard (8 GPUs) still keeps
+// 131 CTAs busy in one wave (a 64-row granularity left 50 SMs idle there, a 256-row one idles 12 % at 100k rows).  Half-group t
+// of a tile lands at rows [32 t, 32 t + 32) of the stage — two consecutive boxes lie exactly like one 64-row group — and belongs
+// to the consumer warps of row half rh = t & 1.  A partial last tile loads and multiplies only its half-groups.
+constexpr int kHalfRows = 32;
+constexpr int kHalvesPerTile = kTileRows / kHalfRows;  // 8
+constexpr int kHalfBytes = kHalfRows * kTileK * 4;     // 4 KB per TMA box
+constexpr int kGroupRows = 64;                         // rows between consecutive groups of one lane
 
 // One pipeline stage (32 cells) of a tile with NG row groups: per 4 cells a lane reads its NG rows (LDS.128, conflict-free
 // through the swizzle) and the 8 queries of its warp (broadcast LDS.128).  Packed FP32 FMAs (FFMA2, sm_100: two FMAs on a
@@ -347,7 +351,7 @@ __device__ __forceinline__ void sc_tile_stage(const float4 *__restrict__ A, cons
 __global__ void __launch_bounds__(kTileThreads, 1)
     sc_scan_tile_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_q, const float *__restrict__ keys,
                         const int *__restrict__ ids, int n_rows, int n_cells, int key_dim, const float *__restrict__ q_keys, int nqc,
-                        float ringkey_thres, int max_id, float sc_width, int groups_per_cta, u64 *__restrict__ scratch, int list_stride) {
+                        float ringkey_thres, int max_id, float sc_width, int halves_per_cta, u64 *__restrict__ scratch, int list_stride) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-B alignment
   float *sA = reinterpret_cast<float *>(base);
@@ -357,10 +361,10 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   uint64_t *empty = full + kTileStages;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
-  const int g_begin = blockIdx.x * groups_per_cta;
-  const int g_end = min(g_begin + groups_per_cta, n_groups);
-  const int row_end = min(g_end * kGroupRows, n_rows);
+  const int n_halves = (n_rows + kHalfRows - 1) / kHalfRows;
+  const int h_begin = blockIdx.x * halves_per_cta;
+  const int h_end = min(h_begin + halves_per_cta, n_halves);
+  const int row_end = min(h_end * kHalfRows, n_rows);
   const int n_chunks = (n_cells + kTileK - 1) / kTileK;
   if (tid == 0) {
     for (int s = 0; s < kTileStages; s++) {
@@ -375,14 +379,14 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     // ---- producer warp: one lane walks (tile, chunk) and keeps kTileStages stages in flight ----
     if (lane == 0) {
       int it = 0;
-      for (int g0 = g_begin; g0 < g_end; g0 += kGroupsPerTile) {
-        const int ng = min(kGroupsPerTile, g_end - g0);
+      for (int h0 = h_begin; h0 < h_end; h0 += kHalvesPerTile) {
+        const int nh = min(kHalvesPerTile, h_end - h0);
         for (int c = 0; c < n_chunks; c++, it++) {
           const int s = it % kTileStages;
           sc_mbar_wait(&empty[s], ((it / kTileStages) & 1) ^ 1);  // passes immediately on the first lap
-          sc_mbar_expect_tx(&full[s], ng * kGroupBytes + kStageBBytes);
+          sc_mbar_expect_tx(&full[s], nh * kHalfBytes + kStageBBytes);
           unsigned char *dst = reinterpret_cast<unsigned char *>(sA) + (size_t)s * kStageABytes;
-          for (int g = 0; g < ng; g++) sc_tma_load_2d(dst + (size_t)g * kGroupBytes, &map_db, c * kTileK, (g0 + g) * kGroupRows, &full[s]);
+          for (int t = 0; t < nh; t++) sc_tma_load_2d(dst + (size_t)t * kHalfBytes, &map_db, c * kTileK, (h0 + t) * kHalfRows, &full[s]);
           sc_tma_load_2d(reinterpret_cast<unsigned char *>(sB) + (size_t)s * kStageBBytes, &map_q, c * kTileK, 0, &full[s]);
         }
       }
@@ -398,8 +402,9 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   TopK top;
   top.init();
   int it = 0;
-  for (int g0 = g_begin; g0 < g_end; g0 += kGroupsPerTile) {
-    const int ng = min(kGroupsPerTile, g_end - g0);
+  for (int h0 = h_begin; h0 < h_end; h0 += kHalvesPerTile) {
+    const int nh = min(kHalvesPerTile, h_end - h0);
+    const int ng = (nh - rh + 1) >> 1;  // half-groups of this tile that belong to this warp's row half: t = rh, rh + 2, ...
     float2 acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -413,9 +418,9 @@ __global__ void __launch_bounds__(kTileThreads, 1)
       const float4 *B = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(sB) + (size_t)s * kStageBBytes) +
                         (size_t)(qt * 8) * (kTileK / 4);
       if (ng == 4) sc_tile_stage<4>(A, B, sw, acc);
-      else if (ng == 3) sc_tile_stage<3>(A, B, sw, acc);  // partial last tile of the CTA's run: only its ng groups were loaded
+      else if (ng == 3) sc_tile_stage<3>(A, B, sw, acc);  // partial last tile of the CTA's run: only its half-groups were loaded
       else if (ng == 2) sc_tile_stage<2>(A, B, sw, acc);
-      else sc_tile_stage<1>(A, B, sw, acc);
+      else if (ng == 1) sc_tile_stage<1>(A, B, sw, acc);
       __syncwarp();
       if (lane == 0) sc_mbar_arrive(&empty[s]);
     }
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     }
     sc_consumer_sync();
     if (q_own < nqc) {
-      const int row0 = g0 * kGroupRows + sub * 32;
+      const int row0 = h0 * kHalfRows + sub * 32;
 #pragma unroll 4
       for (int r = 0; r < 32; r++) {
         const int row = row0 + r;
@@ -459,6 +464,254 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 #pragma unroll
     for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
   }
+}
+
+// ---- sector-cosine scan on the 5th-generation tensor cores (tcgen05.mma + TMEM): query batches --------------------
+// With a batch of queries the scan is D[rows x Q] = DB[rows x cells] * Q^T: 16 flop per DB byte at Q = 32, above the fp32
+// CUDA-core ridge — the FFMA tile kernel above tops out at a third of the HBM rate.  The tensor cores have the headroom, but
+// the top-K must still contain the exact winner, so a plain TF32 product (10-bit mantissas) is not good enough: every fp32
+// operand is split into hi (the 11 significant bits TF32 keeps, exactly) + lo (the remainder, exact in fp32) and the product is
+// formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM ("3xTF32"; the dropped lo*lo term is below 2^-22 relative).
+//   warp 0      : TMA producer — [128 rows x 32 cells] boxes of the DB (128-byte swizzle = the canonical K-major UMMA layout) and
+//                 the matching boxes of the pre-split query batch (hi and lo), kUmStages deep
+//   warps 1-4   : splitters — rewrite the landed DB box as hi in place and write lo next to it (elementwise: the swizzle does not
+//                 matter), then fence the generic-proxy writes towards the async proxy the tensor cores read through
+//   warp 5      : one lane issues 8 x tcgen05.mma.kind::tf32 per stage (per 8 cells: a_hi x [b_hi ; b_lo] with N 64, a_lo x b_hi with N 32; M 128)
+//                 into one of two TMEM accumulators,
+//                 tcgen05.commit hands the stage back to the producer and, after the last stage of a tile, the tile to the epilogue
+//   warps 6-9   : epilogue — tcgen05.ld the accumulator (thread = row, 32 columns = queries), distances -> shared [row][query],
+//                 then thread (query, row group) feeds its running top-K: same packed keys, same merge, same exact re-score.
+// The DB streams through shared memory exactly once; HBM is the bound (4,800 B per row per 32 queries).
+constexpr int kUmRows = 128;                 // UMMA M: DB rows per tile
+constexpr int kUmK = 32;                     // cells per stage = one 128-byte swizzle atom row
+constexpr int kUmN = kQChunk;                // UMMA N: queries per pass
+constexpr int kUmStages = 5;                  // 5 x 40 KB: the HBM latency needs ~44 KB of DB in flight per SM, a stage also spends time in the split and MMA phases
+constexpr int kUmABytes = kUmRows * kUmK * 4;              // 16 KB
+constexpr int kUmBBytes = kUmN * kUmK * 4;                 // 4 KB
+constexpr int kUmStageBytes = 2 * kUmABytes + 2 * kUmBBytes;  // A hi | A lo | B hi | B lo = 40 KB
+constexpr int kUmThreads = 320;
+constexpr int kUmAccCols = 2 * kUmN;          // one accumulator stage: columns [0, N) = hi*hi + lo*hi, [N, 2N) = hi*lo
+constexpr int kUmTmemCols = 2 * kUmAccCols;  // two accumulator stages (a power of two >= 32)
+constexpr size_t kUmSmemBytes = 1024 + (size_t)kUmStages * kUmStageBytes + (size_t)kUmRows * kDistStride * 4 + 32 * sizeof(uint64_t);
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ u64 um_desc(const void *smem) {
+  const uint32_t a = sc_smem_u32(smem);
+  return (u64)((a >> 4) & 0x3fffu) | ((u64)1 << 16) /* LBO: unused for swizzled K-major */ | ((u64)(1024 >> 4) << 32) /* SBO */ |
+         ((u64)1 << 46) /* descriptor version 1 (sm_100) */ | ((u64)2 << 61) /* SWIZZLE_128B */;
+}
+// instruction descriptor of kind::tf32: D fp32, A / B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t um_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kUmRows >> 4) << 24); }
+__device__ __forceinline__ void um_mma(uint32_t tmem_d, u64 adesc, u64 bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void um_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void um_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void um_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void um_epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// hi / lo split of an fp32 array: hi keeps the sign, exponent and the 10 mantissa bits TF32 has; lo = x - hi is exact
+__global__ void sc_split_tf32_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+__global__ void __launch_bounds__(kUmThreads, 1)
+    sc_scan_umma_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+                        const float *__restrict__ keys, const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
+                        const float *__restrict__ q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, int tiles_per_cta,
+                        u64 *__restrict__ scratch, int list_stride) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char *stages = base;
+  float *sD = reinterpret_cast<float *>(base + (size_t)kUmStages * kUmStageBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + kUmRows * kDistStride);
+  uint64_t *full = bars, *split = bars + kUmStages, *empty = bars + 2 * kUmStages, *tfull = bars + 3 * kUmStages, *tempty = tfull + 2;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(tempty + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = (n_rows + kUmRows - 1) / kUmRows;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(t_begin + tiles_per_cta, n_tiles);
+  const int n_chunks = (n_cells + kUmK - 1) / kUmK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kUmStages; s++) {
+      sc_mbar_init(&full[s], 1);
+      sc_mbar_init(&split[s], 4);
+      sc_mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      sc_mbar_init(&tfull[a], 1);
+      sc_mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // one warp allocates (and later frees) the tensor memory of this CTA
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sc_smem_u32(s_tmem)), "r"(kUmTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  um_fence_before();
+  __syncthreads();
+  um_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      int it = 0;
+      for (int t = t_begin; t < t_end; t++) {
+        for (int c = 0; c < n_chunks; c++, it++) {
+          const int s = it % kUmStages;
+          sc_mbar_wait(&empty[s], ((it / kUmStages) & 1) ^ 1);  // passes immediately on the first lap
+          sc_mbar_expect_tx(&full[s], kUmABytes + 2 * kUmBBytes);
+          unsigned char *st = stages + (size_t)s * kUmStageBytes;
+          sc_tma_load_2d(st, &map_db, c * kUmK, t * kUmRows, &full[s]);
+          sc_tma_load_2d(st + 2 * kUmABytes, &map_qhi, c * kUmK, 0, &full[s]);
+          sc_tma_load_2d(st + 2 * kUmABytes + kUmBBytes, &map_qlo, c * kUmK, 0, &full[s]);
+        }
+      }
+    }
+  } else if (warp >= 1 && warp <= 4) {
+    // ---- splitters: A -> (hi in place, lo next to it) ----
+    const int st_tid = tid - 32;
+    int it = 0;
+    for (int t = t_begin; t < t_end; t++) {
+      for (int c = 0; c < n_chunks; c++, it++) {
+        const int s = it % kUmStages;
+        sc_mbar_wait(&full[s], (it / kUmStages) & 1);
+        uint4 *A = reinterpret_cast<uint4 *>(stages + (size_t)s * kUmStageBytes);
+        float4 *Alo = reinterpret_cast<float4 *>(stages + (size_t)s * kUmStageBytes + kUmABytes);
+#pragma unroll
+        for (int j = 0; j < kUmABytes / 16 / 128; j++) {
+          const int i = j * 128 + st_tid;
+          const uint4 v = A[i];
+          uint4 h;
+          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+          A[i] = h;
+          Alo[i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
+                               __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor cores' async proxy
+        __syncwarp();
+        if (lane == 0) sc_mbar_arrive(&split[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer (one lane) ----
+    if (lane == 0) {
+      int it = 0, ti = 0;
+      for (int t = t_begin; t < t_end; t++, ti++) {
+        const int a = ti & 1;
+        sc_mbar_wait(&tempty[a], ((ti >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (passes at once the first two times)
+        um_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * kUmAccCols);
+        for (int c = 0; c < n_chunks; c++, it++) {
+          const int s = it % kUmStages;
+          sc_mbar_wait(&split[s], (it / kUmStages) & 1);
+          um_fence_after();
+          unsigned char *st = stages + (size_t)s * kUmStageBytes;
+          // B hi and B lo lie back to back: one N = 2 * kUmN operand [b_hi ; b_lo], so a_hi is read once for both of its products
+          const u64 a_hi = um_desc(st), a_lo = um_desc(st + kUmABytes), b_both = um_desc(st + 2 * kUmABytes);
+#pragma unroll
+          for (int k = 0; k < kUmK / 8; k++) {  // UMMA K of tf32 = 8 elements = 32 bytes: the start address advances inside the swizzle atom
+            const u64 off = (u64)(k * 32 >> 4);
+            um_mma(tmem_d, a_hi + off, b_both + off, um_idesc(2 * kUmN), (c | k) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
+            um_mma(tmem_d, a_lo + off, b_both + off, um_idesc(kUmN), 1u);                          // + lo*hi onto the first kUmN columns
+          }
+          um_commit(&empty[s]);  // arrives when the MMAs above have read the stage (implies fence::before_thread_sync)
+        }
+        um_commit(&tfull[a]);
+      }
+    }
+  } else {
+    // ---- epilogue + running top-K (warps 6-9; a warp may only touch the TMEM lanes of its quadrant = warp % 4) ----
+    const int quad = warp & 3;
+    const int e = tid - 192, q_own = e & 31, sub = e >> 5;
+    TopK top;
+    top.init();
+    int ti = 0;
+    for (int t = t_begin; t < t_end; t++, ti++) {
+      const int a = ti & 1;
+      sc_mbar_wait(&tfull[a], (ti >> 1) & 1);
+      um_fence_after();
+      uint32_t r[32], r2[32];
+      const uint32_t taddr = tmem_base + (uint32_t)(a * kUmAccCols) + ((uint32_t)(quad * 32) << 16);
+#define DSLAM_TMEM_LD32(R, ADDR)                                                                                                                      \
+  asm volatile(                                                                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, " \
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                                                    \
+      : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]), "=r"(R[10]),        \
+        "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]), "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]),          \
+        "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]),          \
+        "=r"(R[31])                                                                                                                                 \
+      : "r"(ADDR)                                                                                                                                   \
+      : "memory")
+      DSLAM_TMEM_LD32(r, taddr);
+      DSLAM_TMEM_LD32(r2, taddr + (uint32_t)kUmN);
+#undef DSLAM_TMEM_LD32
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      um_fence_before();
+      __syncwarp();
+      if (lane == 0) sc_mbar_arrive(&tempty[a]);  // the accumulator may be overwritten by the tile after next
+      float *drow = sD + (size_t)(quad * 32 + lane) * kDistStride;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 d;
+        d.x = (1.0f - (__uint_as_float(r[j]) + __uint_as_float(r2[j])) / sc_width) / 2.0f;
+        d.y = (1.0f - (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) / sc_width) / 2.0f;
+        d.z = (1.0f - (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) / sc_width) / 2.0f;
+        d.w = (1.0f - (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) / sc_width) / 2.0f;
+        *reinterpret_cast<float4 *>(drow + j) = d;
+      }
+      um_epilogue_sync();
+      if (q_own < nqc) {
+        const int row0 = t * kUmRows + sub * 32;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr++) {
+          const int row = row0 + rr;
+          if (row >= n_rows) break;
+          bool ok = __ldg(ids + row) < max_id;
+          if (ok && ringkey_thres >= 0.f) ok = flann_l2(q_keys + (size_t)q_own * key_dim, keys + (size_t)row * key_dim, key_dim) < ringkey_thres;
+          if (ok) top.insert(make_key(sD[(size_t)(sub * 32 + rr) * kDistStride + q_own], row));
+        }
+      }
+      um_epilogue_sync();
+    }
+    // CTA merge of the four row groups through the distance tile's storage: lists[sub][q][K]
+    u64 *lists = reinterpret_cast<u64 *>(sD);
+#pragma unroll
+    for (int i = 0; i < kScTopK; i++) lists[((size_t)sub * kQChunk + q_own) * kScTopK + i] = top.k[i];
+    um_epilogue_sync();
+    if (e < nqc) {
+      TopK m;
+      m.init();
+      for (int wv = 0; wv < 4; wv++) {
+#pragma unroll
+        for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + e) * kScTopK + i]);
+      }
+      u64 *dst = scratch + ((size_t)e * list_stride + blockIdx.x) * kScTopK;
+#pragma unroll
+      for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+    }
+  }
+  // ---- teardown: every role is done with the tensor memory ----
+  um_fence_before();
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kUmTmemCols) : "memory");
 }
 
 // ---- exact re-score -------------------------------------------------------------------------------------------
@@ -828,6 +1081,7 @@ static int sc_scan_flavour() {
     g_sc_scan_flavour = 0;
     if (e && !strcmp(e, "stream")) g_sc_scan_flavour = 1;
     if (e && !strcmp(e, "tile")) g_sc_scan_flavour = 2;
+    if (e && !strcmp(e, "umma")) g_sc_scan_flavour = 3;
   }
   return g_sc_scan_flavour;
 }
@@ -847,7 +1101,7 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
   const cuuint64_t gstride[1] = {(cuuint64_t)n_cells * sizeof(float)};
   {
     const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)n_rows};
-    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kGroupRows};
+    const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kHalfRows};
     if (enc(&map_db, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sigs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
@@ -859,16 +1113,50 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  const int n_groups = (n_rows + kGroupRows - 1) / kGroupRows;
-  const int groups_per_cta = (n_groups + grid - 1) / grid;
+  const int n_halves = (n_rows + kHalfRows - 1) / kHalfRows;
+  const int halves_per_cta = (n_halves + grid - 1) / grid;
   sc_scan_tile_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(map_db, map_q, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
-                                                                      max_id, sc_width, groups_per_cta, scratch, list_stride);
+                                                                      max_id, sc_width, halves_per_cta, scratch, list_stride);
+  return cudaGetLastError();
+}
+
+// tensor-core flavour: q_split = [2][nq_total][n_cells] scratch for the hi / lo halves of the query batch
+static cudaError_t launch_sc_scan_umma(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
+                                       const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
+                                       int list_stride, int grid, float *q_hi, float *q_lo, cudaStream_t stream) {
+  ScEncodeTiledFn enc = sc_encode_tiled();
+  if (!enc) return cudaErrorNotSupported;
+  cudaError_t e = cudaFuncSetAttribute(sc_scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmSmemBytes);
+  if (e != cudaSuccess) return e;
+  const size_t nq_elems = (size_t)nqc * n_cells;
+  sc_split_tf32_kernel<<<(unsigned)((nq_elems + 255) / 256), 256, 0, stream>>>(q_sigs, q_hi, q_lo, nq_elems);
+  CUtensorMap map_db, map_qhi, map_qlo;
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint64_t gstride[1] = {(cuuint64_t)n_cells * sizeof(float)};
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)n_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)kUmK, (cuuint32_t)kUmRows};
+    if (enc(&map_db, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sigs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  for (int h = 0; h < 2; h++) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)nqc};
+    const cuuint32_t box[2] = {(cuuint32_t)kUmK, (cuuint32_t)kUmN};
+    if (enc(h ? &map_qlo : &map_qhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h ? q_lo : q_hi, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  const int n_tiles = (n_rows + kUmRows - 1) / kUmRows;
+  const int tiles_per_cta = (n_tiles + grid - 1) / grid;
+  sc_scan_umma_kernel<<<grid, kUmThreads, kUmSmemBytes, stream>>>(map_db, map_qhi, map_qlo, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
+                                                                  max_id, sc_width, tiles_per_cta, scratch, list_stride);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                            const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch, int *nlists_out,
-                           cudaStream_t stream) {
+                           float *q_split, cudaStream_t stream) {
   if (n_cells % 4 != 0 || n_cells > 1280 || key_dim > 64) return cudaErrorInvalidValue;
   {  // worst case of any descriptor shape this library accepts; per device and cheap, so set on every launch
     cudaError_t e = cudaFuncSetAttribute(sc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQChunk * 1280 * 4 + kQChunk * 64 * 4);
@@ -882,19 +1170,31 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
   // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
   // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
   // (a shard smaller than one 64-row TMA box always takes the streaming kernel)
-  const bool tiles = n_rows >= 64 && (flavour == 2 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
+  // tensor-core flavour (tcgen05, 3xTF32): query batches over shards of at least two 128-row tiles per SM (1.7x the FFMA tile
+  // kernel at 100k rows); smaller shards keep the 32-row-granular FFMA tile kernel, which balances them better
+  const bool umma = q_split != nullptr && n_rows >= 128 * 2 * num_sms() && (flavour == 3 || (flavour == 0 && nq_first > 8));
+  const bool tiles = !umma && n_rows >= 64 && (flavour == 2 || flavour == 3 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
   int grid = num_sms();
-  if (tiles) {
-    const int n_groups = (n_rows + 63) / 64;
-    if (grid > n_groups) grid = n_groups;
-    const int gpc = (n_groups + grid - 1) / grid;
-    grid = (n_groups + gpc - 1) / gpc;  // no CTA without a group
+  if (umma) {
+    const int n_t = (n_rows + kUmRows - 1) / kUmRows;
+    const int tpc = (n_t + grid - 1) / grid;
+    grid = (n_t + tpc - 1) / tpc;
+  } else if (tiles) {
+    const int n_halves = (n_rows + 31) / 32;
+    if (grid > n_halves) grid = n_halves;
+    const int hpc = (n_halves + grid - 1) / grid;
+    grid = (n_halves + hpc - 1) / hpc;  // no CTA without rows
   }
   if (nlists_out) *nlists_out = grid;
   for (int q0 = 0; q0 < nq; q0 += kQChunk) {
     const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
     unsigned long long *lists = scratch + (size_t)q0 * stride * kScTopK;
-    if (tiles) {
+    if (umma) {
+      float *q_hi = q_split + (size_t)q0 * n_cells, *q_lo = q_split + ((size_t)nq + q0) * n_cells;
+      cudaError_t e = launch_sc_scan_umma(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
+                                          ringkey_thres, max_id, sc_width, lists, stride, grid, q_hi, q_lo, stream);
+      if (e != cudaSuccess) return e;
+    } else if (tiles) {
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
                                            ringkey_thres, max_id, sc_width, lists, stride, grid, stream);
       if (e != cudaSuccess) return e;

@@ -375,3 +375,32 @@ def test_ringkey_width_not_multiple_of_four(session, oracle):
     idx, _ = db.query(sig[:4])
     assert np.array_equal(idx, [0, 1, 2, 3])
     db.close()
+
+
+def test_three_scan_kernels_agree_at_full_size(session, oracle):
+    """100k descriptors (BASELINE config 4): the HBM-streaming kernel, the FFMA tile kernel and the tcgen05 tensor-core kernel
+    (3xTF32 split products, TMEM accumulators) hand the same survivors to the exact re-score: identical argmin and distance bits,
+    with and without the ring-key gate / id limit, for a full chunk, a ragged batch and several chunks; spot-checked against the
+    oracle's brute force."""
+    n = 100_000
+    sig, key = syn.make_sc_database(n, 2024)
+    db = api.ScanContextDB(session, n)
+    db.add(key, sig)
+    try:
+        for nq in (32, 11, 70):
+            qs, qk, truth = syn.make_sc_queries(sig, key, nq, 70 + nq)
+            out = {}
+            for flavour in ("stream", "tile", "umma"):
+                db.set_scan_kernel(flavour)
+                out[flavour] = db.query(qs) + db.query(qs, ringkeys=qk, ringkey_thres=0.5, max_id=n // 2)
+            for flavour in ("tile", "umma"):
+                for a, b in zip(out["stream"], out[flavour]):
+                    assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32)), (flavour, nq)
+            known = truth >= 0
+            assert np.array_equal(out["umma"][0][known], truth[known])
+            for q in range(0, nq, 9):
+                i_o, d_o = oracle.search_sc_dense(qs[q], sig)
+                assert out["umma"][0][q] == i_o and out["umma"][1][q] == np.float32(d_o)
+    finally:
+        db.set_scan_kernel("auto")
+        db.close()

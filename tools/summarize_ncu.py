@@ -102,5 +102,43 @@ if __name__ == "__main__":
         for d in sc:
             if "dram__bytes_read.sum" in d:
                 traffic.setdefault("other", {})[d["kernel"]] = [to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])]
+    # ---- round 2 captures (scratch/job_profiles.sh) --------------------------------------------------------------------------------
+    def total(d):
+        return to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+
+    if have("r02_launches.csv"):
+        import shutil
+
+        launch_list(os.path.join(g, "r02_launches.csv"), "r02 launch list: bench.py --streams 512 --steps 1 --warmup 3 (the TIMED configuration: KITTI 1232x368, "
+                    "512 streams, 8 LM groups, pyramids on the overlap stream)", os.path.join(p, "r02_launches.md"))
+        rows = [r for r in csv.reader(open(os.path.join(g, "r02_launches.csv"))) if len(r) > 10]
+        with open(os.path.join(p, "r02_launches.csv"), "w", newline="") as f:  # kernel, grid, block, ns — the raw list without host names / ids
+            wr = csv.writer(f)
+            h = rows[0]
+            wr.writerow(["kernel", "grid", "block", "gpu__time_duration_ns"])
+            for r in rows[1:]:
+                wr.writerow([short(r[h.index("Kernel Name")]), r[h.index("Grid Size")], r[h.index("Block Size")], r[h.index("Metric Value")]])
+    if have("r02_eval_bench.ncu-rep"):
+        ev = full_report(os.path.join(g, "r02_eval_bench.ncu-rep"), "r02 eval_kernel inside bench.py at the TIMED configuration (512 streams, 8 LM groups: ~64-77 items "
+                         "and ~320k template points per launch, every stream with its own pyramids)", os.path.join(p, "r02_eval_kernel_512streams.md"))
+        tr = [total(d) for d in ev if "dram__bytes_read.sum" in d]
+        if tr:
+            traffic["pose_eval_dram_bytes_per_launch"] = sum(tr) / len(tr)
+            traffic["source"] = ("profiles/r02_eval_kernel_512streams.md (mean over %d launches of the eval kernel captured inside bench.py --streams 512, "
+                                 "the timed configuration)" % len(tr))
+    if have("r02_eval128.ncu-rep"):
+        full_report(os.path.join(g, "r02_eval128.ncu-rep"), "r02 eval_kernel, 128 items of 9.9k points in one launch (tools/one_eval.py kitti 128): pose and scale flavour",
+                    os.path.join(p, "r02_eval_kernel_128items.md"))
+    if have("r02_pyramid.ncu-rep"):
+        py = full_report(os.path.join(g, "r02_pyramid.ncu-rep"), "r02 pyramid kernels inside bench.py --streams 512 (64 frames per launch)", os.path.join(p, "r02_pyramid_kernels.md"))
+        for d in py:
+            if "dram__bytes_read.sum" in d:
+                traffic.setdefault("r02", {}).setdefault(d["kernel"], []).append(total(d))
+    if have("r02_sc.ncu-rep"):
+        sc = full_report(os.path.join(g, "r02_sc.ncu-rep"), "r02 Scan-Context kernels, 100k descriptors: streaming scan (Q = 1), tile scan (Q = 32), re-score + publish",
+                         os.path.join(p, "r02_scan_context_kernels.md"))
+        for d in sc:
+            if "dram__bytes_read.sum" in d:
+                traffic.setdefault("r02", {}).setdefault(d["kernel"], []).append(total(d))
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print(json.dumps(traffic, indent=1))
