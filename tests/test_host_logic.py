@@ -156,6 +156,10 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["gpu_launches"] == 0 and d["config"]["workload"].startswith("kitti_1232x368")
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # one process per core, and the scaling against ONE process is part of the line (a throttled harness would show up here)
+    sc = d["cpu_baseline"]["per_core_scaling"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and sc["procs_1_fps"] > 0
+    assert sc["efficiency_vs_linear"] > 0.5, sc
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=120, env=env)

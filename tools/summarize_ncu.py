@@ -140,5 +140,11 @@ if __name__ == "__main__":
         for d in sc:
             if "dram__bytes_read.sum" in d:
                 traffic.setdefault("r02", {}).setdefault(d["kernel"], []).append(total(d))
+    if have("r02_sc_q1.ncu-rep"):
+        sc = full_report(os.path.join(g, "r02_sc_q1.ncu-rep"), "r02 Scan-Context kernels, 100k descriptors, ONE query: HBM-streaming scan + merge / re-score / publish",
+                         os.path.join(p, "r02_scan_context_q1.md"))
+        for d in sc:
+            if "dram__bytes_read.sum" in d:
+                traffic.setdefault("r02", {}).setdefault(d["kernel"] + " (Q=1)", []).append(total(d))
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print(json.dumps(traffic, indent=1))
