@@ -1437,6 +1437,8 @@ static int frames_build(int n, dslam_frame *const *frames, const float *B256, bo
     for (int k = 0; k < cnt; k++) {
       frames[i + k]->built = true;
       frames[i + k]->staged = stage_dIp || stage_abs;
+      frames[i + k]->staged_dIp = stage_dIp;  // which host-layout copies THIS build filled (a buffer left over from an earlier
+      frames[i + k]->staged_abs = stage_abs;  // build holds another image's data)
       frames[i + k]->async_gen = async ? s->pyr_gen + 1 : 0;
     }
     i += cnt;
@@ -1495,13 +1497,14 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
   if (!f->built) return fail(DSLAM_ESTATE, "frame pyramid has not been built");
   if (!host_dIp && !host_absgrad) return DSLAM_OK;
   const bool need_d = host_dIp != nullptr, need_a = host_absgrad != nullptr;
-  const bool have = f->staged && (!need_d || f->stage_dIp) && (!need_a || f->stage_abs);
-  if (!have) {
+  const bool have = (!need_d || f->staged_dIp) && (!need_a || f->staged_abs);
+  if (!have) {  // the requested array was not staged by the current build: unpack it from the texels
     const int ra = frame_acquire(f);
     if (ra != DSLAM_OK) return ra;
     const int rc = frame_ensure_staging(f, need_d, need_a);
     if (rc != DSLAM_OK) return rc;
-    const int rp = frame_prepare(f, nullptr, f->stage_dIp != nullptr, f->stage_abs != nullptr);
+    const bool un_d = need_d && !f->staged_dIp, un_a = need_a && !f->staged_abs;
+    const int rp = frame_prepare(f, nullptr, un_d, un_a);  // the unpack kernel writes only the arrays that are missing
     if (rp != DSLAM_OK) return rp;
     FrameBatch B;
     B.G = f->geom;
@@ -1509,6 +1512,8 @@ int dslam_frame_download(dslam_frame *f, float *const *host_dIp, float *const *h
     DSLAM_CUDA(launch_unpack(B, 1, f->s->stream));
     f->s->launches++;
     f->staged = true;
+    f->staged_dIp = f->staged_dIp || un_d;
+    f->staged_abs = f->staged_abs || un_a;
   }
   return frame_copy_out(f, host_dIp, host_absgrad);
 }

@@ -129,6 +129,7 @@ struct dslam_frame {
   float *B_dev = nullptr;      // 256-float gamma table (lazy)
   size_t px_off[dslam::kMaxLevels + 1]{};
   bool uploaded = false, built = false, staged = false;
+  bool staged_dIp = false, staged_abs = false;  // host-layout copies filled by the CURRENT build (or unpacked since)
   cudaEvent_t host_ready = nullptr;  // recorded on copy_stream after the D2H of the host mirrors
   cudaEvent_t built_ev = nullptr;    // recorded on the session stream after the kernels that fill the staging copies
   cudaStream_t copy_stream = nullptr;  // D2H of the host mirrors overlaps the tracking kernels of the session stream

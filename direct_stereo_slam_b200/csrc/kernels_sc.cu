@@ -1170,9 +1170,10 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
   // The streaming kernel is HBM-bound up to ~4 queries and costs ~18 us per further query and 100k rows; the tiled
   // kernel costs the same for 1..32 queries (FFMA-bound) and wants at least one tile per two SMs.
   // (a shard smaller than one 64-row TMA box always takes the streaming kernel)
-  // tensor-core flavour (tcgen05, 3xTF32): query batches over shards of at least two 128-row tiles per SM (1.7x the FFMA tile
-  // kernel at 100k rows); smaller shards keep the 32-row-granular FFMA tile kernel, which balances them better
-  const bool umma = q_split != nullptr && n_rows >= 128 * 2 * num_sms() && (flavour == 3 || (flavour == 0 && nq_first > 8));
+  // tensor-core flavour (tcgen05, 3xTF32): query batches over shards of >= 4096 rows (DSLAM_SC_UMMA_MIN_ROWS).  Measured against the
+  // FFMA tile kernel at Q = 32: 100k rows 0.128 vs 0.220 ms, 50k 0.077 vs 0.134, 25k 0.061 vs 0.076, 12.5k 0.042 vs 0.059, 6.25k 0.042 vs 0.054
+  static const int umma_min_rows = [] { const char *e = getenv("DSLAM_SC_UMMA_MIN_ROWS"); const int v = e ? atoi(e) : 0; return v >= 128 ? v : 4096; }();
+  const bool umma = q_split != nullptr && n_rows >= umma_min_rows && (flavour == 3 || (flavour == 0 && nq_first > 8));
   const bool tiles = !umma && n_rows >= 64 && (flavour == 2 || flavour == 3 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
   int grid = num_sms();
   if (umma) {

@@ -136,3 +136,31 @@ def test_async_build_overlaps_tracking_and_stays_ordered(session, oracle):
     assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
     f2.close()
     gc.close()
+
+
+def test_download_of_an_array_the_current_build_did_not_stage(session):
+    """A frame object is rebuilt with only ONE host-layout copy staged while the staging buffer of the other one still holds the
+    previous image: a later download of that other array must unpack the CURRENT pyramid, not hand out the stale buffer."""
+    rng = np.random.default_rng(5)
+    w, h, levels = 320, 192, 3
+    img_a = np.clip(rng.normal(128, 40, (h, w)), 0, 255).astype(np.float32)
+    img_b = np.clip(rng.normal(90, 30, (h, w)), 0, 255).astype(np.float32)
+    want = api.FrameHessian(session, w, h, levels)
+    want.makeImages(img_b)
+    f = api.FrameHessian(session, w, h, levels)
+    f.upload(img_a)
+    api.build_frames([f], stage_host=3)
+    f.download()                              # both staging buffers now hold image A
+    f.upload(img_b)
+    api.build_frames([f], stage_host=1)       # image B: only dIp staged
+    f.download()                              # dIp from the staging copy, absSquaredGrad unpacked from the texels
+    assert np.array_equal(f.dIp_all.view(np.uint32), want.dIp_all.view(np.uint32))
+    assert np.array_equal(f.absSquaredGrad_all.view(np.uint32), want.absSquaredGrad_all.view(np.uint32))
+    f.upload(img_a)
+    api.build_frames([f], stage_host=2)       # the other way round
+    f.download()
+    want.makeImages(img_a)
+    assert np.array_equal(f.dIp_all.view(np.uint32), want.dIp_all.view(np.uint32))
+    assert np.array_equal(f.absSquaredGrad_all.view(np.uint32), want.absSquaredGrad_all.view(np.uint32))
+    f.close()
+    want.close()
