@@ -335,7 +335,7 @@ struct PoseLM {
   hm::Se3 cur, cand;
   double aff_cur[2]{}, aff_cand[2]{};
   int lvl = 0, iteration = 0;
-  bool haveRepeated = false;
+  bool haveRepeated = false, last_rejected = false;
   float levelCutoffRepeat = 1, lambda = 0.01f;
   double H[64]{}, b[8]{}, inc[8]{};
   EvalOut resOld{};
@@ -367,6 +367,42 @@ struct PoseLM {
   void start_level() {
     levelCutoffRepeat = 1;
     phase = START;
+    last_rejected = false;
+  }
+  // Speculation over a run of rejected steps.  After a rejection the next candidate depends only on (H, b, cur, lambda, iteration)
+  // — not on the result that was just rejected — so the driver can ask for the candidates of the next rejections in advance and
+  // evaluate them in the SAME round; consume() then walks the results in order and stops at the first one whose request no
+  // longer matches.  simulate_reject() is consume()'s rejection branch without a result (:583-590); snap / restore undo it.
+  struct Snap {
+    float lambda;
+    int iteration;
+    double inc[8], aff_cand[2];
+    hm::Se3 cand;
+  };
+  Snap snap() const {
+    Snap sn;
+    sn.lambda = lambda; sn.iteration = iteration; sn.cand = cand;
+    std::memcpy(sn.inc, inc, sizeof(inc));
+    sn.aff_cand[0] = aff_cand[0]; sn.aff_cand[1] = aff_cand[1];
+    return sn;
+  }
+  void restore(const Snap &sn) {
+    lambda = sn.lambda; iteration = sn.iteration; cand = sn.cand;
+    std::memcpy(inc, sn.inc, sizeof(inc));
+    aff_cand[0] = sn.aff_cand[0]; aff_cand[1] = sn.aff_cand[1];
+  }
+  bool simulate_reject() {  // true: a further candidate of the same level exists (request() returns it)
+    if (phase != ITER) return false;
+    lambda *= 4;
+    if (lambda < 0.001f) lambda = 0.001f;
+    double nrm = 0;
+    for (int i = 0; i < 8; i++) nrm += inc[i] * inc[i];
+    nrm = std::sqrt(nrm);
+    if (!(nrm > 1e-3)) return false;  // the level would end here (:588)
+    if (iteration + 1 >= kMaxIterations[lvl]) return false;
+    iteration++;
+    prepare_iteration();
+    return true;
   }
   void request(EvalItem &it) const {
     const float cutoff = kCoarseCutoffTH * levelCutoffRepeat;
@@ -390,6 +426,7 @@ struct PoseLM {
     // ITER: resNew = o
     iters++;
     const bool accept = (o.res6[0] / o.res6[1]) < (resOld.res6[0] / resOld.res6[1]);  // :559
+    last_rejected = !accept;
     trace_row(trace, lvl, iteration, accept, o.n_padded, lambda, resOld.res6[0] / resOld.res6[1], o.res6[0] / o.res6[1], inc, 8);
     if (accept) {  // :576-582
       pose_normal_equations(o, H, b);
@@ -491,7 +528,7 @@ struct ScaleLM {
   enum Phase { START, ITER, DONE } phase = START;
   float scale_current = 1.f, scale_new = 1.f, inc = 0.f;
   int lvl = 0, iteration = 0;
-  bool haveRepeated = false;
+  bool haveRepeated = false, last_rejected = false;
   float levelCutoffRepeat = 1, lambda = 0.01f, H = 0.f, b = 0.f;
   EvalOut resOld{};
   float last_residuals[5]{};
@@ -508,6 +545,23 @@ struct ScaleLM {
   }
   void request(EvalItem &it) const {
     fill_scale_item(it, c, f, lvl, phase == START ? scale_current : scale_new, kCoarseCutoffTH * levelCutoffRepeat);
+  }
+  // speculation over a run of rejected steps, as in PoseLM (the rejection branch of :926-945 without a result)
+  struct Snap {
+    float lambda, inc, scale_new;
+    int iteration;
+  };
+  Snap snap() const { return Snap{lambda, inc, scale_new, iteration}; }
+  void restore(const Snap &sn) { lambda = sn.lambda; inc = sn.inc; scale_new = sn.scale_new; iteration = sn.iteration; }
+  bool simulate_reject() {
+    if (phase != ITER) return false;
+    lambda *= 4;
+    if (lambda < 0.001f) lambda = 0.001f;
+    if (!(inc > 1e-3)) return false;  // :937: the level would end here
+    if (iteration + 1 >= kMaxIterations[lvl]) return false;
+    iteration++;
+    prepare_iteration();
+    return true;
   }
   void consume(const EvalOut &o) {
     if (phase == START) {
@@ -526,6 +580,7 @@ struct ScaleLM {
     }
     iters++;
     const bool accept = (o.res6[0] / o.res6[1]) < (resOld.res6[0] / resOld.res6[1]);  // :915
+    last_rejected = !accept;
     const double t[2] = {inc, scale_new};
     trace_row(trace, lvl, iteration, accept, o.n_padded, lambda, resOld.res6[0] / resOld.res6[1], o.res6[0] / o.res6[1], t, 2);
     if (accept) {  // :926-936
@@ -570,6 +625,7 @@ struct ScaleLM {
     if (lvl >= 0) {
       levelCutoffRepeat = 1;
       phase = START;
+      last_rejected = false;
       return;
     }
     phase = DONE;
@@ -708,7 +764,7 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
     std::vector<int> members;  // >= 0: pose machine index, < 0: ~index of a scale machine
     int rc = DSLAM_OK;
     std::string err;
-    long long evals = 0, launches = 0;
+    long long evals = 0, launches = 0, spec_used = 0;
   } grp[G];
   {
     int k = 0;
@@ -763,6 +819,7 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
     Group &gr = grp[g];
     struct Lane {
       std::vector<int> members, who;
+      std::vector<unsigned char> spec;  // per item: 0 = the machine's next evaluation, d > 0 = its candidate after d further rejections
       std::vector<EvalItem> items;
       std::vector<EvalOut> outs;
       unsigned seq = 0;
@@ -785,17 +842,50 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
       const long long t0 = now_ns();
       L.items.clear();
       L.who.clear();
+      L.spec.clear();
+      size_t cap = (size_t)(nl == 2 ? slots_per_half : slots_per_group);  // result slots of this lane
+      if (use_server && cap > (size_t)kMaxItemsPerLaunch) cap = kMaxItemsPerLaunch;
+      const int depth = s->lm_spec_depth;
+      size_t todo = L.members.size();  // members that still need their (mandatory) next evaluation in this round
       for (int m : L.members) {
+        todo--;
         if (m >= 0) {
-          if (pose[m].phase == PoseLM::DONE) continue;
+          PoseLM &M = pose[m];
+          if (M.phase == PoseLM::DONE) continue;
           L.items.emplace_back();
-          pose[m].request(L.items.back());
+          M.request(L.items.back());
+          L.who.push_back(m);
+          L.spec.push_back(0);
+          const int dm = (M.phase == PoseLM::ITER && M.last_rejected) ? depth : 1;
+          if (dm > 1) {  // inside a run of rejections: evaluate its next candidates too
+            const PoseLM::Snap sn = M.snap();
+            for (int d = 1; d < dm && L.items.size() + todo < cap && M.simulate_reject(); d++) {
+              L.items.emplace_back();
+              M.request(L.items.back());
+              L.who.push_back(m);
+              L.spec.push_back((unsigned char)d);
+            }
+            M.restore(sn);
+          }
         } else {
-          if (scale[~m].phase == ScaleLM::DONE) continue;
+          ScaleLM &M = scale[~m];
+          if (M.phase == ScaleLM::DONE) continue;
           L.items.emplace_back();
-          scale[~m].request(L.items.back());
+          M.request(L.items.back());
+          L.who.push_back(m);
+          L.spec.push_back(0);
+          const int dm = (M.phase == ScaleLM::ITER && M.last_rejected) ? depth : 1;
+          if (dm > 1) {
+            const ScaleLM::Snap sn = M.snap();
+            for (int d = 1; d < dm && L.items.size() + todo < cap && M.simulate_reject(); d++) {
+              L.items.emplace_back();
+              M.request(L.items.back());
+              L.who.push_back(m);
+              L.spec.push_back((unsigned char)d);
+            }
+            M.restore(sn);
+          }
         }
-        L.who.push_back(m);
       }
       const long long t1 = now_ns();
       t_prep += t1 - t0;
@@ -820,9 +910,34 @@ int run_lock_step(dslam_session *s, std::vector<PoseLM> &pose, std::vector<Scale
       const long long t3 = now_ns();
       t_wait += t3 - t2;
       gr.evals += (long long)L.items.size();
+      // A speculative result is consumed only if, after the results before it, the machine asks for exactly that evaluation
+      // (same item up to the launch-layout fields): the sequence of evaluations a machine SEES is the sequential one.
+      auto same_request = [](const EvalItem &a, const EvalItem &b) { return std::memcmp(&a, &b, offsetof(EvalItem, nblocks)) == 0; };
+      bool chain_ok = true;
       for (size_t k = 0; k < L.who.size(); k++) {
-        if (L.who[k] >= 0) pose[L.who[k]].consume(L.outs[k]);
-        else scale[~L.who[k]].consume(L.outs[k]);
+        const int m = L.who[k];
+        if (L.spec[k] == 0) {
+          chain_ok = true;
+        } else {
+          if (!chain_ok) continue;
+          EvalItem want;
+          std::memset(&want, 0, sizeof(want));
+          bool live;
+          if (m >= 0) {
+            live = pose[m].phase == PoseLM::ITER && pose[m].last_rejected;
+            if (live) pose[m].request(want);
+          } else {
+            live = scale[~m].phase == ScaleLM::ITER && scale[~m].last_rejected;
+            if (live) scale[~m].request(want);
+          }
+          if (!live || !same_request(want, L.items[k])) {
+            chain_ok = false;
+            continue;
+          }
+          gr.spec_used++;
+        }
+        if (m >= 0) pose[m].consume(L.outs[k]);
+        else scale[~m].consume(L.outs[k]);
       }
       t_prep += now_ns() - t3;
     };
@@ -987,6 +1102,10 @@ int dslam_session_create(int device, dslam_session **out) {
   if (const char *e = getenv("DSLAM_LM_GROUPS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= dslam_session::kLmGroups) s->lm_groups = v;
+  }
+  if (const char *e = getenv("DSLAM_LM_SPEC")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) s->lm_spec_depth = v;
   }
   if (const char *e = getenv("DSLAM_LM_SERVER")) s->srv_enabled = atoi(e) != 0;
   if (const char *e = getenv("DSLAM_LM_SERVER_CTAS")) {

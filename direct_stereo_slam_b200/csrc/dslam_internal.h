@@ -76,6 +76,12 @@ struct dslam_session {
   dslam::EvalScratch lm_scratch2[kLmGroups] = {};
   cudaEvent_t lm_done2[kLmGroups] = {};
   int lm_halves = 2;
+  // Speculation depth over runs of rejected LM steps (DSLAM_LM_SPEC, 1 = off): after a rejection the next candidates depend only on
+  // (H, b, lambda), so up to lm_spec_depth - 1 of them are evaluated in the same round; every machine still consumes exactly the
+  // sequential sequence of evaluations (exact replay), a round trip is saved per rejection of a run.
+  int lm_spec_depth = 4;
+  // (Anticipating the FIRST rejection of a run as well — one extra candidate next to every ordinary step — was measured and does
+  // not reduce the round count further: a run of r rejections needs 1 + ceil((r-1)/depth) rounds either way.)
   cudaEvent_t lm_fork = nullptr;
   struct Worker {
     std::thread th;

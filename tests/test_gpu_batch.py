@@ -115,3 +115,41 @@ def test_resident_server_equals_launch_per_round(oracle, monkeypatch):
     for x, y in zip(a[7], b[7]):
         assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True)
     assert a[8] == 1 and b[8] > 10, "server: one launch per LM call; launch path: one per round (%d / %d)" % (a[8], b[8])
+
+
+def test_speculation_over_rejection_runs_saves_round_trips(oracle, monkeypatch):
+    """After a rejected LM step the next candidate depends only on (H, b, lambda): the driver evaluates the candidates of the next
+    rejections of a run in the same round (DSLAM_LM_SPEC, default depth 4).  The machine still consumes exactly the sequential
+    sequence of evaluations — the trace equals the oracle's and the one without speculation — in fewer host round trips."""
+    from helpers import GpuCase, OracleCase
+    from test_gpu_tracker import _compare_traces
+
+    oc = OracleCase(oracle, "kitti", 1000, scale_error=1.1)
+    from direct_stereo_slam_b200 import synthetic as syn
+    init = syn.pose7(*syn.se3_exp_mat(oc.case["xi_true"] * 0.9))
+    ok_o, pose_o, aff_o, last_o, _ = oc.trk.track_newest_coarse(1, init, (0, 0), oc.levels - 1)
+    to = oc.trk.trace()
+    assert int(((to[:, 1] >= 0) & (to[:, 2] == 0)).sum()) >= 4, "the scene is expected to produce a run of rejected steps"
+    rmse_o, s_o = oc.trk.optimize_scale(1, 1.0, oc.levels - 1)
+    ts_o = oc.trk.trace()
+    got = {}
+    for depth in ("1", "4"):
+        monkeypatch.setenv("DSLAM_LM_SPEC", depth)
+        s = api.Session(0)
+        gc = GpuCase(s, oc, template="device")
+        l0 = s.launch_count()
+        ok, pose, aff, last = gc.trk.trackNewestCoarse(gc.f_new, init, (0, 0), oc.levels - 1)
+        n_track = s.launch_count() - l0
+        tg = gc.trk.trace()
+        l0 = s.launch_count()
+        rmse, sc = gc.trk.optimizeScale(gc.f_right, 1.0, oc.levels - 1)
+        n_scale = s.launch_count() - l0
+        tsg = gc.trk.trace()
+        assert ok == ok_o and _compare_traces(tg, to, 8) < 1e-5 and rel_err(pose, pose_o) < 1e-8
+        assert tsg.shape == ts_o.shape and np.array_equal(tsg[:, :4], ts_o[:, :4]) and abs(sc - s_o) <= 1e-6 * abs(s_o)
+        got[depth] = (n_track, n_scale, tg, tsg)
+        gc.close()
+        s.close()
+    assert np.array_equal(got["1"][2][:, :4], got["4"][2][:, :4]) and np.allclose(got["1"][2], got["4"][2], rtol=1e-12, atol=0, equal_nan=True)
+    assert got["4"][0] < got["1"][0] and got["4"][1] < got["1"][1], (got["1"][:2], got["4"][:2])
+    print("launches track / scale: no speculation %d / %d, depth 4: %d / %d" % (got["1"][0], got["1"][1], got["4"][0], got["4"][1]))
