@@ -179,9 +179,10 @@ cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int
 // query); the re-score kernel merges them.  ids must ascend with the row so that ties still resolve to the lowest id.
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim,
                            const float *q_sigs, const float *q_keys, int nq, float ringkey_thres, int max_id, float sc_width,
-                           unsigned long long *scratch, int *nlists_out, float *q_split /* [2][nq][n_cells] or null */, cudaStream_t stream);
+                           unsigned long long *scratch, int *nlists_out, float *q_split /* sc_qsplit_floats(nq, n_cells) floats, or null */, cudaStream_t stream);
 int sc_list_stride();
 size_t sc_scratch_bytes(int nq);
+size_t sc_qsplit_floats(int cap, int n_cells);  // scratch of the tensor-core scan for batches of up to cap queries
 // scan kernel selection: 0 = by batch size (default; DSLAM_SC_SCAN=stream|tile|umma overrides), 1 = streaming, 2 = tiled, 3 = tcgen05 (3xTF32)
 void sc_set_scan_flavour(int flavour);
 // ScanContext::generate on the device: moments (mean[3], cov[6]) of an n x 3 fp64 cloud; then binning + normalisation

@@ -141,7 +141,7 @@ int ensure_query_buffers(dslam_scdb *db, int nq) {
     const int cap = std::max(32, nq);
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs, (size_t)cap * db->n_cells * sizeof(float)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_qkeys, (size_t)cap * db->n_rings * sizeof(float)));
-    DSLAM_CUDA(cudaMalloc((void **)&db->d_qsplit, (size_t)2 * cap * db->n_cells * sizeof(float)));
+    DSLAM_CUDA(cudaMalloc((void **)&db->d_qsplit, dslam::sc_qsplit_floats(cap, db->n_cells) * sizeof(float)));
     if (db->fp64) DSLAM_CUDA(cudaMalloc((void **)&db->d_qsigs64, (size_t)cap * db->n_cells * sizeof(double)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_topk, (size_t)cap * kScTopK * sizeof(u64)));
     DSLAM_CUDA(cudaMalloc((void **)&db->d_exact, (size_t)cap * kScTopK * sizeof(u64)));

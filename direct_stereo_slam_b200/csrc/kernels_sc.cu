@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(kScanThreads) sc_scan_kernel(const float *__re
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < nqc * n_cells / 4; i += kScanThreads)
     reinterpret_cast<float4 *>(qs)[i] = __ldg(reinterpret_cast<const float4 *>(q_sigs) + i);
-  for (int i = tid; i < nqc * key_dim; i += kScanThreads) qk[i] = q_keys[i];
+  if (ringkey_thres >= 0.f)  // without the ring-key gate the caller need not have uploaded query keys
+    for (int i = tid; i < nqc * key_dim; i += kScanThreads) qk[i] = q_keys[i];
   __syncthreads();
 
   const int n4 = n_cells / 4;  // float4 per row (300)
@@ -308,6 +309,12 @@ __device__ __forceinline__ void sc_tma_load_2d(void *dst, const CUtensorMap *map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    sc_smem_u32(dst)),
                "l"(map), "r"(c0), "r"(c1), "r"(sc_smem_u32(bar))
+               : "memory");
+}
+// plain (1-D) bulk copy global -> shared, completion on an mbarrier: 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void sc_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sc_smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(sc_smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void sc_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); }
@@ -484,15 +491,21 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // The DB streams through shared memory exactly once; HBM is the bound (4,800 B per row per 32 queries).
 constexpr int kUmRows = 128;                 // UMMA M: DB rows per tile
 constexpr int kUmK = 32;                     // cells per stage = one 128-byte swizzle atom row
-constexpr int kUmN = kQChunk;                // UMMA N: queries per pass
-constexpr int kUmStages = 5;                  // 5 x 40 KB: the HBM latency needs ~44 KB of DB in flight per SM, a stage also spends time in the split and MMA phases
 constexpr int kUmABytes = kUmRows * kUmK * 4;              // 16 KB
-constexpr int kUmBBytes = kUmN * kUmK * 4;                 // 4 KB
-constexpr int kUmStageBytes = 2 * kUmABytes + 2 * kUmBBytes;  // A hi | A lo | B hi | B lo = 40 KB
 constexpr int kUmThreads = 320;
-constexpr int kUmAccCols = 2 * kUmN;          // one accumulator stage: columns [0, N) = hi*hi + lo*hi, [N, 2N) = hi*lo
-constexpr int kUmTmemCols = 2 * kUmAccCols;  // two accumulator stages (a power of two >= 32)
-constexpr size_t kUmSmemBytes = 1024 + (size_t)kUmStages * kUmStageBytes + (size_t)kUmRows * kDistStride * 4 + 32 * sizeof(uint64_t);
+// Queries per pass NQ = UMMA N of the lo*hi product (the [hi*hi | hi*lo] product runs at N = 2 NQ <= 256).  A pass streams the DB
+// once, so a larger NQ divides the HBM traffic per query: 32 (5 stages of 40 KB), 64 (4 x 48 KB) or 128 (3 x 64 KB; the pass is then
+// bound by the tensor pipe and by the query tiles re-read from L2 for every DB tile, not by HBM).
+template <int NQ>
+struct UmCfg {
+  static_assert(NQ == 32 || NQ == 64 || NQ == 128, "queries per pass");
+  static constexpr int kStages = NQ == 32 ? 5 : (NQ == 64 ? 4 : 3);
+  static constexpr int kBBytes = NQ * kUmK * 4;                    // 4 / 8 / 16 KB
+  static constexpr int kStageBytes = 2 * kUmABytes + 2 * kBBytes;  // A hi | A lo | B hi | B lo
+  static constexpr int kAccCols = 2 * NQ;       // one accumulator stage: columns [0, NQ) = hi*hi + lo*hi, [NQ, 2 NQ) = hi*lo
+  static constexpr int kTmemCols = 2 * kAccCols;  // two accumulator stages: 128 / 256 / 512 columns (a power of two >= 32)
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + (size_t)kUmRows * kDistStride * 4 + 32 * sizeof(uint64_t);
+};
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ u64 um_desc(const void *smem) {
@@ -519,21 +532,32 @@ __device__ __forceinline__ void um_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void um_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void um_epilogue_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-// hi / lo split of an fp32 array: hi keeps the sign, exponent and the 10 mantissa bits TF32 has; lo = x - hi is exact
-__global__ void sc_split_tf32_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, size_t n) {
+// hi / lo split of the query batch of one pass, written as the tensor cores want to read it: hi keeps the sign, exponent and the
+// 10 mantissa bits TF32 has, lo = x - hi is exact.  out[chunk][hi | lo][NQ rows][32 cells] — every [NQ][32] block is one K-major
+// SWIZZLE_128B operand tile (row = 128 bytes, the 16-byte unit index XOR-ed with row % 8, exactly what a TMA box load with
+// CU_TENSOR_MAP_SWIZZLE_128B would leave in shared memory), hi and lo of a chunk back to back: ONE contiguous bulk copy per
+// pipeline stage instead of 2 NQ separate 128-byte row segments (the TMA unit moves a box row by row; at ~7 clocks per
+// segment the query boxes, not HBM, bounded the first version of this kernel).  Queries >= nqc and cells >= n_cells are zero.
+__global__ void sc_split_tf32_tiled_kernel(const float *__restrict__ q, int nqc, int n_cells, int nq_pass, int n_chunks, float *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = x[i];
+  if (i >= (size_t)n_chunks * nq_pass * kUmK) return;
+  const int k = (int)(i % kUmK), row = (int)((i / kUmK) % nq_pass), c = (int)(i / ((size_t)kUmK * nq_pass));
+  const int cell = c * kUmK + k;
+  const float v = (row < nqc && cell < n_cells) ? q[(size_t)row * n_cells + cell] : 0.f;
   const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  hi[i] = h;
-  lo[i] = v - h;
+  const size_t tile = (size_t)nq_pass * kUmK;
+  const size_t at = (size_t)c * 2 * tile + (size_t)row * kUmK + (size_t)((((k >> 2) ^ (row & 7)) << 2) | (k & 3));
+  out[at] = h;
+  out[at + tile] = v - h;
 }
-
+template <int NQ>
 __global__ void __launch_bounds__(kUmThreads, 1)
-    sc_scan_umma_kernel(const __grid_constant__ CUtensorMap map_db, const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+    sc_scan_umma_kernel(const __grid_constant__ CUtensorMap map_db, const float *__restrict__ q_tiles /* sc_split_tf32_tiled_kernel's output */,
                         const float *__restrict__ keys, const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
                         const float *__restrict__ q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, int tiles_per_cta,
                         u64 *__restrict__ scratch, int list_stride) {
+  using C = UmCfg<NQ>;
+  constexpr int kUmStages = C::kStages, kUmBBytes = C::kBBytes, kUmStageBytes = C::kStageBytes, kUmAccCols = C::kAccCols, kUmTmemCols = C::kTmemCols;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((1024u - (sc_smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char *stages = base;
@@ -580,8 +604,7 @@ __global__ void __launch_bounds__(kUmThreads, 1)
           sc_mbar_expect_tx(&full[s], kUmABytes + 2 * kUmBBytes);
           unsigned char *st = stages + (size_t)s * kUmStageBytes;
           sc_tma_load_2d(st, &map_db, c * kUmK, t * kUmRows, &full[s]);
-          sc_tma_load_2d(st + 2 * kUmABytes, &map_qhi, c * kUmK, 0, &full[s]);
-          sc_tma_load_2d(st + 2 * kUmABytes + kUmBBytes, &map_qlo, c * kUmK, 0, &full[s]);
+          sc_bulk_load(st + 2 * kUmABytes, q_tiles + (size_t)c * (2 * kUmBBytes / 4), 2 * kUmBBytes, &full[s]);  // [b_hi ; b_lo] of this chunk
         }
       }
     }
@@ -595,15 +618,19 @@ __global__ void __launch_bounds__(kUmThreads, 1)
         sc_mbar_wait(&full[s], (it / kUmStages) & 1);
         uint4 *A = reinterpret_cast<uint4 *>(stages + (size_t)s * kUmStageBytes);
         float4 *Alo = reinterpret_cast<float4 *>(stages + (size_t)s * kUmStageBytes + kUmABytes);
+        // all loads of the thread first (8 x 16 B in flight: one shared-memory latency per stage, not eight), then the stores
+        constexpr int kPer = kUmABytes / 16 / 128;
+        uint4 v[kPer];
 #pragma unroll
-        for (int j = 0; j < kUmABytes / 16 / 128; j++) {
+        for (int j = 0; j < kPer; j++) v[j] = A[j * 128 + st_tid];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
           const int i = j * 128 + st_tid;
-          const uint4 v = A[i];
           uint4 h;
-          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+          h.x = v[j].x & 0xffffe000u; h.y = v[j].y & 0xffffe000u; h.z = v[j].z & 0xffffe000u; h.w = v[j].w & 0xffffe000u;
           A[i] = h;
-          Alo[i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
-                               __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
+          Alo[i] = make_float4(__uint_as_float(v[j].x) - __uint_as_float(h.x), __uint_as_float(v[j].y) - __uint_as_float(h.y),
+                               __uint_as_float(v[j].z) - __uint_as_float(h.z), __uint_as_float(v[j].w) - __uint_as_float(h.w));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor cores' async proxy
         __syncwarp();
@@ -624,13 +651,13 @@ __global__ void __launch_bounds__(kUmThreads, 1)
           sc_mbar_wait(&split[s], (it / kUmStages) & 1);
           um_fence_after();
           unsigned char *st = stages + (size_t)s * kUmStageBytes;
-          // B hi and B lo lie back to back: one N = 2 * kUmN operand [b_hi ; b_lo], so a_hi is read once for both of its products
+          // B hi and B lo lie back to back: one N = 2 * NQ operand [b_hi ; b_lo], so a_hi is read once for both of its products
           const u64 a_hi = um_desc(st), a_lo = um_desc(st + kUmABytes), b_both = um_desc(st + 2 * kUmABytes);
 #pragma unroll
           for (int k = 0; k < kUmK / 8; k++) {  // UMMA K of tf32 = 8 elements = 32 bytes: the start address advances inside the swizzle atom
             const u64 off = (u64)(k * 32 >> 4);
-            um_mma(tmem_d, a_hi + off, b_both + off, um_idesc(2 * kUmN), (c | k) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
-            um_mma(tmem_d, a_lo + off, b_both + off, um_idesc(kUmN), 1u);                          // + lo*hi onto the first kUmN columns
+            um_mma(tmem_d, a_hi + off, b_both + off, um_idesc(2 * NQ), (c | k) != 0 ? 1u : 0u);  // [hi*hi | hi*lo]
+            um_mma(tmem_d, a_lo + off, b_both + off, um_idesc(NQ), 1u);                              // + lo*hi onto the first NQ columns
           }
           um_commit(&empty[s]);  // arrives when the MMAs above have read the stage (implies fence::before_thread_sync)
         }
@@ -639,16 +666,27 @@ __global__ void __launch_bounds__(kUmThreads, 1)
     }
   } else {
     // ---- epilogue + running top-K (warps 6-9; a warp may only touch the TMEM lanes of its quadrant = warp % 4) ----
+    // The accumulator is drained in chunks of 32 queries through the [128 rows][32 queries] distance tile; thread (query, row group)
+    // keeps one running top-K per chunk.
+    constexpr int kChunks = NQ / kQChunk;
     const int quad = warp & 3;
     const int e = tid - 192, q_own = e & 31, sub = e >> 5;
-    TopK top;
-    top.init();
+    TopK top[kChunks];
+#pragma unroll
+    for (int cq = 0; cq < kChunks; cq++) top[cq].init();
+    // The approximate distance only ranks candidates for the exact re-score: one multiplication by the reciprocal instead of the
+    // IEEE division of the reference formula (the divisions alone kept the XU pipe 36 % busy and this warp-starved role was the
+    // critical path of the kernel: profiles/r02_sc_umma_kernel.md).
+    const float inv_w = 1.0f / sc_width;
     int ti = 0;
     for (int t = t_begin; t < t_end; t++, ti++) {
       const int a = ti & 1;
+      // which of this warp's 32 rows exist and pass the id limit: one coalesced load per tile instead of one dependent load per row and chunk
+      const int row0 = t * kUmRows + sub * 32;
+      const bool row_ok = row0 + lane < n_rows && __ldg(ids + row0 + lane) < max_id;
+      const unsigned vmask = __ballot_sync(0xffffffffu, row_ok);
       sc_mbar_wait(&tfull[a], (ti >> 1) & 1);
       um_fence_after();
-      uint32_t r[32], r2[32];
       const uint32_t taddr = tmem_base + (uint32_t)(a * kUmAccCols) + ((uint32_t)(quad * 32) << 16);
 #define DSLAM_TMEM_LD32(R, ADDR)                                                                                                                      \
   asm volatile(                                                                                                                                       \
@@ -660,52 +698,69 @@ __global__ void __launch_bounds__(kUmThreads, 1)
         "=r"(R[31])                                                                                                                                 \
       : "r"(ADDR)                                                                                                                                   \
       : "memory")
-      DSLAM_TMEM_LD32(r, taddr);
-      DSLAM_TMEM_LD32(r2, taddr + (uint32_t)kUmN);
-#undef DSLAM_TMEM_LD32
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      um_fence_before();
-      __syncwarp();
-      if (lane == 0) sc_mbar_arrive(&tempty[a]);  // the accumulator may be overwritten by the tile after next
-      float *drow = sD + (size_t)(quad * 32 + lane) * kDistStride;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 d;
-        d.x = (1.0f - (__uint_as_float(r[j]) + __uint_as_float(r2[j])) / sc_width) / 2.0f;
-        d.y = (1.0f - (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) / sc_width) / 2.0f;
-        d.z = (1.0f - (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) / sc_width) / 2.0f;
-        d.w = (1.0f - (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) / sc_width) / 2.0f;
-        *reinterpret_cast<float4 *>(drow + j) = d;
-      }
-      um_epilogue_sync();
-      if (q_own < nqc) {
-        const int row0 = t * kUmRows + sub * 32;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; rr++) {
-          const int row = row0 + rr;
-          if (row >= n_rows) break;
-          bool ok = __ldg(ids + row) < max_id;
-          if (ok && ringkey_thres >= 0.f) ok = flann_l2(q_keys + (size_t)q_own * key_dim, keys + (size_t)row * key_dim, key_dim) < ringkey_thres;
-          if (ok) top.insert(make_key(sD[(size_t)(sub * 32 + rr) * kDistStride + q_own], row));
+      for (int cq = 0; cq < kChunks; cq++) {
+        uint32_t r[32], r2[32];
+        DSLAM_TMEM_LD32(r, taddr + (uint32_t)(cq * kQChunk));
+        DSLAM_TMEM_LD32(r2, taddr + (uint32_t)(NQ + cq * kQChunk));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cq == kChunks - 1) {
+          um_fence_before();
+          __syncwarp();
+          if (lane == 0) sc_mbar_arrive(&tempty[a]);  // the accumulator may be overwritten by the tile after next
         }
+        float *drow = sD + (size_t)(quad * 32 + lane) * kDistStride;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 d;
+          d.x = (1.0f - (__uint_as_float(r[j]) + __uint_as_float(r2[j])) * inv_w) * 0.5f;
+          d.y = (1.0f - (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) * inv_w) * 0.5f;
+          d.z = (1.0f - (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) * inv_w) * 0.5f;
+          d.w = (1.0f - (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) * inv_w) * 0.5f;
+          *reinterpret_cast<float4 *>(drow + j) = d;
+        }
+        um_epilogue_sync();
+        const int q = cq * kQChunk + q_own;
+        if (q < nqc) {
+          for (int r8 = 0; r8 < 32; r8 += 8) {
+            float dv[8];  // independent shared-memory loads first, the serial top-K chain after them
+#pragma unroll
+            for (int j = 0; j < 8; j++) dv[j] = sD[(size_t)(sub * 32 + r8 + j) * kDistStride + q_own];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              if ((vmask >> (r8 + j)) & 1u) {
+                const int row = row0 + r8 + j;
+                bool ok = true;
+                if (ringkey_thres >= 0.f) ok = flann_l2(q_keys + (size_t)q * key_dim, keys + (size_t)row * key_dim, key_dim) < ringkey_thres;
+                if (ok) top[cq].insert(make_key(dv[j], row));
+              }
+            }
+          }
+        }
+        um_epilogue_sync();
       }
-      um_epilogue_sync();
+#undef DSLAM_TMEM_LD32
     }
-    // CTA merge of the four row groups through the distance tile's storage: lists[sub][q][K]
+    // CTA merge of the four row groups through the distance tile's storage, one chunk of queries at a time: lists[sub][q][K]
     u64 *lists = reinterpret_cast<u64 *>(sD);
 #pragma unroll
-    for (int i = 0; i < kScTopK; i++) lists[((size_t)sub * kQChunk + q_own) * kScTopK + i] = top.k[i];
-    um_epilogue_sync();
-    if (e < nqc) {
-      TopK m;
-      m.init();
-      for (int wv = 0; wv < 4; wv++) {
+    for (int cq = 0; cq < kChunks; cq++) {
 #pragma unroll
-        for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + e) * kScTopK + i]);
+      for (int i = 0; i < kScTopK; i++) lists[((size_t)sub * kQChunk + q_own) * kScTopK + i] = top[cq].k[i];
+      um_epilogue_sync();
+      const int q = cq * kQChunk + e;
+      if (e < kQChunk && q < nqc) {
+        TopK m;
+        m.init();
+        for (int wv = 0; wv < 4; wv++) {
+#pragma unroll
+          for (int i = 0; i < kScTopK; i++) m.insert(lists[((size_t)wv * kQChunk + e) * kScTopK + i]);
+        }
+        u64 *dst = scratch + ((size_t)q * list_stride + blockIdx.x) * kScTopK;
+#pragma unroll
+        for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
       }
-      u64 *dst = scratch + ((size_t)e * list_stride + blockIdx.x) * kScTopK;
-#pragma unroll
-      for (int i = 0; i < kScTopK; i++) dst[i] = m.k[i];
+      um_epilogue_sync();
     }
   }
   // ---- teardown: every role is done with the tensor memory ----
@@ -1045,6 +1100,9 @@ constexpr int kRingGridX = 64;
 
 // per-CTA top-K lists of every query of a batch: lists[q][sc_list_stride()][K]
 int sc_list_stride() { return num_sms() > kRingGridX ? num_sms() : kRingGridX; }
+// floats of the split-query scratch for batches of up to `cap` queries: every pass holds at most max(2 nqc, 128) rows of
+// ceil(n_cells / 32) * 32 cells, hi and lo
+size_t sc_qsplit_floats(int cap, int n_cells) { return (size_t)2 * ((size_t)2 * cap + 128) * (size_t)((n_cells + kUmK - 1) / kUmK) * kUmK; }
 size_t sc_scratch_bytes(int nq) { return (size_t)(nq > kQChunk ? nq : kQChunk) * sc_list_stride() * kScTopK * sizeof(u64); }
 
 cudaError_t launch_sc_ringkey(const float *keys, const int *ids, int n_rows, int dim, const float *queries, int nq, int max_id,
@@ -1120,17 +1178,19 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
   return cudaGetLastError();
 }
 
-// tensor-core flavour: q_split = [2][nq_total][n_cells] scratch for the hi / lo halves of the query batch
+// tensor-core flavour: q_tiles = this pass's slice of the split-query scratch (sc_qsplit_floats)
+template <int NQ>
 static cudaError_t launch_sc_scan_umma(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                                        const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
-                                       int list_stride, int grid, float *q_hi, float *q_lo, cudaStream_t stream) {
+                                       int list_stride, int grid, float *q_tiles, cudaStream_t stream) {
   ScEncodeTiledFn enc = sc_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(sc_scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(sc_scan_umma_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmCfg<NQ>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  const size_t nq_elems = (size_t)nqc * n_cells;
-  sc_split_tf32_kernel<<<(unsigned)((nq_elems + 255) / 256), 256, 0, stream>>>(q_sigs, q_hi, q_lo, nq_elems);
-  CUtensorMap map_db, map_qhi, map_qlo;
+  const int n_chunks = (n_cells + kUmK - 1) / kUmK;
+  const size_t nq_elems = (size_t)n_chunks * NQ * kUmK;
+  sc_split_tf32_tiled_kernel<<<(unsigned)((nq_elems + 255) / 256), 256, 0, stream>>>(q_sigs, nqc, n_cells, NQ, n_chunks, q_tiles);
+  CUtensorMap map_db;
   const cuuint32_t estr[2] = {1, 1};
   const cuuint64_t gstride[1] = {(cuuint64_t)n_cells * sizeof(float)};
   {
@@ -1140,18 +1200,17 @@ static cudaError_t launch_sc_scan_umma(const float *sigs, const float *keys, con
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  for (int h = 0; h < 2; h++) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)n_cells, (cuuint64_t)nqc};
-    const cuuint32_t box[2] = {(cuuint32_t)kUmK, (cuuint32_t)kUmN};
-    if (enc(h ? &map_qlo : &map_qhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h ? q_lo : q_hi, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
-  }
   const int n_tiles = (n_rows + kUmRows - 1) / kUmRows;
   const int tiles_per_cta = (n_tiles + grid - 1) / grid;
-  sc_scan_umma_kernel<<<grid, kUmThreads, kUmSmemBytes, stream>>>(map_db, map_qhi, map_qlo, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc, ringkey_thres,
-                                                                  max_id, sc_width, tiles_per_cta, scratch, list_stride);
+  sc_scan_umma_kernel<NQ><<<grid, kUmThreads, UmCfg<NQ>::kSmemBytes, stream>>>(map_db, q_tiles, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc,
+                                                                               ringkey_thres, max_id, sc_width, tiles_per_cta, scratch, list_stride);
   return cudaGetLastError();
+}
+
+// queries per pass of the tensor-core scan: 0 = by batch size (DSLAM_SC_UMMA_NQ=32|64|128 pins it: tests / sweeps)
+static int sc_umma_nq_override() {
+  static const int v = [] { const char *e = getenv("DSLAM_SC_UMMA_NQ"); const int x = e ? atoi(e) : 0; return (x == 32 || x == 64 || x == 128) ? x : 0; }();
+  return v;
 }
 
 cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
@@ -1187,13 +1246,26 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
     grid = (n_halves + hpc - 1) / hpc;  // no CTA without rows
   }
   if (nlists_out) *nlists_out = grid;
-  for (int q0 = 0; q0 < nq; q0 += kQChunk) {
-    const int nqc = nq - q0 < kQChunk ? nq - q0 : kQChunk;
+  size_t split_at = 0;  // floats of q_split used by the passes so far
+  for (int q0 = 0; q0 < nq;) {
+    int pass = kQChunk;  // queries of this pass
+    if (umma) {
+      pass = sc_umma_nq_override();
+      if (pass == 0) pass = nq - q0 > 64 ? 128 : (nq - q0 > 32 ? 64 : 32);
+    }
+    const int nqc = nq - q0 < pass ? nq - q0 : pass;
     unsigned long long *lists = scratch + (size_t)q0 * stride * kScTopK;
     if (umma) {
-      float *q_hi = q_split + (size_t)q0 * n_cells, *q_lo = q_split + ((size_t)nq + q0) * n_cells;
-      cudaError_t e = launch_sc_scan_umma(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
-                                          ringkey_thres, max_id, sc_width, lists, stride, grid, q_hi, q_lo, stream);
+      float *q_tiles = q_split + split_at;
+      split_at += (size_t)2 * pass * ((n_cells + kUmK - 1) / kUmK) * kUmK;
+      const float *qs = q_sigs + (size_t)q0 * n_cells, *qk = q_keys + (size_t)q0 * key_dim;
+      cudaError_t e;
+      if (pass == 128)
+        e = launch_sc_scan_umma<128>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
+      else if (pass == 64)
+        e = launch_sc_scan_umma<64>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
+      else
+        e = launch_sc_scan_umma<32>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
       if (e != cudaSuccess) return e;
     } else if (tiles) {
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,
@@ -1206,6 +1278,7 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
       sc_scan_kernel<<<grid, kScanThreads, smem, stream>>>(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells,
                                                            q_keys + (size_t)q0 * key_dim, nqc, ringkey_thres, max_id, sc_width, lists, stride);
     }
+    q0 += nqc;
   }
   return cudaGetLastError();
 }

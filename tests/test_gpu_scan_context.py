@@ -380,14 +380,15 @@ def test_ringkey_width_not_multiple_of_four(session, oracle):
 def test_three_scan_kernels_agree_at_full_size(session, oracle):
     """100k descriptors (BASELINE config 4): the HBM-streaming kernel, the FFMA tile kernel and the tcgen05 tensor-core kernel
     (3xTF32 split products, TMEM accumulators) hand the same survivors to the exact re-score: identical argmin and distance bits,
-    with and without the ring-key gate / id limit, for a full chunk, a ragged batch and several chunks; spot-checked against the
-    oracle's brute force."""
+    with and without the ring-key gate / id limit, for a full chunk, a ragged batch and several chunks — the tensor-core kernel in
+    all three of its queries-per-pass variants (32: nq 11 / 32, 64: nq 50, 128: nq 70 and the first pass of 150) — spot-checked
+    against the oracle's brute force."""
     n = 100_000
     sig, key = syn.make_sc_database(n, 2024)
     db = api.ScanContextDB(session, n)
     db.add(key, sig)
     try:
-        for nq in (32, 11, 70):
+        for nq in (32, 11, 50, 70, 150):
             qs, qk, truth = syn.make_sc_queries(sig, key, nq, 70 + nq)
             out = {}
             for flavour in ("stream", "tile", "umma"):
