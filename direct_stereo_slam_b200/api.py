@@ -614,8 +614,8 @@ class ScanContextDB:
         return ms.value
 
     def set_scan_kernel(self, flavour):
-        """0 = auto, 1 = streaming kernel, 2 = TMA tile kernel (process-wide; dslam_sc_set_scan_kernel)."""
-        check(self.lib.dslam_sc_set_scan_kernel({"auto": 0, "stream": 1, "tile": 2, "umma": 3}.get(flavour, flavour)))
+        """auto / stream / tile / umma (tcgen05) / umma_masked (process-wide; dslam_sc_set_scan_kernel)."""
+        check(self.lib.dslam_sc_set_scan_kernel({"auto": 0, "stream": 1, "tile": 2, "umma": 3, "umma_masked": 4}.get(flavour, flavour)))
 
     def attach_comm(self, id128, world_size, rank):
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id128))

@@ -894,7 +894,7 @@ int dslam_sc_last_scan_ms(dslam_scdb *db, float *ms) {
 }
 
 int dslam_sc_set_scan_kernel(int flavour) {
-  if (flavour < 0 || flavour > 3) return fail(DSLAM_EINVAL, "scan kernel flavour must be 0 (auto), 1 (stream), 2 (tile) or 3 (tcgen05)");
+  if (flavour < 0 || flavour > 4) return fail(DSLAM_EINVAL, "scan kernel flavour must be 0 (auto), 1 (stream), 2 (tile), 3 (tcgen05) or 4 (tcgen05, masked hi operand)");
   sc_set_scan_flavour(flavour);
   return DSLAM_OK;
 }

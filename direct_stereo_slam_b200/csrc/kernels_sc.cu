@@ -481,8 +481,11 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM ("3xTF32"; the dropped lo*lo term is below 2^-22 relative).
 //   warp 0      : TMA producer — [128 rows x 32 cells] boxes of the DB (128-byte swizzle = the canonical K-major UMMA layout) and
 //                 the matching boxes of the pre-split query batch (hi and lo), kUmStages deep
-//   warps 1-4   : splitters — rewrite the landed DB box as hi in place and write lo next to it (elementwise: the swizzle does not
-//                 matter), then fence the generic-proxy writes towards the async proxy the tensor cores read through
+//   warps 1-4   : splitters — write lo = x - hi of the landed DB box next to it (elementwise: the swizzle does not matter), then fence
+//                 the generic-proxy writes towards the async proxy the tensor cores read through.  The box itself serves as the hi
+//                 operand as it is: a tf32 operand's low 13 mantissa bits are not read by the tensor cores (truncation), so
+//                 raw x and the masked hi are the same operand (flavour "umma_masked" stores the masked hi in place instead and
+//                 does not rely on that; tests/test_gpu_scan_context.py::test_tensor_core_split_is_exact pins the behaviour)
 //   warp 5      : one lane issues 8 x tcgen05.mma.kind::tf32 per stage (per 8 cells: a_hi x [b_hi ; b_lo] with N 64, a_lo x b_hi with N 32; M 128)
 //                 into one of two TMEM accumulators,
 //                 tcgen05.commit hands the stage back to the producer and, after the last stage of a tile, the tile to the epilogue
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(kUmThreads, 1)
     sc_scan_umma_kernel(const __grid_constant__ CUtensorMap map_db, const float *__restrict__ q_tiles /* sc_split_tf32_tiled_kernel's output */,
                         const float *__restrict__ keys, const int *__restrict__ ids, int n_rows, int n_cells, int key_dim,
                         const float *__restrict__ q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, int tiles_per_cta,
-                        u64 *__restrict__ scratch, int list_stride) {
+                        u64 *__restrict__ scratch, int list_stride, int raw_hi) {
   using C = UmCfg<NQ>;
   constexpr int kUmStages = C::kStages, kUmBBytes = C::kBBytes, kUmStageBytes = C::kStageBytes, kUmAccCols = C::kAccCols, kUmTmemCols = C::kTmemCols;
   extern __shared__ unsigned char smem_raw[];
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(kUmThreads, 1)
           const int i = j * 128 + st_tid;
           uint4 h;
           h.x = v[j].x & 0xffffe000u; h.y = v[j].y & 0xffffe000u; h.z = v[j].z & 0xffffe000u; h.w = v[j].w & 0xffffe000u;
-          A[i] = h;
+          if (!raw_hi) A[i] = h;
           Alo[i] = make_float4(__uint_as_float(v[j].x) - __uint_as_float(h.x), __uint_as_float(v[j].y) - __uint_as_float(h.y),
                                __uint_as_float(v[j].z) - __uint_as_float(h.z), __uint_as_float(v[j].w) - __uint_as_float(h.w));
         }
@@ -1131,7 +1134,7 @@ static ScEncodeTiledFn sc_encode_tiled() {
   return fn;
 }
 
-// 0 = choose by batch size, 1 = always the streaming kernel, 2 = always the tiled kernel (tests / sweeps)
+// 0 = choose by batch size, 1 = always the streaming kernel, 2 = always the tiled kernel, 3 / 4 = tensor-core kernel (tests / sweeps)
 static int g_sc_scan_flavour = -1;
 static int sc_scan_flavour() {
   if (g_sc_scan_flavour < 0) {
@@ -1140,6 +1143,7 @@ static int sc_scan_flavour() {
     if (e && !strcmp(e, "stream")) g_sc_scan_flavour = 1;
     if (e && !strcmp(e, "tile")) g_sc_scan_flavour = 2;
     if (e && !strcmp(e, "umma")) g_sc_scan_flavour = 3;
+    if (e && !strcmp(e, "umma_masked")) g_sc_scan_flavour = 4;
   }
   return g_sc_scan_flavour;
 }
@@ -1182,7 +1186,7 @@ static cudaError_t launch_sc_scan_tiles(const float *sigs, const float *keys, co
 template <int NQ>
 static cudaError_t launch_sc_scan_umma(const float *sigs, const float *keys, const int *ids, int n_rows, int n_cells, int key_dim, const float *q_sigs,
                                        const float *q_keys, int nqc, float ringkey_thres, int max_id, float sc_width, unsigned long long *scratch,
-                                       int list_stride, int grid, float *q_tiles, cudaStream_t stream) {
+                                       int list_stride, int grid, float *q_tiles, int raw_hi, cudaStream_t stream) {
   ScEncodeTiledFn enc = sc_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(sc_scan_umma_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmCfg<NQ>::kSmemBytes);
@@ -1203,7 +1207,7 @@ static cudaError_t launch_sc_scan_umma(const float *sigs, const float *keys, con
   const int n_tiles = (n_rows + kUmRows - 1) / kUmRows;
   const int tiles_per_cta = (n_tiles + grid - 1) / grid;
   sc_scan_umma_kernel<NQ><<<grid, kUmThreads, UmCfg<NQ>::kSmemBytes, stream>>>(map_db, q_tiles, keys, ids, n_rows, n_cells, key_dim, q_keys, nqc,
-                                                                               ringkey_thres, max_id, sc_width, tiles_per_cta, scratch, list_stride);
+                                                                               ringkey_thres, max_id, sc_width, tiles_per_cta, scratch, list_stride, raw_hi);
   return cudaGetLastError();
 }
 
@@ -1232,8 +1236,9 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
   // tensor-core flavour (tcgen05, 3xTF32): query batches over shards of >= 4096 rows (DSLAM_SC_UMMA_MIN_ROWS).  Measured against the
   // FFMA tile kernel at Q = 32: 100k rows 0.128 vs 0.220 ms, 50k 0.077 vs 0.134, 25k 0.061 vs 0.076, 12.5k 0.042 vs 0.059, 6.25k 0.042 vs 0.054
   static const int umma_min_rows = [] { const char *e = getenv("DSLAM_SC_UMMA_MIN_ROWS"); const int v = e ? atoi(e) : 0; return v >= 128 ? v : 4096; }();
-  const bool umma = q_split != nullptr && n_rows >= umma_min_rows && (flavour == 3 || (flavour == 0 && nq_first > 8));
-  const bool tiles = !umma && n_rows >= 64 && (flavour == 2 || flavour == 3 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
+  const bool umma = q_split != nullptr && n_rows >= umma_min_rows && (flavour == 3 || flavour == 4 || (flavour == 0 && nq_first > 8));
+  const int raw_hi = flavour != 4;  // 4: the splitters store the masked hi operand explicitly
+  const bool tiles = !umma && n_rows >= 64 && (flavour == 2 || flavour == 3 || flavour == 4 || (flavour == 0 && nq_first > 8 && n_tiles * 2 >= num_sms()));
   int grid = num_sms();
   if (umma) {
     const int n_t = (n_rows + kUmRows - 1) / kUmRows;
@@ -1261,11 +1266,11 @@ cudaError_t launch_sc_scan(const float *sigs, const float *keys, const int *ids,
       const float *qs = q_sigs + (size_t)q0 * n_cells, *qk = q_keys + (size_t)q0 * key_dim;
       cudaError_t e;
       if (pass == 128)
-        e = launch_sc_scan_umma<128>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
+        e = launch_sc_scan_umma<128>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, raw_hi, stream);
       else if (pass == 64)
-        e = launch_sc_scan_umma<64>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
+        e = launch_sc_scan_umma<64>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, raw_hi, stream);
       else
-        e = launch_sc_scan_umma<32>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, stream);
+        e = launch_sc_scan_umma<32>(sigs, keys, ids, n_rows, n_cells, key_dim, qs, qk, nqc, ringkey_thres, max_id, sc_width, lists, stride, grid, q_tiles, raw_hi, stream);
       if (e != cudaSuccess) return e;
     } else if (tiles) {
       cudaError_t e = launch_sc_scan_tiles(sigs, keys, ids, n_rows, n_cells, key_dim, q_sigs + (size_t)q0 * n_cells, q_keys + (size_t)q0 * key_dim, nqc,

@@ -288,8 +288,9 @@ int dslam_sc_last_scan_ms(dslam_scdb *db, float *ms);
 /* Tuning / test knob (process-wide): which scan kernel dslam_sc_query uses.  0 = chosen per query batch (default: the
  * HBM-streaming kernel for batches of <= 8 queries or small shards; above that the tcgen05 tensor-core kernel (3xTF32, TMEM
  * accumulators) for shards of >= 2 x 128 rows per SM and the register-blocked TMA / FFMA2 tile kernel otherwise; the environment
- * variable DSLAM_SC_SCAN=stream|tile|umma sets the initial value), 1 = always streaming, 2 = always the FFMA tile kernel,
- * 3 = tcgen05 wherever the shard is large enough.  All produce the same top-K survivors up to fp32-level rounding of the
+ * variable DSLAM_SC_SCAN=stream|tile|umma|umma_masked sets the initial value), 1 = always streaming, 2 = always the FFMA tile
+ * kernel, 3 = tcgen05 wherever the shard is large enough, 4 = the same with the hi half of the 3xTF32 split stored explicitly
+ * (3 feeds the raw fp32 operand and relies on the tensor cores not reading the low 13 mantissa bits).  All produce the same top-K survivors up to fp32-level rounding of the
  * approximate distances; the final (index, distance) is re-scored exactly. */
 int dslam_sc_set_scan_kernel(int flavour);
 

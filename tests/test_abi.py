@@ -73,7 +73,7 @@ def test_library_is_in_tree_and_has_no_link_time_cuda_driver_dependency():
 def test_argument_validation_needs_no_device():
     """Bad arguments are rejected before anything touches CUDA (same error behaviour with and without a GPU)."""
     lib = _lib.load()
-    assert lib.dslam_sc_set_scan_kernel(4) == _lib.EINVAL and b"flavour" in lib.dslam_last_error()
+    assert lib.dslam_sc_set_scan_kernel(5) == _lib.EINVAL and b"flavour" in lib.dslam_last_error()
     assert lib.dslam_sc_set_scan_kernel(-1) == _lib.EINVAL
     for f in (1, 2, 0):  # process-wide knob, no device needed; leave it on "auto"
         assert lib.dslam_sc_set_scan_kernel(f) == 0

@@ -405,3 +405,33 @@ def test_three_scan_kernels_agree_at_full_size(session, oracle):
     finally:
         db.set_scan_kernel("auto")
         db.close()
+
+
+def test_tensor_core_split_is_exact(session, oracle):
+    """3xTF32 on values chosen against the split.  Nine decoy rows hold 1 + 2^-11 + 2^-12 in every cell, the true best row holds
+    1 + 2^-10 (a tf32 number), the query is all ones.  With an exact hi / lo split the decoys score 1200.88 and the best row
+    1201.17.  If the tensor cores ROUNDED the raw fp32 operand to tf32 instead of dropping its low 13 mantissa bits, the "umma"
+    flavour (which feeds the landed fp32 box as the hi operand) would see hi = 1 + 2^-10 for the decoys on top of their lo part:
+    all nine would outrank the best row, push it out of the 8 survivors and the exact re-score could not bring it back.  The
+    "umma_masked" flavour stores the masked hi explicitly and is the reference for the other."""
+    n, cells = 8192, 1200
+    sig, key = syn.make_sc_database(n, 99)
+    sig = np.ascontiguousarray(sig, np.float32)
+    assert sig.shape[1] == cells
+    sig[0:9, :] = np.float32(1 + 2.0 ** -11 + 2.0 ** -12)
+    sig[9, :] = np.float32(1 + 2.0 ** -10)
+    db = api.ScanContextDB(session, n)
+    db.add(key, sig)
+    qs = np.ascontiguousarray(sig[100:109] * np.float32(0.999), np.float32)
+    qs[0, :] = 1.0
+    try:
+        i_o, d_o = oracle.search_sc_dense(qs[0], sig)
+        assert i_o == 9
+        for flavour in ("umma_masked", "umma", "tile"):
+            db.set_scan_kernel(flavour)
+            idx, diff = db.query(qs)
+            assert idx[0] == 9 and diff[0] == np.float32(d_o), (flavour, idx[0], diff[0], d_o)
+            assert np.array_equal(idx[1:], np.arange(101, 109)), (flavour, idx)
+    finally:
+        db.set_scan_kernel("auto")
+        db.close()
