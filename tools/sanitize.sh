@@ -17,3 +17,5 @@ run memcheck_pe 300 $CS --tool memcheck python -m pytest -x -q -m gpu tests/test
 run racecheck_smoke 300 $CS --tool racecheck python -c "$SMOKE"
 run synccheck_smoke 240 $CS --tool synccheck python -c "$SMOKE"
 run initcheck_smoke 240 $CS --tool initcheck python -c "$SMOKE"
+run memcheck_umma 120 $CS --tool memcheck python tools/sc_umma_check.py 8192 150
+run racecheck_umma 120 $CS --tool racecheck python tools/sc_umma_check.py 8192 50
