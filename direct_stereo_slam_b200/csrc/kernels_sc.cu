@@ -479,26 +479,27 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // the top-K must still contain the exact winner, so a plain TF32 product (10-bit mantissas) is not good enough: every fp32
 // operand is split into hi (the 11 significant bits TF32 keeps, exactly) + lo (the remainder, exact in fp32) and the product is
 // formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM ("3xTF32"; the dropped lo*lo term is below 2^-22 relative).
-//   warp 0      : TMA producer — [128 rows x 32 cells] boxes of the DB (128-byte swizzle = the canonical K-major UMMA layout) and
-//                 the matching boxes of the pre-split query batch (hi and lo), kUmStages deep
+//   warp 0      : producer — TMA [128 rows x 32 cells] boxes of the DB (128-byte swizzle = the canonical K-major UMMA layout) and one
+//                 bulk copy of the matching pre-split, pre-swizzled [b_hi ; b_lo] tile of the query batch, UmCfg::kStages deep
 //   warps 1-4   : splitters — write lo = x - hi of the landed DB box next to it (elementwise: the swizzle does not matter), then fence
 //                 the generic-proxy writes towards the async proxy the tensor cores read through.  The box itself serves as the hi
 //                 operand as it is: a tf32 operand's low 13 mantissa bits are not read by the tensor cores (truncation), so
 //                 raw x and the masked hi are the same operand (flavour "umma_masked" stores the masked hi in place instead and
 //                 does not rely on that; tests/test_gpu_scan_context.py::test_tensor_core_split_is_exact pins the behaviour)
-//   warp 5      : one lane issues 8 x tcgen05.mma.kind::tf32 per stage (per 8 cells: a_hi x [b_hi ; b_lo] with N 64, a_lo x b_hi with N 32; M 128)
+//   warp 5      : one lane issues 8 x tcgen05.mma.kind::tf32 per stage (per 8 cells: a_hi x [b_hi ; b_lo] with N = 2 NQ, a_lo x b_hi with N = NQ; M 128)
 //                 into one of two TMEM accumulators,
 //                 tcgen05.commit hands the stage back to the producer and, after the last stage of a tile, the tile to the epilogue
-//   warps 6-9   : epilogue — tcgen05.ld the accumulator (thread = row, 32 columns = queries), distances -> shared [row][query],
-//                 then thread (query, row group) feeds its running top-K: same packed keys, same merge, same exact re-score.
-// The DB streams through shared memory exactly once; HBM is the bound (4,800 B per row per 32 queries).
+//   warps 6-9   : epilogue — tcgen05.ld the accumulator in chunks of 32 queries (thread = row, 32 columns = queries), distances -> shared
+//                 [row][query], then thread (query, row group) feeds its running top-K of that chunk: same packed keys, same merge,
+//                 same exact re-score.
+// The DB streams through shared memory exactly once per pass (4,800 B per row per NQ queries).  Measured bound: the instruction rate of
+// the K = 8 tf32 MMA on a 128-byte-swizzled operand (~140 clocks per MMA, N <= 128), not HBM — profiles/r02_sc_umma_kernel.md.
 constexpr int kUmRows = 128;                 // UMMA M: DB rows per tile
 constexpr int kUmK = 32;                     // cells per stage = one 128-byte swizzle atom row
 constexpr int kUmABytes = kUmRows * kUmK * 4;              // 16 KB
 constexpr int kUmThreads = 320;
 // Queries per pass NQ = UMMA N of the lo*hi product (the [hi*hi | hi*lo] product runs at N = 2 NQ <= 256).  A pass streams the DB
-// once, so a larger NQ divides the HBM traffic per query: 32 (5 stages of 40 KB), 64 (4 x 48 KB) or 128 (3 x 64 KB; the pass is then
-// bound by the tensor pipe and by the query tiles re-read from L2 for every DB tile, not by HBM).
+// once, so a larger NQ divides the HBM traffic and the MMA count per query: 32 (5 stages of 40 KB), 64 (4 x 48 KB) or 128 (3 x 64 KB).
 template <int NQ>
 struct UmCfg {
   static_assert(NQ == 32 || NQ == 64 || NQ == 128, "queries per pass");
