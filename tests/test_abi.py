@@ -75,7 +75,7 @@ def test_argument_validation_needs_no_device():
     lib = _lib.load()
     assert lib.dslam_sc_set_scan_kernel(5) == _lib.EINVAL and b"flavour" in lib.dslam_last_error()
     assert lib.dslam_sc_set_scan_kernel(-1) == _lib.EINVAL
-    for f in (1, 2, 0):  # process-wide knob, no device needed; leave it on "auto"
+    for f in (1, 2, 3, 4, 0):  # process-wide knob, no device needed; leave it on "auto"
         assert lib.dslam_sc_set_scan_kernel(f) == 0
     assert lib.dslam_frame_upload_batch(0, None, None) == _lib.EINVAL
     assert lib.dslam_frame_upload_batch(2, None, None) == _lib.EINVAL
