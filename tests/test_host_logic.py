@@ -165,3 +165,38 @@ def test_bench_reference_arm_contract():
     r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_three_pass_tf32_split_keeps_the_winner_among_the_survivors():
+    """The tensor-core Scan-Context scan ranks candidates with hi*hi + hi*lo + lo*hi on tf32 operands (the tensor cores read the top
+    19 bits of an fp32 word) and fp32 accumulation; the exact re-score then sees the 8 best.  Emulated here in numpy on the synthetic
+    database: the approximate sector products stay within 2^-19 of sum|a*b| of the exact ones, and that bound is at least 30x
+    smaller than the distance between the best and the 9th-best candidate of every query — the margin that keeps the exact winner
+    inside the survivors (the GPU side is test_three_scan_kernels_agree_at_full_size / test_tensor_core_split_is_exact)."""
+    from direct_stereo_slam_b200 import synthetic as syn
+
+    def tf32(x):  # what the tensor cores read of an fp32 operand: low 13 mantissa bits dropped
+        return (np.ascontiguousarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    n, nq = 3000, 24
+    sig, key = syn.make_sc_database(n, 5)
+    qs, _, truth = syn.make_sc_queries(sig, key, nq, 6)
+    a_hi, b_hi = tf32(sig), tf32(qs)
+    a_lo, b_lo = tf32(sig - a_hi), tf32(qs - b_hi)  # the lo halves are exact in fp32; the MMA truncates them too
+    approx = (a_hi.astype(np.float64) @ b_hi.T.astype(np.float64) + a_hi.astype(np.float64) @ b_lo.T.astype(np.float64)
+              + a_lo.astype(np.float64) @ b_hi.T.astype(np.float64))
+    exact = sig.astype(np.float64) @ qs.T.astype(np.float64)
+    scale = np.abs(sig).astype(np.float64) @ np.abs(qs).T.astype(np.float64)
+    split_err = np.abs(approx - exact)
+    assert np.all(split_err <= 2.0 ** -19 * scale + 1e-300)
+    # fp32 accumulation of 1200 terms adds at most 1200 * 2^-24 * sum|a*b| (any order)
+    bound = (2.0 ** -19 + 1200 * 2.0 ** -24) * scale
+    # plain tf32 (hi*hi only) would NOT be good enough by the same yardstick
+    plain_err = np.abs(a_hi.astype(np.float64) @ b_hi.T.astype(np.float64) - exact)
+    order = np.sort(-exact, axis=0)  # per query: descending products = ascending distances
+    gap = (-order[0]) - (-order[8])  # best minus 9th best product
+    worst_bound = bound.max(axis=0)
+    assert np.all(gap > 30 * worst_bound), float((gap / worst_bound).min())
+    assert plain_err.max() > 50 * split_err.max()
+    known = truth >= 0
+    assert np.array_equal(np.argmax(approx, axis=0)[known], truth[known])
